@@ -1,0 +1,157 @@
+/*
+ * pybmf_b200.h -- C ABI of the B200-native Asso hot path (libbmf_b200.so).
+ *
+ * The reference (PreferredAI/PyBMF) is pure Python and has no FFI: its "operator
+ * API" for this path is a handful of Python functions.  Each entry
+ * point below names the reference function (file:line under /root/reference) whose
+ * arithmetic it replaces.  INTEGRATION.md shows the ctypes stub a PyBMF maintainer
+ * would add at each of those call sites.
+ *
+ * Conventions
+ *  - plain C types only; every pointer is a DEVICE pointer owned by the caller
+ *    unless the parameter name ends in `_host`;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and the
+ *    call returns without synchronising;
+ *  - return value: 0 ok, <0 invalid argument (BMF_E_*), >0 a cudaError_t;
+ *    bmf_last_error() gives a thread-local message for the last non-zero return;
+ *  - bit matrices are row-major arrays of uint64 words, bit c of a row lives in
+ *    word c>>6 at position c&63; rows are `words` uint64 apart, `words` is EVEN
+ *    (rows are 16-byte aligned so kernels can use 128-bit loads) and pad bits are 0;
+ *  - int8 operand planes are row-major with leading dimension `ld` (bytes), a
+ *    multiple of 128, rows padded to the tile multiple given per function, pad = 0.
+ */
+#ifndef PYBMF_B200_H
+#define PYBMF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BMF_ABI_VERSION 1
+
+#define BMF_E_ARG (-1)      /* bad shape / null pointer / misaligned leading dimension   */
+#define BMF_E_NOGPU (-2)    /* no sm_100 device visible                                   */
+#define BMF_E_DRIVER (-3)   /* cuTensorMapEncodeTiled unavailable / failed                */
+
+/* tile multiples the int8 tensor-core kernels expect (callers pad to these) */
+#define BMF_I8_CAND_TILE 128  /* rows of the "candidate" operand (MMA M)                  */
+#define BMF_I8_ROW_TILE 256   /* rows of the "data row" operand (MMA N)                   */
+#define BMF_I8_K_TILE 128     /* bytes of K per pipeline stage (= one 128B swizzle row)   */
+
+typedef void* bmf_stream_t;
+
+int bmf_abi_version(void);
+const char* bmf_last_error(void);
+/* sm count and compute capability of the current device */
+int bmf_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- input packing ------------------------------------------------------------------
+ * Replaces the csr containers of BaseModel.load_dataset (PyBMF/models/BaseModel.py:146).
+ * Non-zero pattern of a CSR matrix -> bit rows.  transposed=1 writes X^T (n rows of
+ * ceil(m/64) words).  `bits` must be zero-filled by the caller (bmf_fill_zero). */
+int bmf_pack_csr(const int64_t* indptr, const int32_t* indices, int64_t m, int64_t n,
+                 int transposed, uint64_t* bits, int64_t words, bmf_stream_t stream);
+int bmf_fill_zero(void* ptr, int64_t bytes, bmf_stream_t stream);
+/* bits[rows][words] -> int8 plane[rows_pad][ld]: value `one` where the bit is set,
+ * `zero` where it is clear and the column < ncols, 0 in all padding. */
+int bmf_expand_bits_i8(const uint64_t* bits, int64_t rows, int64_t ncols, int64_t words,
+                       int8_t one, int8_t zero, int8_t* plane, int64_t rows_pad, int64_t ld,
+                       bmf_stream_t stream);
+
+/* ---- association matrix: build_assoc, PyBMF/models/Asso.py:191-213 -------------------
+ * cnt[i][j] = |col_i AND col_j| = (X^T X)[i][j], int32, leading dimension ldc.
+ * popc variant: XT bits [n][words_m].  i8 variant (tcgen05 kind::i8, TMA, TMEM):
+ * XT plane int8 [n_pad(256)][ld] of 0/1 with K = rows of X along ld. */
+int bmf_assoc_counts_popc(const uint64_t* xt_bits, int64_t n, int64_t words_m, int32_t* cnt,
+                          int64_t ldc, bmf_stream_t stream);
+/* the primitive under both int8 paths, exported for parity tests:
+ * c[i][j] = sum_k a[i][k]*b[j][k], a rows multiple of 128, b rows multiple of 256, int32 out */
+int bmf_gemm_i8_nt(const int8_t* a_plane, int64_t a_rows_pad, const int8_t* b_plane, int64_t b_rows_pad,
+                   int64_t ld, int32_t* c, int64_t ldc, bmf_stream_t stream);
+int bmf_assoc_counts_i8(const int8_t* xt_plane, int64_t n, int64_t n_pad, int64_t ld, int32_t* cnt,
+                        int64_t ldc, bmf_stream_t stream);
+/* build_basis, Asso.py:216-235 + binarize, PyBMF/utils/common.py:75: bit (i,j) =
+ * ((double)cnt[i][j] / (double)cnt[i][i] > tau) when cnt[i][i] > 0, else 0 (IEEE
+ * division, strict >).  alive[i] = row i has any bit set (the reference drops all-zero
+ * rows but keeps order, so candidate rank = rank among alive rows).  cand_plane
+ * (nullable) receives the same rows as int8 0/1, [n_pad(128)][ld]. */
+int bmf_basis_threshold(const int32_t* cnt, int64_t ldc, int64_t n, double tau, uint64_t* basis_bits,
+                        int64_t words, int8_t* cand_plane, int64_t ld, uint8_t* alive,
+                        bmf_stream_t stream);
+
+/* ---- greedy cover-gain scoring: the hot loop Asso.py:83-95 -> get_vector Asso.py:144-188,
+ *      coverage_score PyBMF/utils/metrics.py:189-201 ------------------------------------
+ * For every candidate row b_j and data row i:
+ *   P = |x_i & ~c_i & b_j|, N = |~x_i & ~c_i & b_j|,
+ *   use(i,j) = (s_new > s_old) with s = (-w_fp)*FP + w_fn*TP evaluated in fp64, no FMA.
+ * Integer mode (wa, wb > 0 given, w_fp = wa/2^s, w_fn = wb/2^s): use <=> wb*P - wa*N > 0,
+ *   gain_p[j] = sum_i relu(wb*P - wa*N), gain_n untouched.
+ * General mode (wa = wb = 0): gain_p[j] = sum_{use} P, gain_n[j] = sum_{use} N, with
+ *   tp_old/fp_old the per-row counts of the current cover.
+ * Outputs are overwritten (not accumulated). */
+int bmf_cover_score_popc(const uint64_t* x_bits, const uint64_t* c_bits, int64_t m, int64_t n,
+                         int64_t words, const uint64_t* basis_bits, const uint8_t* alive,
+                         const int32_t* tp_old, const int32_t* fp_old, int32_t wa, int32_t wb,
+                         double w_fp, double w_fn, int64_t* gain_p, int64_t* gain_n,
+                         bmf_stream_t stream);
+/* tcgen05 kind::i8 variant, integer mode only: rows_plane[i][k] = (~c & x) ? wb : (~c & ~x) ? -wa : 0,
+ * cand_plane = 0/1 basis rows; gain[j] = sum_i relu(sum_k cand[j][k]*rows[i][k]).
+ * gain has cand_pad entries. */
+int bmf_cover_score_i8(const int8_t* cand_plane, int64_t cand_pad, const int8_t* rows_plane,
+                       int64_t rows_pad, int64_t ld, int64_t* gain, bmf_stream_t stream);
+
+/* argmax of Asso.py:94: first j (lowest index) among alive candidates whose score is
+ * strictly greater than `best_score` and than every earlier score.
+ * integer mode: score_j = (double)(base_int + gain_p[j]) * scale
+ * general mode: score_j = (-w_fp)*(double)(fp_tot + gain_n[j]) + w_fn*(double)(tp_tot + gain_p[j])
+ * record[0] = winner index or -1, record[1] = bit pattern of the winning score (double). */
+int bmf_select_first_max(const int64_t* gain_p, const int64_t* gain_n, const uint8_t* alive, int64_t n,
+                         int32_t wa, int32_t wb, int64_t base_int, double scale, double w_fp,
+                         double w_fn, int64_t tp_tot, int64_t fp_tot, double best_score,
+                         int64_t* record, bmf_stream_t stream);
+
+/* set_factors + cover update for the chosen candidate (Asso.py:103-110): recompute
+ * use(i) for basis row *winner (device int64; <0 = no-op), write u_bits (bit i of a
+ * ceil(m/64)-word vector, caller-zeroed), OR the row into c_bits where used, add P/N to
+ * tp_old/fp_old, zero the used rows' entries of rows_plane (nullable) on the row's
+ * support, clear alive[winner].  totals[0..2] += (#used rows, sum P, sum N). */
+int bmf_cover_apply(const uint64_t* x_bits, uint64_t* c_bits, int64_t m, int64_t n, int64_t words,
+                    const uint64_t* basis_bits, uint8_t* alive, const int64_t* winner, int32_t* tp_old,
+                    int32_t* fp_old, int32_t wa, int32_t wb, double w_fp, double w_fn,
+                    int8_t* rows_plane, int64_t ld, uint64_t* u_bits, int64_t* totals,
+                    bmf_stream_t stream);
+
+/* ---- Boolean product and confusion counts ------------------------------------------------
+ * get_prediction / matmul(boolean=True): PyBMF/utils/common.py:98-107, boolean_utils.py:61-84.
+ * u_words[m][kw]: bit l of row i = U[i][l]; vt_bits[k][words] = rows of V^T.
+ * pd_bits[i] = OR_{l in U_i} vt_bits[l]. */
+int bmf_bool_product(const uint64_t* u_words, int64_t m, int64_t kw, const uint64_t* vt_bits,
+                     int64_t k, int64_t words, uint64_t* pd_bits, bmf_stream_t stream);
+/* TP/FP/FN of PyBMF/utils/metrics.py:56-76 against the product computed on the fly
+ * (never materialised).  counts[0..2] += (TP, FP, FN); row_tp/row_fp nullable int32[m]. */
+int bmf_confusion_factors(const uint64_t* gt_bits, int64_t m, int64_t words, const uint64_t* u_words,
+                          int64_t kw, const uint64_t* vt_bits, int64_t k, int64_t* counts,
+                          int32_t* row_tp, int32_t* row_fp, bmf_stream_t stream);
+/* same against a materialised prediction */
+int bmf_confusion_bits(const uint64_t* gt_bits, const uint64_t* pd_bits, int64_t m, int64_t words,
+                       int64_t* counts, int32_t* row_tp, int32_t* row_fp, bmf_stream_t stream);
+/* eval(task='prediction'), PyBMF/utils/evaluate_utils.py:32-44: counts over stored triplets
+ * (i, j, gt != 0); counts[0..3] += (TP, FP, FN, TN). */
+int bmf_confusion_triplets(const int32_t* rows, const int32_t* cols, const uint8_t* gt, int64_t nnz,
+                           const uint64_t* u_words, int64_t kw, const uint64_t* v_words,
+                           int64_t* counts, bmf_stream_t stream);
+
+/* ---- AssoIter.get_refined_column, PyBMF/models/AssoIter.py:80-100 -------------------------
+ * One streaming pass over the rows: cover without factor `col`, get_vector with basis
+ * V[:, col], overwrite bit `col` of u_words (AssoIter.py:60), and accumulate
+ * out[0..4] += (TP, FP of the new cover, #used rows, sum_{use} P, sum_{use} N). */
+int bmf_refine_column(const uint64_t* x_bits, int64_t m, int64_t n, int64_t words, uint64_t* u_words,
+                      int64_t kw, const uint64_t* vt_bits, int64_t k, int64_t col, int32_t wa,
+                      int32_t wb, double w_fp, double w_fn, int64_t* out, bmf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYBMF_B200_H */

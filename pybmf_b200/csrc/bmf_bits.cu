@@ -1,0 +1,683 @@
+// Bit-packed kernels of the Asso hot path (sm_100a): packing, popcount contractions,
+// covered-mask update, Boolean product, confusion counts, AssoIter column refinement.
+// All of these are streaming integer kernels bound by HBM bandwidth or by the integer
+// pipe (POPC); rows are 16-byte aligned so every row stream uses 128-bit loads.
+#include "bmf_common.cuh"
+
+namespace bmf {
+
+// =========================================================================================
+// packing
+// =========================================================================================
+__global__ void pack_csr_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                int64_t m, int transposed, unsigned long long* __restrict__ bits,
+                                int64_t words) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = warp0; r < m; r += nwarps) {
+    const int64_t beg = indptr[r], end = indptr[r + 1];
+    for (int64_t e = beg + lane; e < end; e += 32) {
+      const int64_t c = indices[e];
+      if (!transposed)
+        atomicOr(bits + r * words + (c >> 6), 1ull << (c & 63));
+      else
+        atomicOr(bits + c * words + (r >> 6), 1ull << (r & 63));
+    }
+  }
+}
+
+// 16 bits -> 16 int8 per thread, one 128-bit store
+__global__ void expand_bits_i8_kernel(const uint64_t* __restrict__ bits, int64_t rows, int64_t ncols,
+                                      int64_t words, int one, int zero, int8_t* __restrict__ plane,
+                                      int64_t rows_pad, int64_t ld) {
+  const int64_t chunks = ld >> 4;
+  const int64_t total = rows_pad * chunks;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / chunks, ch = t - r * chunks;
+    const int64_t c0 = ch << 4;
+    uint32_t out[4] = {0, 0, 0, 0};
+    if (r < rows && c0 < ncols) {
+      const int64_t w = c0 >> 6;
+      const uint32_t b16 = (w < words) ? (uint32_t)((bits[r * words + w] >> (c0 & 63)) & 0xffffu) : 0u;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        int v = (c0 + i < ncols) ? (((b16 >> i) & 1u) ? one : zero) : 0;
+        out[i >> 2] |= (uint32_t)(uint8_t)(int8_t)v << ((i & 3) * 8);
+      }
+    }
+    *reinterpret_cast<uint4*>(plane + r * ld + c0) = make_uint4(out[0], out[1], out[2], out[3]);
+  }
+}
+
+// =========================================================================================
+// popcount contraction tiles.  Block = 256 threads computes a 64 x 64 tile of
+// (row i of A) x (row j of B); thread (ty, tx) owns rows ty*4+r and columns c*16+tx so that
+// shared-memory reads of B are conflict free and reads of A are broadcasts.
+// =========================================================================================
+constexpr int PT = 64;    // tile edge
+constexpr int PW = 16;    // words per shared-memory chunk
+constexpr int PWP = PW + 1;
+
+__device__ __forceinline__ void stage_words(uint64_t (*dst)[PWP], const uint64_t* __restrict__ src,
+                                            int64_t row0, int64_t nrows, int64_t words, int64_t w0) {
+  // 64 rows x 16 words, 256 threads: each thread moves 4 words
+  for (int e = threadIdx.x; e < PT * PW; e += blockDim.x) {
+    const int r = e / PW, w = e % PW;
+    const int64_t gr = row0 + r, gw = w0 + w;
+    dst[r][w] = (gr < nrows && gw < words) ? __ldg(src + gr * words + gw) : 0ull;
+  }
+}
+
+__global__ void __launch_bounds__(256) assoc_counts_popc_kernel(const uint64_t* __restrict__ xt, int64_t n,
+                                                               int64_t words, int32_t* __restrict__ cnt,
+                                                               int64_t ldc) {
+  __shared__ uint64_t As[PT][PWP];
+  __shared__ uint64_t Bs[PT][PWP];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t i0 = (int64_t)blockIdx.y * PT, j0 = (int64_t)blockIdx.x * PT;
+  int acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0;
+  for (int64_t w0 = 0; w0 < words; w0 += PW) {
+    stage_words(As, xt, i0, n, words, w0);
+    stage_words(Bs, xt, j0, n, words, w0);
+    __syncthreads();
+#pragma unroll 4
+    for (int w = 0; w < PW; ++w) {
+      uint64_t a[4], b[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] = As[ty * 4 + r][w];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) b[c] = Bs[c * 16 + tx][w];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] += __popcll(a[r] & b[c]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int64_t i = i0 + ty * 4 + r, j = j0 + c * 16 + tx;
+      if (i < n && j < n) cnt[i * ldc + j] = acc[r][c];
+    }
+}
+
+// basis bit (i, j) = cnt[i][j] / cnt[i][i] > tau, one warp per row, one 64-bit word per lane pass
+__global__ void basis_threshold_kernel(const int32_t* __restrict__ cnt, int64_t ldc, int64_t n, double tau,
+                                       uint64_t* __restrict__ basis_bits, int64_t words,
+                                       int8_t* __restrict__ cand_plane, int64_t ld,
+                                       uint8_t* __restrict__ alive) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t i = warp0; i < n; i += nwarps) {
+    const int32_t si = cnt[i * ldc + i];
+    const double s = (double)si;
+    int any = 0;
+    for (int64_t w = 0; w < words; ++w) {       // each pass: 2 x 32 columns -> one word
+      uint64_t word = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int64_t j = w * 64 + h * 32 + lane;
+        bool bit = false;
+        if (j < n && si > 0) bit = ((double)cnt[i * ldc + j] / s) > tau;   // IEEE division, strict >
+        if (cand_plane != nullptr && j < ld) cand_plane[i * ld + j] = bit ? 1 : 0;
+        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+        word |= (uint64_t)bal << (h * 32);
+      }
+      if (lane == 0) basis_bits[i * words + w] = word;
+      any |= (word != 0);
+    }
+    if (cand_plane != nullptr)                     // tail of the padded row beyond words*64
+      for (int64_t j = words * 64 + lane; j < ld; j += 32) cand_plane[i * ld + j] = 0;
+    if (lane == 0) alive[i] = any ? 1 : 0;
+  }
+}
+
+// =========================================================================================
+// cover-gain scoring, popcount variant.
+// grid.x = candidate tiles (64), grid.y = row splits; every block walks its share of row
+// tiles and keeps per-candidate partial gains in registers; one atomic per candidate at the end.
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+cover_score_popc_kernel(const uint64_t* __restrict__ xb, const uint64_t* __restrict__ cb, int64_t m,
+                        int64_t n, int64_t words, const uint64_t* __restrict__ basis,
+                        const uint8_t* __restrict__ alive, const int32_t* __restrict__ tp_old,
+                        const int32_t* __restrict__ fp_old, int wa, int wb, double neg_w_fp, double w_fn,
+                        unsigned long long* __restrict__ gain_p, unsigned long long* __restrict__ gain_n) {
+  __shared__ uint64_t Ps[PT][PWP];   // x & ~c        (uncovered ones)
+  __shared__ uint64_t Ns[PT][PWP];   // ~x & ~c & valid (uncovered zeros)
+  __shared__ uint64_t Bs[PT][PWP];
+  __shared__ long long red_p[PT];
+  __shared__ long long red_n[PT];
+  __shared__ int any_alive;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t j0 = (int64_t)blockIdx.x * PT;
+  if (threadIdx.x == 0) any_alive = 0;
+  if (threadIdx.x < PT) { red_p[threadIdx.x] = 0; red_n[threadIdx.x] = 0; }
+  __syncthreads();
+  if (threadIdx.x < PT && j0 + threadIdx.x < n && alive[j0 + threadIdx.x]) any_alive = 1;
+  __syncthreads();
+  if (!any_alive) return;
+
+  long long gp[4] = {0, 0, 0, 0}, gn[4] = {0, 0, 0, 0};
+  const int64_t row_tiles = (m + PT - 1) / PT;
+  for (int64_t rt = blockIdx.y; rt < row_tiles; rt += gridDim.y) {
+    const int64_t i0 = rt * PT;
+    int accp[4][4], accn[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { accp[r][c] = 0; accn[r][c] = 0; }
+    for (int64_t w0 = 0; w0 < words; w0 += PW) {
+      for (int e = threadIdx.x; e < PT * PW; e += blockDim.x) {
+        const int r = e / PW, w = e % PW;
+        const int64_t gr = i0 + r, gw = w0 + w;
+        uint64_t p = 0, q = 0;
+        if (gr < m && gw < words) {
+          const uint64_t x = __ldg(xb + gr * words + gw), c = __ldg(cb + gr * words + gw);
+          const int64_t rem = n - gw * 64;                      // valid columns in this word
+          const uint64_t valid = rem >= 64 ? ~0ull : (rem <= 0 ? 0ull : ((1ull << rem) - 1ull));
+          p = x & ~c;
+          q = ~x & ~c & valid;
+        }
+        Ps[r][w] = p;
+        Ns[r][w] = q;
+      }
+      stage_words(Bs, basis, j0, n, words, w0);
+      __syncthreads();
+#pragma unroll 2
+      for (int w = 0; w < PW; ++w) {
+        uint64_t p[4], q[4], b[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { p[r] = Ps[ty * 4 + r][w]; q[r] = Ns[ty * 4 + r][w]; }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) b[c] = Bs[c * 16 + tx][w];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            accp[r][c] += __popcll(p[r] & b[c]);
+            accn[r][c] += __popcll(q[r] & b[c]);
+          }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t i = i0 + ty * 4 + r;
+      if (i >= m) continue;
+      int tpo = 0, fpo = 0;
+      if (!(wa | wb)) { tpo = tp_old[i]; fpo = fp_old[i]; }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int P = accp[r][c], N = accn[r][c];
+        if (wa | wb) {
+          const int d = wb * P - wa * N;
+          gp[c] += d > 0 ? d : 0;
+        } else if (row_uses(0, 0, neg_w_fp, w_fn, tpo, fpo, P, N)) {
+          gp[c] += P;
+          gn[c] += N;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    atomicAdd((unsigned long long*)&red_p[c * 16 + tx], (unsigned long long)gp[c]);
+    if (!(wa | wb)) atomicAdd((unsigned long long*)&red_n[c * 16 + tx], (unsigned long long)gn[c]);
+  }
+  __syncthreads();
+  if (threadIdx.x < PT && j0 + threadIdx.x < n) {
+    atomicAdd(gain_p + j0 + threadIdx.x, (unsigned long long)red_p[threadIdx.x]);
+    if (!(wa | wb)) atomicAdd(gain_n + j0 + threadIdx.x, (unsigned long long)red_n[threadIdx.x]);
+  }
+}
+
+// =========================================================================================
+// argmax with the reference's tie-breaking (first strict maximum above the inherited best)
+// =========================================================================================
+__global__ void __launch_bounds__(1024)
+select_first_max_kernel(const int64_t* __restrict__ gain_p, const int64_t* __restrict__ gain_n,
+                        const uint8_t* __restrict__ alive, int64_t n, int wa, int wb, int64_t base_int,
+                        double scale, double neg_w_fp, double w_fn, int64_t tp_tot, int64_t fp_tot,
+                        double best_score, int64_t* __restrict__ record) {
+  __shared__ double s_val[32];
+  __shared__ long long s_idx[32];
+  double best = 0.0;
+  long long idx = -1;
+  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+    if (!alive[j]) continue;
+    double sc;
+    if (wa | wb)
+      sc = __dmul_rn((double)(base_int + gain_p[j]), scale);
+    else
+      sc = __dadd_rn(__dmul_rn(neg_w_fp, (double)(fp_tot + gain_n[j])),
+                     __dmul_rn(w_fn, (double)(tp_tot + gain_p[j])));
+    if (idx < 0 || sc > best) { best = sc; idx = j; }   // ascending j per thread: first max kept
+  }
+  // warp then block reduction; on equal scores the lower index wins
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (oi >= 0 && (idx < 0 || ov > best || (ov == best && oi < idx))) { best = ov; idx = oi; }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_val[warp] = best; s_idx[warp] = idx; }
+  __syncthreads();
+  if (warp == 0) {
+    best = s_val[lane];
+    idx = s_idx[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (oi >= 0 && (idx < 0 || ov > best || (ov == best && oi < idx))) { best = ov; idx = oi; }
+    }
+    if (lane == 0) {
+      if (idx >= 0 && !(best > best_score)) idx = -1;       // Asso.py:94 `score > best_score`
+      record[0] = idx;
+      record[1] = __double_as_longlong(idx >= 0 ? best : best_score);
+    }
+  }
+}
+
+// =========================================================================================
+// apply the chosen candidate: one warp per data row, 128-bit row streams
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+cover_apply_kernel(const uint64_t* __restrict__ xb, uint64_t* __restrict__ cb, int64_t m, int64_t n,
+                   int64_t words, const uint64_t* __restrict__ basis, uint8_t* __restrict__ alive,
+                   const int64_t* __restrict__ winner, int32_t* __restrict__ tp_old,
+                   int32_t* __restrict__ fp_old, int wa, int wb, double neg_w_fp, double w_fn,
+                   int8_t* __restrict__ rows_plane, int64_t ld, unsigned long long* __restrict__ u_bits,
+                   unsigned long long* __restrict__ totals) {
+  const int64_t j = *winner;
+  if (j < 0) return;
+  const uint64_t* __restrict__ b = basis + j * words;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t pairs = words >> 1;
+  long long t_used = 0, t_p = 0, t_n = 0;
+  for (int64_t i = warp0; i < m; i += nwarps) {
+    int P = 0, N = 0;
+    for (int64_t p = lane; p < pairs; p += 32) {
+      const ulonglong2 x = ld_words2(xb + i * words + 2 * p);
+      const ulonglong2 c = *reinterpret_cast<const ulonglong2*>(cb + i * words + 2 * p);
+      const ulonglong2 v = ld_words2(b + 2 * p);
+      P += __popcll(x.x & ~c.x & v.x) + __popcll(x.y & ~c.y & v.y);
+      N += __popcll(~x.x & ~c.x & v.x) + __popcll(~x.y & ~c.y & v.y);   // v has zero pad bits
+    }
+    P = warp_sum(P);
+    N = warp_sum(N);
+    const int tpo = tp_old[i], fpo = fp_old[i];
+    if (!row_uses(wa, wb, neg_w_fp, w_fn, tpo, fpo, P, N)) continue;    // warp-uniform
+    for (int64_t p = lane; p < pairs; p += 32) {
+      ulonglong2* cp = reinterpret_cast<ulonglong2*>(cb + i * words + 2 * p);
+      ulonglong2 c = *cp;
+      const ulonglong2 v = ld_words2(b + 2 * p);
+      if (rows_plane != nullptr) {
+        uint64_t s0 = v.x & ~c.x, s1 = v.y & ~c.y;                      // newly covered columns
+        int8_t* rowp = rows_plane + i * ld + p * 128;
+        while (s0) { const int k = __ffsll((long long)s0) - 1; s0 &= s0 - 1; rowp[k] = 0; }
+        while (s1) { const int k = __ffsll((long long)s1) - 1; s1 &= s1 - 1; rowp[64 + k] = 0; }
+      }
+      c.x |= v.x;
+      c.y |= v.y;
+      *cp = c;
+    }
+    if (lane == 0) {
+      tp_old[i] = tpo + P;
+      fp_old[i] = fpo + N;
+      atomicOr(u_bits + (i >> 6), 1ull << (i & 63));
+      t_used += 1; t_p += P; t_n += N;
+    }
+  }
+  if (lane == 0 && t_used) {
+    atomicAdd(totals + 0, (unsigned long long)t_used);
+    atomicAdd(totals + 1, (unsigned long long)t_p);
+    atomicAdd(totals + 2, (unsigned long long)t_n);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) alive[j] = 0;               // Asso.py:106-107
+}
+
+// =========================================================================================
+// Boolean product and confusion counts.  One warp per row; a row's prediction is the OR of
+// the V^T rows selected by the set bits of its k-bit usage word(s).
+// =========================================================================================
+__device__ __forceinline__ ulonglong2 product_pair(const uint64_t* __restrict__ uw, int64_t kw,
+                                                   const uint64_t* __restrict__ vt, int64_t words,
+                                                   int64_t p, int64_t skip) {
+  ulonglong2 acc = make_ulonglong2(0ull, 0ull);
+  for (int64_t q = 0; q < kw; ++q) {
+    uint64_t sel = uw[q];
+    if (skip >= 0 && (skip >> 6) == q) sel &= ~(1ull << (skip & 63));
+    while (sel) {
+      const int l = __ffsll((long long)sel) - 1;
+      sel &= sel - 1;
+      const ulonglong2 v = ld_words2(vt + (q * 64 + l) * words + 2 * p);
+      acc.x |= v.x;
+      acc.y |= v.y;
+    }
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(256)
+bool_product_kernel(const uint64_t* __restrict__ u_words, int64_t m, int64_t kw,
+                    const uint64_t* __restrict__ vt, int64_t words, uint64_t* __restrict__ pd) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t pairs = words >> 1;
+  for (int64_t i = warp0; i < m; i += nwarps) {
+    const uint64_t* uw = u_words + i * kw;
+    for (int64_t p = lane; p < pairs; p += 32) {
+      const ulonglong2 acc = product_pair(uw, kw, vt, words, p, -1);
+      *reinterpret_cast<ulonglong2*>(pd + i * words + 2 * p) = acc;    // 128-bit coalesced store
+    }
+  }
+}
+
+template <bool FROM_FACTORS>
+__global__ void __launch_bounds__(256)
+confusion_kernel(const uint64_t* __restrict__ gt, const uint64_t* __restrict__ pd_bits, int64_t m,
+                 int64_t words, const uint64_t* __restrict__ u_words, int64_t kw,
+                 const uint64_t* __restrict__ vt, unsigned long long* __restrict__ counts,
+                 int32_t* __restrict__ row_tp, int32_t* __restrict__ row_fp) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t pairs = words >> 1;
+  long long t_tp = 0, t_fp = 0, t_fn = 0;
+  for (int64_t i = warp0; i < m; i += nwarps) {
+    int tp = 0, fp = 0, fn = 0;
+    for (int64_t p = lane; p < pairs; p += 32) {
+      const ulonglong2 g = ld_words2(gt + i * words + 2 * p);
+      ulonglong2 d;
+      if (FROM_FACTORS) d = product_pair(u_words + i * kw, kw, vt, words, p, -1);
+      else d = ld_words2(pd_bits + i * words + 2 * p);
+      tp += __popcll(g.x & d.x) + __popcll(g.y & d.y);
+      fp += __popcll(~g.x & d.x) + __popcll(~g.y & d.y);
+      fn += __popcll(g.x & ~d.x) + __popcll(g.y & ~d.y);
+    }
+    tp = warp_sum(tp); fp = warp_sum(fp); fn = warp_sum(fn);
+    if (lane == 0) {
+      if (row_tp != nullptr) row_tp[i] = tp;
+      if (row_fp != nullptr) row_fp[i] = fp;
+      t_tp += tp; t_fp += fp; t_fn += fn;
+    }
+  }
+  if (lane == 0 && (t_tp | t_fp | t_fn)) {
+    atomicAdd(counts + 0, (unsigned long long)t_tp);
+    atomicAdd(counts + 1, (unsigned long long)t_fp);
+    atomicAdd(counts + 2, (unsigned long long)t_fn);
+  }
+}
+
+__global__ void confusion_triplets_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ cols,
+                                          const uint8_t* __restrict__ gt, int64_t nnz,
+                                          const uint64_t* __restrict__ u_words, int64_t kw,
+                                          const uint64_t* __restrict__ v_words,
+                                          unsigned long long* __restrict__ counts) {
+  int c[4] = {0, 0, 0, 0};   // TP FP FN TN
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t* uw = u_words + (int64_t)rows[e] * kw;
+    const uint64_t* vw = v_words + (int64_t)cols[e] * kw;
+    uint64_t hit = 0;
+    for (int64_t q = 0; q < kw; ++q) hit |= uw[q] & vw[q];
+    const bool pd = hit != 0, g = gt[e] != 0;
+    c[g ? (pd ? 0 : 2) : (pd ? 1 : 3)] += 1;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int s = warp_sum(c[q]);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(counts + q, (unsigned long long)s);
+  }
+}
+
+// AssoIter.get_refined_column in one pass (PyBMF/models/AssoIter.py:80-100)
+__global__ void __launch_bounds__(256)
+refine_column_kernel(const uint64_t* __restrict__ xb, int64_t m, int64_t n, int64_t words,
+                     uint64_t* __restrict__ u_words, int64_t kw, const uint64_t* __restrict__ vt,
+                     int64_t col, int wa, int wb, double neg_w_fp, double w_fn,
+                     unsigned long long* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t pairs = words >> 1;
+  const uint64_t* __restrict__ vcol = vt + col * words;
+  long long t_tp = 0, t_fp = 0, t_used = 0, t_p = 0, t_n = 0;
+  for (int64_t i = warp0; i < m; i += nwarps) {
+    uint64_t* uw = u_words + i * kw;
+    int tpo = 0, fpo = 0, P = 0, N = 0;
+    for (int64_t p = lane; p < pairs; p += 32) {
+      const ulonglong2 x = ld_words2(xb + i * words + 2 * p);
+      const ulonglong2 c = product_pair(uw, kw, vt, words, p, col);      // cover without factor `col`
+      const ulonglong2 v = ld_words2(vcol + 2 * p);
+      tpo += __popcll(x.x & c.x) + __popcll(x.y & c.y);
+      fpo += __popcll(~x.x & c.x) + __popcll(~x.y & c.y);
+      P += __popcll(x.x & ~c.x & v.x) + __popcll(x.y & ~c.y & v.y);
+      N += __popcll(~x.x & ~c.x & v.x) + __popcll(~x.y & ~c.y & v.y);
+    }
+    tpo = warp_sum(tpo); fpo = warp_sum(fpo); P = warp_sum(P); N = warp_sum(N);
+    const bool use = row_uses(wa, wb, neg_w_fp, w_fn, tpo, fpo, P, N);
+    __syncwarp();
+    if (lane == 0) {
+      const uint64_t bit = 1ull << (col & 63);
+      uint64_t w = uw[col >> 6];
+      w = use ? (w | bit) : (w & ~bit);                                  // AssoIter.py:60: always overwritten
+      uw[col >> 6] = w;
+      t_tp += tpo + (use ? P : 0);
+      t_fp += fpo + (use ? N : 0);
+      if (use) { t_used += 1; t_p += P; t_n += N; }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    atomicAdd(out + 0, (unsigned long long)t_tp);
+    atomicAdd(out + 1, (unsigned long long)t_fp);
+    atomicAdd(out + 2, (unsigned long long)t_used);
+    atomicAdd(out + 3, (unsigned long long)t_p);
+    atomicAdd(out + 4, (unsigned long long)t_n);
+  }
+}
+
+static inline int row_stream_grid() { return num_sms() * 8; }
+
+}  // namespace bmf
+
+using namespace bmf;
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" int bmf_fill_zero(void* ptr, int64_t bytes, bmf_stream_t stream) {
+  BMF_REQUIRE(ptr != nullptr && bytes >= 0, "bmf_fill_zero: null pointer or negative size");
+  return check_cuda(cudaMemsetAsync(ptr, 0, (size_t)bytes, as_stream(stream)), "bmf_fill_zero");
+}
+
+extern "C" int bmf_pack_csr(const int64_t* indptr, const int32_t* indices, int64_t m, int64_t n,
+                            int transposed, uint64_t* bits, int64_t words, bmf_stream_t stream) {
+  BMF_REQUIRE(indptr && bits && m >= 0 && n >= 0, "bmf_pack_csr: null pointer or negative shape");
+  BMF_REQUIRE(words % 2 == 0 && words * 64 >= (transposed ? m : n), "bmf_pack_csr: words must be even and cover the row");
+  if (m == 0) return 0;
+  BMF_REQUIRE(indices != nullptr, "bmf_pack_csr: null indices");
+  const int64_t blocks = ceil_div(m, 8);
+  pack_csr_kernel<<<(unsigned)(blocks > 1048576 ? 1048576 : blocks), 256, 0, as_stream(stream)>>>(
+      indptr, indices, m, transposed, reinterpret_cast<unsigned long long*>(bits), words);
+  BMF_LAUNCH_CHECK("bmf_pack_csr");
+  return 0;
+}
+
+extern "C" int bmf_expand_bits_i8(const uint64_t* bits, int64_t rows, int64_t ncols, int64_t words,
+                                  int8_t one, int8_t zero, int8_t* plane, int64_t rows_pad, int64_t ld,
+                                  bmf_stream_t stream) {
+  BMF_REQUIRE(bits && plane, "bmf_expand_bits_i8: null pointer");
+  BMF_REQUIRE(ld % 128 == 0 && ld >= ncols && rows_pad >= rows && rows >= 0, "bmf_expand_bits_i8: bad ld / rows_pad");
+  if (rows_pad == 0) return 0;
+  const int64_t total = rows_pad * (ld >> 4);
+  int64_t blocks = ceil_div(total, 256);
+  if (blocks > (int64_t)num_sms() * 64) blocks = (int64_t)num_sms() * 64;
+  expand_bits_i8_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(bits, rows, ncols, words, one, zero,
+                                                                       plane, rows_pad, ld);
+  BMF_LAUNCH_CHECK("bmf_expand_bits_i8");
+  return 0;
+}
+
+extern "C" int bmf_assoc_counts_popc(const uint64_t* xt_bits, int64_t n, int64_t words_m, int32_t* cnt,
+                                     int64_t ldc, bmf_stream_t stream) {
+  BMF_REQUIRE(xt_bits && cnt && n > 0 && ldc >= n && words_m > 0, "bmf_assoc_counts_popc: bad arguments");
+  dim3 grid((unsigned)ceil_div(n, PT), (unsigned)ceil_div(n, PT));
+  assoc_counts_popc_kernel<<<grid, 256, 0, as_stream(stream)>>>(xt_bits, n, words_m, cnt, ldc);
+  BMF_LAUNCH_CHECK("bmf_assoc_counts_popc");
+  return 0;
+}
+
+extern "C" int bmf_basis_threshold(const int32_t* cnt, int64_t ldc, int64_t n, double tau,
+                                   uint64_t* basis_bits, int64_t words, int8_t* cand_plane, int64_t ld,
+                                   uint8_t* alive, bmf_stream_t stream) {
+  BMF_REQUIRE(cnt && basis_bits && alive && n > 0 && ldc >= n, "bmf_basis_threshold: bad arguments");
+  BMF_REQUIRE(words % 2 == 0 && words * 64 >= n, "bmf_basis_threshold: words must be even and cover n");
+  BMF_REQUIRE(cand_plane == nullptr || (ld % 128 == 0 && ld >= n), "bmf_basis_threshold: bad ld");
+  int64_t blocks = ceil_div(n, 8);
+  basis_threshold_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(cnt, ldc, n, tau, basis_bits, words,
+                                                                        cand_plane, ld, alive);
+  BMF_LAUNCH_CHECK("bmf_basis_threshold");
+  return 0;
+}
+
+extern "C" int bmf_cover_score_popc(const uint64_t* x_bits, const uint64_t* c_bits, int64_t m, int64_t n,
+                                    int64_t words, const uint64_t* basis_bits, const uint8_t* alive,
+                                    const int32_t* tp_old, const int32_t* fp_old, int32_t wa, int32_t wb,
+                                    double w_fp, double w_fn, int64_t* gain_p, int64_t* gain_n,
+                                    bmf_stream_t stream) {
+  BMF_REQUIRE(x_bits && c_bits && basis_bits && alive && gain_p, "bmf_cover_score_popc: null pointer");
+  BMF_REQUIRE(m > 0 && n > 0 && words * 64 >= n, "bmf_cover_score_popc: bad shape");
+  const bool integer_mode = (wa | wb) != 0;
+  BMF_REQUIRE(integer_mode || (tp_old && fp_old && gain_n), "bmf_cover_score_popc: general mode needs tp_old/fp_old/gain_n");
+  BMF_REQUIRE(wa >= 0 && wb >= 0 && wa <= 127 && wb <= 127, "bmf_cover_score_popc: integer weights out of range");
+  int rc = check_cuda(cudaMemsetAsync(gain_p, 0, sizeof(int64_t) * n, as_stream(stream)), "bmf_cover_score_popc");
+  if (rc) return rc;
+  if (!integer_mode) {
+    rc = check_cuda(cudaMemsetAsync(gain_n, 0, sizeof(int64_t) * n, as_stream(stream)), "bmf_cover_score_popc");
+    if (rc) return rc;
+  }
+  const int64_t cand_tiles = ceil_div(n, PT), row_tiles = ceil_div(m, PT);
+  int64_t splits = ceil_div((int64_t)num_sms() * 8, cand_tiles);
+  if (splits > row_tiles) splits = row_tiles;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  dim3 grid((unsigned)cand_tiles, (unsigned)splits);
+  cover_score_popc_kernel<<<grid, 256, 0, as_stream(stream)>>>(
+      x_bits, c_bits, m, n, words, basis_bits, alive, tp_old, fp_old, wa, wb, -w_fp, w_fn,
+      reinterpret_cast<unsigned long long*>(gain_p), reinterpret_cast<unsigned long long*>(gain_n));
+  BMF_LAUNCH_CHECK("bmf_cover_score_popc");
+  return 0;
+}
+
+extern "C" int bmf_select_first_max(const int64_t* gain_p, const int64_t* gain_n, const uint8_t* alive,
+                                    int64_t n, int32_t wa, int32_t wb, int64_t base_int, double scale,
+                                    double w_fp, double w_fn, int64_t tp_tot, int64_t fp_tot,
+                                    double best_score, int64_t* record, bmf_stream_t stream) {
+  BMF_REQUIRE(gain_p && alive && record && n > 0, "bmf_select_first_max: bad arguments");
+  BMF_REQUIRE((wa | wb) != 0 || gain_n != nullptr, "bmf_select_first_max: general mode needs gain_n");
+  select_first_max_kernel<<<1, 1024, 0, as_stream(stream)>>>(gain_p, gain_n, alive, n, wa, wb, base_int, scale,
+                                                            -w_fp, w_fn, tp_tot, fp_tot, best_score, record);
+  BMF_LAUNCH_CHECK("bmf_select_first_max");
+  return 0;
+}
+
+extern "C" int bmf_cover_apply(const uint64_t* x_bits, uint64_t* c_bits, int64_t m, int64_t n, int64_t words,
+                               const uint64_t* basis_bits, uint8_t* alive, const int64_t* winner,
+                               int32_t* tp_old, int32_t* fp_old, int32_t wa, int32_t wb, double w_fp,
+                               double w_fn, int8_t* rows_plane, int64_t ld, uint64_t* u_bits,
+                               int64_t* totals, bmf_stream_t stream) {
+  BMF_REQUIRE(x_bits && c_bits && basis_bits && alive && winner && tp_old && fp_old && u_bits && totals,
+              "bmf_cover_apply: null pointer");
+  BMF_REQUIRE(m > 0 && n > 0 && words % 2 == 0 && words * 64 >= n, "bmf_cover_apply: bad shape");
+  BMF_REQUIRE(rows_plane == nullptr || (ld % 128 == 0 && ld >= words * 64), "bmf_cover_apply: ld must cover words*64");
+  int64_t blocks = ceil_div(m, 8);
+  if (blocks > row_stream_grid()) blocks = row_stream_grid();
+  cover_apply_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+      x_bits, c_bits, m, n, words, basis_bits, alive, winner, tp_old, fp_old, wa, wb, -w_fp, w_fn, rows_plane,
+      ld, reinterpret_cast<unsigned long long*>(u_bits), reinterpret_cast<unsigned long long*>(totals));
+  BMF_LAUNCH_CHECK("bmf_cover_apply");
+  return 0;
+}
+
+extern "C" int bmf_bool_product(const uint64_t* u_words, int64_t m, int64_t kw, const uint64_t* vt_bits,
+                                int64_t k, int64_t words, uint64_t* pd_bits, bmf_stream_t stream) {
+  BMF_REQUIRE(u_words && pd_bits && m > 0 && kw > 0 && k >= 0 && k <= kw * 64, "bmf_bool_product: bad arguments");
+  BMF_REQUIRE(words > 0 && words % 2 == 0 && (k == 0 || vt_bits), "bmf_bool_product: bad words / vt_bits");
+  int64_t blocks = ceil_div(m, 8);
+  if (blocks > row_stream_grid()) blocks = row_stream_grid();
+  bool_product_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(u_words, m, kw, vt_bits, words, pd_bits);
+  BMF_LAUNCH_CHECK("bmf_bool_product");
+  return 0;
+}
+
+extern "C" int bmf_confusion_factors(const uint64_t* gt_bits, int64_t m, int64_t words, const uint64_t* u_words,
+                                     int64_t kw, const uint64_t* vt_bits, int64_t k, int64_t* counts,
+                                     int32_t* row_tp, int32_t* row_fp, bmf_stream_t stream) {
+  BMF_REQUIRE(gt_bits && u_words && counts && m > 0 && kw > 0 && k <= kw * 64, "bmf_confusion_factors: bad arguments");
+  BMF_REQUIRE(words > 0 && words % 2 == 0 && (k == 0 || vt_bits), "bmf_confusion_factors: bad words / vt_bits");
+  int64_t blocks = ceil_div(m, 8);
+  if (blocks > row_stream_grid()) blocks = row_stream_grid();
+  confusion_kernel<true><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+      gt_bits, nullptr, m, words, u_words, kw, vt_bits, reinterpret_cast<unsigned long long*>(counts), row_tp,
+      row_fp);
+  BMF_LAUNCH_CHECK("bmf_confusion_factors");
+  return 0;
+}
+
+extern "C" int bmf_confusion_bits(const uint64_t* gt_bits, const uint64_t* pd_bits, int64_t m, int64_t words,
+                                  int64_t* counts, int32_t* row_tp, int32_t* row_fp, bmf_stream_t stream) {
+  BMF_REQUIRE(gt_bits && pd_bits && counts && m > 0 && words > 0 && words % 2 == 0, "bmf_confusion_bits: bad arguments");
+  int64_t blocks = ceil_div(m, 8);
+  if (blocks > row_stream_grid()) blocks = row_stream_grid();
+  confusion_kernel<false><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+      gt_bits, pd_bits, m, words, nullptr, 0, nullptr, reinterpret_cast<unsigned long long*>(counts), row_tp,
+      row_fp);
+  BMF_LAUNCH_CHECK("bmf_confusion_bits");
+  return 0;
+}
+
+extern "C" int bmf_confusion_triplets(const int32_t* rows, const int32_t* cols, const uint8_t* gt, int64_t nnz,
+                                      const uint64_t* u_words, int64_t kw, const uint64_t* v_words,
+                                      int64_t* counts, bmf_stream_t stream) {
+  BMF_REQUIRE(counts && kw > 0 && nnz >= 0, "bmf_confusion_triplets: bad arguments");
+  if (nnz == 0) return 0;
+  BMF_REQUIRE(rows && cols && gt && u_words && v_words, "bmf_confusion_triplets: null pointer");
+  int64_t blocks = ceil_div(nnz, 256);
+  if (blocks > row_stream_grid()) blocks = row_stream_grid();
+  confusion_triplets_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+      rows, cols, gt, nnz, u_words, kw, v_words, reinterpret_cast<unsigned long long*>(counts));
+  BMF_LAUNCH_CHECK("bmf_confusion_triplets");
+  return 0;
+}
+
+extern "C" int bmf_refine_column(const uint64_t* x_bits, int64_t m, int64_t n, int64_t words, uint64_t* u_words,
+                                 int64_t kw, const uint64_t* vt_bits, int64_t k, int64_t col, int32_t wa,
+                                 int32_t wb, double w_fp, double w_fn, int64_t* out, bmf_stream_t stream) {
+  BMF_REQUIRE(x_bits && u_words && vt_bits && out, "bmf_refine_column: null pointer");
+  BMF_REQUIRE(m > 0 && n > 0 && words % 2 == 0 && words * 64 >= n && kw > 0 && k <= kw * 64, "bmf_refine_column: bad shape");
+  BMF_REQUIRE(col >= 0 && col < k, "bmf_refine_column: column out of range");
+  int64_t blocks = ceil_div(m, 8);
+  if (blocks > row_stream_grid()) blocks = row_stream_grid();
+  refine_column_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+      x_bits, m, n, words, u_words, kw, vt_bits, col, wa, wb, -w_fp, w_fn,
+      reinterpret_cast<unsigned long long*>(out));
+  BMF_LAUNCH_CHECK("bmf_refine_column");
+  return 0;
+}

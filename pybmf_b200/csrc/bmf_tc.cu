@@ -1,0 +1,363 @@
+// Dense 0/1 contractions of the Asso hot path on the 5th-generation tensor cores (sm_100a):
+//   D[j][i] = sum_k cand[j][k] * rows[i][k]      (int8 x int8 -> int32, tcgen05.mma kind::i8)
+// Both operands are K-major int8 planes in HBM, moved by TMA (SWIZZLE_128B) into a 4-stage
+// shared-memory ring, multiplied by a single elected thread into TMEM accumulators
+// (2 x 256 columns, double buffered) and drained by four epilogue warps that apply the fused
+// epilogue without writing D to HBM:
+//   EPI_GAIN : gain[j] += sum_i relu(D[j][i])           (cover-gain scoring, Asso.py:83-95/144-188)
+//   EPI_STORE: cnt[j][i] = D[j][i]                      (association counts X^T X, Asso.py:207)
+// Candidates sit on the MMA M axis (TMEM lanes): each epilogue thread owns one candidate and
+// reduces over its tile columns in registers -- no cross-lane traffic.
+//
+// Warp roles (192 threads, 1 CTA/SM, persistent over a grouped tile raster):
+//   warp 0: TMA producer (one lane)      warp 1: TMEM allocator + MMA issuer (one lane)
+//   warps 2-5: epilogue (TMEM lane quadrant = warp_id % 4)
+#include <cuda.h>
+
+#include "bmf_common.cuh"
+
+namespace bmf {
+namespace tc {
+
+constexpr int BM = BMF_I8_CAND_TILE;   // 128 candidates per tile (MMA M)
+constexpr int BN = BMF_I8_ROW_TILE;    // 256 data rows per tile (MMA N)
+constexpr int BK = BMF_I8_K_TILE;      // 128 bytes of K per stage = one swizzle row
+constexpr int UMMA_K = 32;             // K per tcgen05.mma kind::i8
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK;       // 16 KB
+constexpr int B_BYTES = BN * BK;       // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;         // 2 accumulators x 256 columns x 128 lanes x int32
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+enum { EPI_GAIN = 0, EPI_STORE = 1 };
+
+// instruction descriptor (cute::UMMA::InstrDescriptor layout): dense, no saturate,
+// C = S32 (2) at [4,6), A = S8 (1) at [7,10), B = S8 (1) at [10,13), K-major both,
+// N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                              ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug must fault the launch, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > (1ll << 33)) {
+      printf("bmf_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_128B,
+// rows 128 B apart, 8-row groups 1024 B apart (SBO), version 1
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+  uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// 32 lanes x 32 consecutive columns of int32: thread t of the warp gets lane (quadrant*32 + t)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Grouped raster: GROUP_M candidate tiles share the L2-resident candidate panel while the
+// row tiles sweep; a wave of CTAs covers a near-square block of the tile grid.
+__device__ __forceinline__ void tile_coords(int64_t t, int mt_total, int nt_total, int group_m, int& mt, int& nt) {
+  const int64_t per_group = (int64_t)group_m * nt_total;
+  const int g = (int)(t / per_group);
+  const int64_t r = t - (int64_t)g * per_group;
+  const int first = g * group_m;
+  const int gsize = min(group_m, mt_total - first);
+  mt = first + (int)(r % gsize);
+  nt = (int)(r / gsize);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               int mt_total, int nt_total, int kb_total, int group_m, unsigned long long* __restrict__ gain,
+               int32_t* __restrict__ C, int64_t ldc) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then tmem base
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t total_tiles = (int64_t)mt_total * nt_total;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_base_slot);
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int mt, nt;
+        tile_coords(t, mt_total, nt_total, group_m, mt, nt);
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
+          tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * BK, mt * BM);
+          tma_load_2d(a_dst + A_BYTES, &tmap_b, full_bar(stage), kb * BK, nt * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);       // epilogue has drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(full_bar(stage), phase);              // TMA bytes have landed
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
+          const uint64_t da = make_smem_desc(a_addr), db = make_smem_desc(a_addr + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            tcgen05_mma_i8(d_tmem, da + (uint64_t)(k * (UMMA_K >> 4)), db + (uint64_t)(k * (UMMA_K >> 4)),
+                           IDESC_I8, (uint32_t)((kb | k) != 0));
+          tcgen05_commit(empty_bar(stage));               // smem slot free once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tcgen05_commit(tfull_bar(acc));                   // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue warps =====
+    const int quad = warp & 3;                            // TMEM lanes [32*quad, 32*quad+32)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int mt, nt;
+      tile_coords(t, mt_total, nt_total, group_m, mt, nt);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      const int64_t row = (int64_t)mt * BM + quad * 32 + lane;
+      long long relu_sum = 0;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+        if (EPI == EPI_GAIN) {
+          int part = 0;                                   // 32 * 127 * K fits int32 for K < 5e5
+#pragma unroll
+          for (int q = 0; q < 32; ++q) part += max((int)v[q], 0);
+          relu_sum += part;
+        } else {
+          int4* dst = reinterpret_cast<int4*>(C + row * ldc + (int64_t)nt * BN + c * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            dst[q] = make_int4((int)v[4 * q], (int)v[4 * q + 1], (int)v[4 * q + 2], (int)v[4 * q + 3]);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));        // 4 arrivals free the accumulator
+      if (EPI == EPI_GAIN && relu_sum != 0) atomicAdd(gain + row, (unsigned long long)relu_sum);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess || p == nullptr)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// plane[rows][ld] int8, box = box_rows x 128 bytes, 128-byte swizzle
+static int make_plane_map(CUtensorMap* map, const int8_t* plane, int64_t rows, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available from the driver");
+    return BMF_E_DRIVER;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(plane), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld ld=%lld)", (int)r, (long long)rows,
+              (long long)ld);
+    return BMF_E_DRIVER;
+  }
+  return 0;
+}
+
+template <int EPI>
+static int launch_gemm(const int8_t* a, int64_t a_rows, const int8_t* b, int64_t b_rows, int64_t ld,
+                       unsigned long long* gain, int32_t* C, int64_t ldc, cudaStream_t stream) {
+  CUtensorMap ma, mb;
+  int rc = make_plane_map(&ma, a, a_rows, ld, BM);
+  if (rc) return rc;
+  rc = make_plane_map(&mb, b, b_rows, ld, BN);
+  if (rc) return rc;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[EPI]) {
+    rc = check_cuda(cudaFuncSetAttribute(gemm_i8_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES),
+                    "cudaFuncSetAttribute(gemm_i8_kernel)");
+    if (rc) return rc;
+    attr_set[EPI] = true;
+  }
+  const int mt = (int)(a_rows / BM), nt = (int)(b_rows / BN), kb = (int)(ld / BK);
+  const int64_t tiles = (int64_t)mt * nt;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  const int group_m = 8;
+  gemm_i8_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, mt, nt, kb, group_m, gain, C, ldc);
+  return check_cuda(cudaGetLastError(), "gemm_i8_kernel launch");
+}
+
+}  // namespace tc
+}  // namespace bmf
+
+using namespace bmf;
+
+extern "C" int bmf_gemm_i8_nt(const int8_t* a_plane, int64_t a_rows_pad, const int8_t* b_plane, int64_t b_rows_pad,
+                              int64_t ld, int32_t* c, int64_t ldc, bmf_stream_t stream) {
+  BMF_REQUIRE(a_plane && b_plane && c, "bmf_gemm_i8_nt: null pointer");
+  BMF_REQUIRE(a_rows_pad > 0 && a_rows_pad % tc::BM == 0, "bmf_gemm_i8_nt: a rows must be a positive multiple of 128");
+  BMF_REQUIRE(b_rows_pad > 0 && b_rows_pad % tc::BN == 0, "bmf_gemm_i8_nt: b rows must be a positive multiple of 256");
+  BMF_REQUIRE(ld > 0 && ld % tc::BK == 0, "bmf_gemm_i8_nt: ld must be a positive multiple of 128");
+  BMF_REQUIRE(ldc >= b_rows_pad && ldc % 4 == 0, "bmf_gemm_i8_nt: ldc must cover b rows and be a multiple of 4");
+  return tc::launch_gemm<tc::EPI_STORE>(a_plane, a_rows_pad, b_plane, b_rows_pad, ld, nullptr, c, ldc, as_stream(stream));
+}
+
+extern "C" int bmf_assoc_counts_i8(const int8_t* xt_plane, int64_t n, int64_t n_pad, int64_t ld, int32_t* cnt,
+                                   int64_t ldc, bmf_stream_t stream) {
+  BMF_REQUIRE(xt_plane && cnt && n > 0, "bmf_assoc_counts_i8: null pointer or empty matrix");
+  BMF_REQUIRE(n_pad >= n && n_pad % tc::BN == 0, "bmf_assoc_counts_i8: n_pad must be a multiple of 256 covering n");
+  BMF_REQUIRE(ld > 0 && ld % tc::BK == 0, "bmf_assoc_counts_i8: ld must be a positive multiple of 128");
+  BMF_REQUIRE(ldc >= n_pad && ldc % 4 == 0, "bmf_assoc_counts_i8: ldc must be >= n_pad and a multiple of 4");
+  const int64_t a_rows = ceil_div(n, tc::BM) * tc::BM;    // <= n_pad
+  return tc::launch_gemm<tc::EPI_STORE>(xt_plane, a_rows, xt_plane, n_pad, ld, nullptr, cnt, ldc, as_stream(stream));
+}
+
+extern "C" int bmf_cover_score_i8(const int8_t* cand_plane, int64_t cand_pad, const int8_t* rows_plane,
+                                  int64_t rows_pad, int64_t ld, int64_t* gain, bmf_stream_t stream) {
+  BMF_REQUIRE(cand_plane && rows_plane && gain, "bmf_cover_score_i8: null pointer");
+  BMF_REQUIRE(cand_pad > 0 && cand_pad % tc::BM == 0, "bmf_cover_score_i8: cand_pad must be a positive multiple of 128");
+  BMF_REQUIRE(rows_pad > 0 && rows_pad % tc::BN == 0, "bmf_cover_score_i8: rows_pad must be a positive multiple of 256");
+  BMF_REQUIRE(ld > 0 && ld % tc::BK == 0, "bmf_cover_score_i8: ld must be a positive multiple of 128");
+  int rc = check_cuda(cudaMemsetAsync(gain, 0, sizeof(int64_t) * cand_pad, as_stream(stream)), "bmf_cover_score_i8");
+  if (rc) return rc;
+  return tc::launch_gemm<tc::EPI_GAIN>(cand_plane, cand_pad, rows_plane, rows_pad, ld,
+                                       reinterpret_cast<unsigned long long*>(gain), nullptr, 0, as_stream(stream));
+}

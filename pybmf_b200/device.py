@@ -1,0 +1,96 @@
+"""Device-side containers for the Asso path: bit-packed matrices and int8 operand planes in HBM.
+
+Layout (see include/pybmf_b200.h): a bit matrix is a row-major torch.int64 tensor
+[rows, words] (uint64 words viewed as int64), bit c of a row in word c>>6 at position
+c&63, `words` even so that every row is 16-byte aligned; pad bits are zero.
+torch supplies memory and streams only -- every operation on these buffers is a
+kernel of libbmf_b200.so.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import _native
+
+
+def words_for(ncols: int) -> int:
+    """Even number of uint64 words covering `ncols` bits (>= 2)."""
+    w = (int(ncols) + 63) // 64
+    w += w & 1
+    return max(w, 2)
+
+
+def round_up(x: int, mult: int) -> int:
+    return ((int(x) + mult - 1) // mult) * mult
+
+
+def dev():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def zeros(shape, dtype):
+    return torch.zeros(shape, dtype=dtype, device=dev())
+
+
+def empty(shape, dtype):
+    return torch.empty(shape, dtype=dtype, device=dev())
+
+
+# ---- host <-> bit words (numpy side; used for inputs, outputs and tests) --------------------
+def dense_to_words(A: np.ndarray, words: int | None = None) -> np.ndarray:
+    """0/1 array [rows, ncols] -> int64 words [rows, words] in the library's bit order."""
+    A = (np.asarray(A) != 0).astype(np.uint8)
+    rows, ncols = A.shape
+    words = words_for(ncols) if words is None else words
+    padded = np.zeros((rows, words * 64), dtype=np.uint8)
+    padded[:, :ncols] = A
+    return np.ascontiguousarray(np.packbits(padded, axis=1, bitorder="little")).view(np.int64).reshape(rows, words)
+
+
+def words_to_dense(W: np.ndarray, ncols: int) -> np.ndarray:
+    W = np.ascontiguousarray(W).view(np.uint8).reshape(W.shape[0], -1)
+    return np.unpackbits(W, axis=1, bitorder="little")[:, :ncols]
+
+
+def to_csr_pattern(X) -> sp.csr_matrix:
+    """Non-zero pattern of X as canonical csr (sorted, no duplicates, no explicit zeros)."""
+    X = sp.csr_matrix(X)
+    X = X.copy()
+    X.sum_duplicates()
+    X.eliminate_zeros()
+    X.sort_indices()
+    return X
+
+
+# ---- device packing --------------------------------------------------------------------------
+def upload_csr(X: sp.csr_matrix):
+    """H2D copy of the pattern arrays through pinned staging (indptr int64, indices int32)."""
+    indptr = torch.from_numpy(np.ascontiguousarray(X.indptr.astype(np.int64)))
+    indices = torch.from_numpy(np.ascontiguousarray(X.indices.astype(np.int32)))
+    d = dev()
+    return (indptr.pin_memory().to(d, non_blocking=True), indices.pin_memory().to(d, non_blocking=True))
+
+
+def pack_csr(indptr_d, indices_d, m: int, n: int, transposed: bool = False):
+    """CSR pattern on device -> bit matrix [m, words(n)] (or X^T: [n, words(m)])."""
+    rows, cols = (n, m) if transposed else (m, n)
+    words = words_for(cols)
+    bits = zeros((max(rows, 1), words), torch.int64)
+    if m > 0 and indices_d.numel() > 0:
+        _native.call("bmf_pack_csr", indptr_d, indices_d, m, n, 1 if transposed else 0, bits, words)
+    return bits
+
+
+def expand_bits_i8(bits, rows: int, ncols: int, one: int, zero: int, row_tile: int):
+    """Bit matrix -> int8 plane [round_up(rows,row_tile), round_up(ncols,128)]."""
+    ld = round_up(max(ncols, 1), 128)
+    rows_pad = round_up(max(rows, 1), row_tile)
+    plane = empty((rows_pad, ld), torch.int8)
+    _native.call("bmf_expand_bits_i8", bits, rows, ncols, bits.shape[1], one, zero, plane, rows_pad, ld)
+    return plane
+
+
+def bits_to_host(bits, ncols: int) -> np.ndarray:
+    return words_to_dense(bits.cpu().numpy(), ncols)

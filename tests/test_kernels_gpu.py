@@ -1,0 +1,318 @@
+"""GPU: every C-ABI entry point of libbmf_b200.so against numpy / the oracle on seeded inputs.
+Integer and bit work must be bit-exact."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+from oracle import asso_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def nat():
+    from pybmf_b200 import _native, device
+    _native.require_gpu()
+    return _native, device
+
+
+def _rand01(rng, m, n, d):
+    return (rng.rand(m, n) < d).astype(np.uint8)
+
+
+def _dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+@pytest.mark.parametrize("m,n,d", [(1, 1, 1.0), (7, 130, 0.3), (300, 500, 0.2), (1000, 64, 0.05), (65, 129, 0.0)])
+def test_pack_csr_both_orientations(nat, m, n, d):
+    _native, device = nat
+    rng = np.random.RandomState(m * 1000 + n)
+    A = _rand01(rng, m, n, d)
+    X = device.to_csr_pattern(sp.csr_matrix(A))
+    ip, ix = device.upload_csr(X)
+    bits = device.pack_csr(ip, ix, m, n)
+    assert np.array_equal(device.bits_to_host(bits, n), A)
+    assert np.array_equal(bits.cpu().numpy(), device.dense_to_words(A))          # pad bits are zero
+    bt = device.pack_csr(ip, ix, m, n, transposed=True)
+    assert np.array_equal(device.bits_to_host(bt, m), A.T)
+
+
+@pytest.mark.parametrize("rows,ncols,tile", [(5, 70, 128), (300, 500, 256), (257, 128, 256)])
+def test_expand_bits_i8(nat, rows, ncols, tile):
+    _native, device = nat
+    rng = np.random.RandomState(rows + ncols)
+    A = _rand01(rng, rows, ncols, 0.4)
+    bits = _dev(device.dense_to_words(A))
+    plane = device.expand_bits_i8(bits, rows, ncols, 3, -2, tile).cpu().numpy()
+    want = np.zeros_like(plane)
+    want[:rows, :ncols] = np.where(A == 1, 3, -2)
+    assert plane.shape == (device.round_up(rows, tile), device.round_up(ncols, 128))
+    assert np.array_equal(plane, want)
+
+
+@pytest.mark.parametrize("m,n", [(90, 70), (300, 500), (1000, 200)])
+def test_assoc_counts_popc(nat, m, n):
+    _native, device = nat
+    rng = np.random.RandomState(m + n)
+    A = _rand01(rng, m, n, 0.2)
+    xt = _dev(device.dense_to_words(A.T))
+    cnt = device.zeros((n, n), torch.int32)
+    _native.call("bmf_assoc_counts_popc", xt, n, xt.shape[1], cnt, n)
+    assert np.array_equal(cnt.cpu().numpy().astype(np.int64), O.assoc_counts(A))
+
+
+@pytest.mark.parametrize("ma,nb,k", [(128, 256, 128), (128, 256, 512), (256, 512, 384), (384, 256, 1152),
+                                      (1280, 2304, 640)])
+def test_gemm_i8_tcgen05_exact(nat, ma, nb, k):
+    """tcgen05 kind::i8 + TMA + TMEM primitive on random signed int8 (catches descriptor/swizzle bugs)."""
+    _native, device = nat
+    rng = np.random.RandomState(ma + nb + k)
+    A = rng.randint(-128, 128, size=(ma, k)).astype(np.int8)
+    B = rng.randint(-128, 128, size=(nb, k)).astype(np.int8)
+    c = device.zeros((ma, nb), torch.int32)
+    _native.call("bmf_gemm_i8_nt", _dev(A), ma, _dev(B), nb, k, c, nb)
+    torch.cuda.synchronize()
+    want = A.astype(np.int64) @ B.astype(np.int64).T
+    assert np.array_equal(c.cpu().numpy().astype(np.int64), want)
+
+
+@pytest.mark.parametrize("m,n", [(300, 500), (700, 130)])
+def test_assoc_counts_i8_matches_popc_and_oracle(nat, m, n):
+    _native, device = nat
+    rng = np.random.RandomState(m * 3 + n)
+    A = _rand01(rng, m, n, 0.15)
+    xt = _dev(device.dense_to_words(A.T))
+    plane = device.expand_bits_i8(xt, n, m, 1, 0, 256)
+    n_pad = plane.shape[0]
+    cnt = device.zeros((n_pad, n_pad), torch.int32)
+    _native.call("bmf_assoc_counts_i8", plane, n, n_pad, plane.shape[1], cnt, n_pad)
+    assert np.array_equal(cnt.cpu().numpy()[:n, :n].astype(np.int64), O.assoc_counts(A))
+
+
+@pytest.mark.parametrize("tau", [0.0, 0.25, 0.5, 0.99, 1.0])
+def test_basis_threshold(nat, tau):
+    _native, device = nat
+    rng = np.random.RandomState(17)
+    m, n = 200, 150
+    A = _rand01(rng, m, n, 0.2)
+    A[:, 5] = 0                                                    # an empty column -> dead candidate
+    cnt_h = O.assoc_counts(A)
+    cnt = _dev(cnt_h.astype(np.int32))
+    words = device.words_for(n)
+    ld = device.round_up(n, 128)
+    bits = device.zeros((n, words), torch.int64)
+    plane = device.zeros((device.round_up(n, 128), ld), torch.int8)
+    alive = device.zeros((n,), torch.uint8)
+    _native.call("bmf_basis_threshold", cnt, n, n, float(tau), bits, words, plane, ld, alive)
+    want = (O.build_assoc(A) > tau).astype(np.uint8)
+    assert np.array_equal(device.bits_to_host(bits, n), want)
+    assert np.array_equal(plane.cpu().numpy()[:n, :n], want.astype(np.int8))
+    assert plane.cpu().numpy()[:, n:].sum() == 0 and plane.cpu().numpy()[n:].sum() == 0
+    assert np.array_equal(alive.cpu().numpy(), (want.sum(axis=1) != 0).astype(np.uint8))
+
+
+def _cover_inputs(seed, m, n, nb_density=0.25):
+    rng = np.random.RandomState(seed)
+    X = _rand01(rng, m, n, 0.3)
+    C = _rand01(rng, m, n, 0.15)
+    B = _rand01(rng, n, n, nb_density)
+    alive = (rng.rand(n) < 0.9).astype(np.uint8)
+    return X, C, B, alive
+
+
+@pytest.mark.parametrize("m,n", [(70, 50), (300, 200), (129, 257)])
+@pytest.mark.parametrize("w", [(0.5, 0.5), (0.25, 0.75), (0.2, 0.8), (0.3, 0.6)])
+def test_cover_score_popc(nat, m, n, w):
+    _native, device = nat
+    X, C, B, alive = _cover_inputs(m + n, m, n)
+    w_fp, w_fn = w
+    iw = O.integer_weights(w_fp, w_fn)
+    wa, wb = (iw[0], iw[1]) if iw else (0, 0)
+    words = device.words_for(n)
+    tpo, fpo, _ = O.confusion(X, C, axis=1)
+    gp = device.zeros((n,), torch.int64)
+    gn = device.zeros((n,), torch.int64)
+    _native.call("bmf_cover_score_popc", _dev(device.dense_to_words(X)), _dev(device.dense_to_words(C)), m, n, words,
+                 _dev(device.dense_to_words(B)), _dev(alive), _dev(tpo.astype(np.int32)), _dev(fpo.astype(np.int32)),
+                 wa, wb, w_fp, w_fn, gp, gn)
+    score, use, P, N, _, _ = O.score_candidates(X, C, B, w_fp, w_fn)
+    live = alive.astype(bool)
+    # 64-candidate tiles with no live candidate are skipped entirely; live ones must be exact
+    if iw:
+        G = O.integer_gains(X, C, B, wa, wb)
+        assert np.array_equal(gp.cpu().numpy()[live], G[live])
+    else:
+        assert np.array_equal(gp.cpu().numpy()[live], (P * use).sum(axis=0)[live])
+        assert np.array_equal(gn.cpu().numpy()[live], (N * use).sum(axis=0)[live])
+
+
+@pytest.mark.parametrize("m,n,w", [(70, 50, (0.5, 0.5)), (300, 200, (0.25, 0.75)), (600, 700, (0.5, 0.5)),
+                                   (1000, 500, (0.375, 0.5))])
+def test_cover_score_i8_tcgen05(nat, m, n, w):
+    _native, device = nat
+    X, C, B, alive = _cover_inputs(m * 7 + n, m, n)
+    wa, wb, _ = O.integer_weights(*w)
+    words = device.words_for(n)
+    rows = np.where(C == 1, 0, np.where(X == 1, wb, -wa)).astype(np.int8)
+    ld = device.round_up(n, 128)
+    rows_plane = np.zeros((device.round_up(m, 256), ld), np.int8)
+    rows_plane[:m, :n] = rows
+    cand_plane = np.zeros((device.round_up(n, 128), ld), np.int8)
+    cand_plane[:n, :n] = B
+    gain = device.zeros((cand_plane.shape[0],), torch.int64)
+    _native.call("bmf_cover_score_i8", _dev(cand_plane), cand_plane.shape[0], _dev(rows_plane), rows_plane.shape[0],
+                 ld, gain)
+    G = O.integer_gains(X, C, B, wa, wb)
+    got = gain.cpu().numpy()
+    assert np.array_equal(got[:n], G) and got[n:].sum() == 0
+
+
+def test_select_first_max(nat):
+    _native, device = nat
+    n = 3000
+    rng = np.random.RandomState(5)
+    g = rng.randint(0, 50, size=n).astype(np.int64)
+    g[[700, 1500, 2900]] = 99                                      # three-way tie: lowest live index wins
+    alive = np.ones(n, np.uint8)
+    alive[700] = 0
+    rec = device.zeros((2,), torch.int64)
+    args = (_dev(g), None, _dev(alive), n, 1, 1, 10, 0.5, 0.5, 0.5, 0, 0)
+    _native.call("bmf_select_first_max", *args, 0.0, rec)
+    r = rec.cpu().numpy()
+    assert r[0] == 1500 and r[1:2].view(np.float64)[0] == (10 + 99) * 0.5
+    _native.call("bmf_select_first_max", *args, 54.5, rec)          # not strictly greater than inherited best
+    assert rec.cpu().numpy()[0] == -1
+    # general mode: score from totals in fp64
+    gp = rng.randint(0, 1000, size=n).astype(np.int64)
+    gn = rng.randint(0, 1000, size=n).astype(np.int64)
+    _native.call("bmf_select_first_max", _dev(gp), _dev(gn), _dev(alive), n, 0, 0, 0, 0.0, 0.2, 0.8, 12345, 678,
+                 -1e300, rec)
+    sc = -0.2 * (678 + gn).astype(np.float64) + 0.8 * (12345 + gp).astype(np.float64)
+    sc[alive == 0] = -np.inf
+    r = rec.cpu().numpy()
+    assert r[0] == int(np.argmax(sc)) and r[1:2].view(np.float64)[0] == sc.max()
+
+
+@pytest.mark.parametrize("w", [(0.5, 0.5), (0.2, 0.8)])
+def test_cover_apply(nat, w):
+    _native, device = nat
+    m, n = 333, 200
+    X, C, B, alive = _cover_inputs(99, m, n)
+    alive[:] = 1
+    w_fp, w_fn = w
+    iw = O.integer_weights(w_fp, w_fn)
+    wa, wb = (iw[0], iw[1]) if iw else (0, 0)
+    j = 37
+    words = device.words_for(n)
+    ld = device.round_up(n, 128)
+    tpo, fpo, _ = O.confusion(X, C, axis=1)
+    score, use, P, N, _, _ = O.score_candidates(X, C, B[j:j + 1], w_fp, w_fn)
+    u = use[:, 0]
+    rows = np.zeros((device.round_up(m, 256), ld), np.int8)
+    rows[:m, :n] = np.where(C == 1, 0, np.where(X == 1, max(wb, 1), -max(wa, 1)))
+    rows_d = _dev(rows)
+    c_d = _dev(device.dense_to_words(C))
+    tp_d, fp_d = _dev(tpo.astype(np.int32)), _dev(fpo.astype(np.int32))
+    alive_d = _dev(alive)
+    ub = device.zeros((device.words_for(m),), torch.int64)
+    tot = device.zeros((3,), torch.int64)
+    win = _dev(np.array([j], np.int64))
+    _native.call("bmf_cover_apply", _dev(device.dense_to_words(X)), c_d, m, n, words, _dev(device.dense_to_words(B)),
+                 alive_d, win, tp_d, fp_d, wa, wb, w_fp, w_fn, rows_d, ld, ub, tot)
+    Cn = C | (u[:, None].astype(np.uint8) & B[j][None, :])
+    assert np.array_equal(device.bits_to_host(c_d, n), Cn)
+    assert np.array_equal(device.words_to_dense(ub.cpu().numpy().reshape(1, -1), m)[0], u.astype(np.uint8))
+    tpn, fpn, _ = O.confusion(X, Cn, axis=1)
+    assert np.array_equal(tp_d.cpu().numpy(), tpn) and np.array_equal(fp_d.cpu().numpy(), fpn)
+    assert list(tot.cpu().numpy()) == [int(u.sum()), int(P[u, 0].sum()), int(N[u, 0].sum())]
+    want_rows = rows.copy()
+    want_rows[:m, :n][Cn == 1] = 0
+    assert np.array_equal(rows_d.cpu().numpy(), want_rows)
+    assert alive_d.cpu().numpy()[j] == 0 and alive_d.cpu().numpy().sum() == n - 1
+    # winner < 0 is a no-op
+    before = c_d.clone()
+    _native.call("bmf_cover_apply", _dev(device.dense_to_words(X)), c_d, m, n, words, _dev(device.dense_to_words(B)),
+                 alive_d, _dev(np.array([-1], np.int64)), tp_d, fp_d, wa, wb, w_fp, w_fn, rows_d, ld, ub, tot)
+    assert torch.equal(before, c_d)
+
+
+@pytest.mark.parametrize("m,n,k", [(50, 70, 1), (300, 500, 5), (257, 129, 64), (100, 200, 70)])
+def test_bool_product_and_confusion(nat, m, n, k):
+    _native, device = nat
+    rng = np.random.RandomState(m + n + k)
+    U = _rand01(rng, m, k, 0.2)
+    V = _rand01(rng, n, k, 0.2)
+    X = _rand01(rng, m, n, 0.3)
+    kw = (k + 63) // 64
+    uw = np.ascontiguousarray(device.dense_to_words(U, words=kw))
+    vt = device.dense_to_words(V.T)
+    words = device.words_for(n)
+    pd = device.zeros((m, words), torch.int64)
+    _native.call("bmf_bool_product", _dev(uw), m, kw, _dev(vt), k, words, pd)
+    want = O.bool_product(U, V)
+    assert np.array_equal(device.bits_to_host(pd, n), want)
+    assert np.array_equal(pd.cpu().numpy(), device.dense_to_words(want))
+    tp, fp, fn = O.confusion(X, want)
+    rtp, rfp, _ = O.confusion(X, want, axis=1)
+    for mode in ("factors", "bits"):
+        counts = device.zeros((3,), torch.int64)
+        row_tp = device.zeros((m,), torch.int32)
+        row_fp = device.zeros((m,), torch.int32)
+        if mode == "factors":
+            _native.call("bmf_confusion_factors", _dev(device.dense_to_words(X)), m, words, _dev(uw), kw, _dev(vt), k,
+                         counts, row_tp, row_fp)
+        else:
+            _native.call("bmf_confusion_bits", _dev(device.dense_to_words(X)), pd, m, words, counts, row_tp, row_fp)
+        assert list(counts.cpu().numpy()) == [int(tp), int(fp), int(fn)]
+        assert np.array_equal(row_tp.cpu().numpy(), rtp) and np.array_equal(row_fp.cpu().numpy(), rfp)
+
+
+def test_confusion_triplets(nat):
+    _native, device = nat
+    rng = np.random.RandomState(8)
+    m, n, k, nnz = 120, 90, 6, 5000
+    U = _rand01(rng, m, k, 0.3)
+    V = _rand01(rng, n, k, 0.3)
+    r = rng.randint(0, m, nnz).astype(np.int32)
+    c = rng.randint(0, n, nnz).astype(np.int32)
+    g = (rng.rand(nnz) < 0.5).astype(np.uint8)
+    pd = O.bool_product(U, V)[r, c]
+    counts = device.zeros((4,), torch.int64)
+    _native.call("bmf_confusion_triplets", _dev(r), _dev(c), _dev(g), nnz, _dev(device.dense_to_words(U, words=1)), 1,
+                 _dev(device.dense_to_words(V, words=1)), counts)
+    want = [int(((g == 1) & (pd == 1)).sum()), int(((g == 0) & (pd == 1)).sum()),
+            int(((g == 1) & (pd == 0)).sum()), int(((g == 0) & (pd == 0)).sum())]
+    assert list(counts.cpu().numpy()) == want
+
+
+@pytest.mark.parametrize("w", [(0.5, 0.5), (0.2, 0.8)])
+def test_refine_column(nat, w):
+    _native, device = nat
+    rng = np.random.RandomState(21)
+    m, n, k = 310, 190, 5
+    X = _rand01(rng, m, n, 0.3)
+    U = _rand01(rng, m, k, 0.3)
+    V = _rand01(rng, n, k, 0.3)
+    w_fp, w_fn = w
+    iw = O.integer_weights(w_fp, w_fn)
+    wa, wb = (iw[0], iw[1]) if iw else (0, 0)
+    words = device.words_for(n)
+    uw = _dev(device.dense_to_words(U, words=1))
+    vt = _dev(device.dense_to_words(V.T))
+    xb = _dev(device.dense_to_words(X))
+    for col in (0, 3):
+        out = device.zeros((5,), torch.int64)
+        _native.call("bmf_refine_column", xb, m, n, words, uw, 1, vt, k, col, wa, wb, w_fp, w_fn, out)
+        idx = [i for i in range(k) if i != col]
+        C_old = O.bool_product(U[:, idx], V[:, idx])
+        score, use, P, N, tpo, fpo = O.score_candidates(X, C_old, V[:, col].reshape(1, -1), w_fp, w_fn)
+        U[:, col] = use[:, 0]
+        assert np.array_equal(device.words_to_dense(uw.cpu().numpy(), k), U)
+        tp, fp, _ = O.confusion(X, O.bool_product(U, V))
+        u = use[:, 0]
+        assert list(out.cpu().numpy()) == [int(tp), int(fp), int(u.sum()), int(P[u, 0].sum()), int(N[u, 0].sum())]
