@@ -55,10 +55,11 @@ int bmf_pack_csr(const int64_t* indptr, const int32_t* indices, int64_t m, int64
                  int transposed, uint64_t* bits, int64_t words, bmf_stream_t stream);
 int bmf_fill_zero(void* ptr, int64_t bytes, bmf_stream_t stream);
 /* bits[rows][words] -> int8 plane[rows_pad][ld]: value `one` where the bit is set,
- * `zero` where it is clear and the column < ncols, 0 in all padding. */
-int bmf_expand_bits_i8(const uint64_t* bits, int64_t rows, int64_t ncols, int64_t words,
-                       int8_t one, int8_t zero, int8_t* plane, int64_t rows_pad, int64_t ld,
-                       bmf_stream_t stream);
+ * `zero` where it is clear and the column < ncols, 0 in all padding and wherever
+ * mask_bits (nullable, same layout; the covered mask) has a 1. */
+int bmf_expand_bits_i8(const uint64_t* bits, const uint64_t* mask_bits, int64_t rows, int64_t ncols,
+                       int64_t words, int8_t one, int8_t zero, int8_t* plane, int64_t rows_pad,
+                       int64_t ld, bmf_stream_t stream);
 
 /* ---- association matrix: build_assoc, PyBMF/models/Asso.py:191-213 -------------------
  * cnt[i][j] = |col_i AND col_j| = (X^T X)[i][j], int32, leading dimension ldc.

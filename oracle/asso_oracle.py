@@ -265,9 +265,9 @@ def asso_iter_fit(X, U, V, k, w_fp=0.5, w_fn=None):
     is_improving = True
     while is_improving:
         for c in range(k):
-            if c >= V.shape[1]:
-                raise IndexError("column index (%d) out of range" % c)   # lil indexing, AssoIter.py:89
-            idx = [i for i in range(k) if i != c and i < U.shape[1]]
+            if k > U.shape[1]:                                 # lil fancy indexing U[:, idx], AssoIter.py:85-86
+                raise IndexError("index (%d) out of range" % (k - 1))
+            idx = [i for i in range(k) if i != c]
             C_old = bool_product(U[:, idx], V[:, idx])         # AssoIter.py:86
             score, u = get_vector(X, C_old, V[:, c], w_fp, w_fn)
             U[:, c] = u                                        # AssoIter.py:60 (always)

@@ -23,7 +23,7 @@ SIGNATURES = {
     "bmf_device_info": [_p, _p, _p],
     "bmf_fill_zero": [_p, _i64, _p],
     "bmf_pack_csr": [_p, _p, _i64, _i64, C.c_int, _p, _i64, _p],
-    "bmf_expand_bits_i8": [_p, _i64, _i64, _i64, _i8, _i8, _p, _i64, _i64, _p],
+    "bmf_expand_bits_i8": [_p, _p, _i64, _i64, _i64, _i8, _i8, _p, _i64, _i64, _p],
     "bmf_assoc_counts_popc": [_p, _i64, _i64, _p, _i64, _p],
     "bmf_gemm_i8_nt": [_p, _i64, _p, _i64, _i64, _p, _i64, _p],
     "bmf_assoc_counts_i8": [_p, _i64, _i64, _i64, _p, _i64, _p],

@@ -28,9 +28,9 @@ __global__ void pack_csr_kernel(const int64_t* __restrict__ indptr, const int32_
 }
 
 // 16 bits -> 16 int8 per thread, one 128-bit store
-__global__ void expand_bits_i8_kernel(const uint64_t* __restrict__ bits, int64_t rows, int64_t ncols,
-                                      int64_t words, int one, int zero, int8_t* __restrict__ plane,
-                                      int64_t rows_pad, int64_t ld) {
+__global__ void expand_bits_i8_kernel(const uint64_t* __restrict__ bits, const uint64_t* __restrict__ mask,
+                                      int64_t rows, int64_t ncols, int64_t words, int one, int zero,
+                                      int8_t* __restrict__ plane, int64_t rows_pad, int64_t ld) {
   const int64_t chunks = ld >> 4;
   const int64_t total = rows_pad * chunks;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -41,9 +41,10 @@ __global__ void expand_bits_i8_kernel(const uint64_t* __restrict__ bits, int64_t
     if (r < rows && c0 < ncols) {
       const int64_t w = c0 >> 6;
       const uint32_t b16 = (w < words) ? (uint32_t)((bits[r * words + w] >> (c0 & 63)) & 0xffffu) : 0u;
+      const uint32_t k16 = (mask != nullptr && w < words) ? (uint32_t)((mask[r * words + w] >> (c0 & 63)) & 0xffffu) : 0u;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        int v = (c0 + i < ncols) ? (((b16 >> i) & 1u) ? one : zero) : 0;
+        int v = (c0 + i < ncols && !((k16 >> i) & 1u)) ? (((b16 >> i) & 1u) ? one : zero) : 0;
         out[i >> 2] |= (uint32_t)(uint8_t)(int8_t)v << ((i & 3) * 8);
       }
     }
@@ -520,17 +521,17 @@ extern "C" int bmf_pack_csr(const int64_t* indptr, const int32_t* indices, int64
   return 0;
 }
 
-extern "C" int bmf_expand_bits_i8(const uint64_t* bits, int64_t rows, int64_t ncols, int64_t words,
-                                  int8_t one, int8_t zero, int8_t* plane, int64_t rows_pad, int64_t ld,
-                                  bmf_stream_t stream) {
+extern "C" int bmf_expand_bits_i8(const uint64_t* bits, const uint64_t* mask_bits, int64_t rows, int64_t ncols,
+                                  int64_t words, int8_t one, int8_t zero, int8_t* plane, int64_t rows_pad,
+                                  int64_t ld, bmf_stream_t stream) {
   BMF_REQUIRE(bits && plane, "bmf_expand_bits_i8: null pointer");
   BMF_REQUIRE(ld % 128 == 0 && ld >= ncols && rows_pad >= rows && rows >= 0, "bmf_expand_bits_i8: bad ld / rows_pad");
   if (rows_pad == 0) return 0;
   const int64_t total = rows_pad * (ld >> 4);
   int64_t blocks = ceil_div(total, 256);
   if (blocks > (int64_t)num_sms() * 64) blocks = (int64_t)num_sms() * 64;
-  expand_bits_i8_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(bits, rows, ncols, words, one, zero,
-                                                                       plane, rows_pad, ld);
+  expand_bits_i8_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(bits, mask_bits, rows, ncols, words, one,
+                                                                       zero, plane, rows_pad, ld);
   BMF_LAUNCH_CHECK("bmf_expand_bits_i8");
   return 0;
 }

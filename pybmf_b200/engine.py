@@ -1,0 +1,239 @@
+"""Device-resident state of one Asso fit: bit-packed X and cover, candidate basis, int8 operand
+planes, and the per-step launch sequence  score-all -> (all-reduce) -> argmax -> apply.
+
+Rows of X are sharded across ranks when torch.distributed is initialised (one process per
+GPU); the candidate basis, V and the greedy decisions are replicated.  Integer partial
+gains are summed with ONE all-reduce per greedy step, so every rank sees identical
+totals and takes the identical lowest-index strict argmax.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import _native, device
+
+ROW_ALIGN = 256        # shard boundaries are multiples of the MMA N tile (and of 64-bit u words)
+
+
+def integer_weights(w_fp, w_fn, max_int=127, max_shift=30):
+    """(a, b, s) with w_fp = a/2^s and w_fn = b/2^s exactly and 0 <= a, b <= 127, else None.
+
+    When it exists, every product and sum of the reference's fp64 score expression
+    (PyBMF/utils/metrics.py:201) is exact, so `s_new > s_old` <=> b*P - a*N > 0 and the
+    score is 2^-s times an integer: one signed int8 contraction decides everything."""
+    for s in range(max_shift + 1):
+        a, b = w_fp * (1 << s), w_fn * (1 << s)
+        if a == int(a) and b == int(b):
+            a, b = int(a), int(b)
+            if 0 <= a <= max_int and 0 <= b <= max_int and (a | b):
+                return a, b, s
+            return None
+    return None
+
+
+class ShardPlan:
+    """Contiguous row ranges per rank, aligned to ROW_ALIGN (pure host logic, CPU-testable)."""
+
+    def __init__(self, m: int, world: int):
+        per = device.round_up(-(-m // max(world, 1)), ROW_ALIGN)
+        self.m, self.world = m, world
+        self.bounds = [(min(r * per, m), min((r + 1) * per, m)) for r in range(world)]
+
+    def rows(self, rank: int):
+        return self.bounds[rank]
+
+
+def dist_ctx():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def all_reduce_sum(t):
+    """In-place integer SUM across ranks (NCCL on GPU tensors, gloo on CPU tensors in tests)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+class CoverEngine:
+    """All device buffers and kernel launches behind Asso.init_model / Asso._fit."""
+
+    def __init__(self, X: sp.csr_matrix, w_fp: float, w_fn: float, scorer: str = "auto", assoc: str = "auto"):
+        _native.require_gpu()
+        self.rank, self.world = dist_ctx()
+        self.m, self.n = X.shape
+        self.plan = ShardPlan(self.m, self.world)
+        r0, r1 = self.plan.rows(self.rank)
+        self.r0, self.r1 = r0, r1
+        self.m_loc = r1 - r0
+        Xl = device.to_csr_pattern(X[r0:r1] if self.world > 1 else X)
+        self.sum_x = int(X.nnz) if self.world == 1 else int(device.to_csr_pattern(X).nnz)
+        self.w_fp, self.w_fn = float(w_fp), float(w_fn)
+        iw = integer_weights(self.w_fp, self.w_fn)
+        self.wa, self.wb, self.shift = iw if iw else (0, 0, 0)
+        self.integer_mode = iw is not None
+        if scorer == "auto":
+            scorer = "tcgen05" if self.integer_mode else "popc"
+        if scorer == "tcgen05" and not self.integer_mode:
+            raise ValueError("the tcgen05 scorer needs weights of the form a/2^s, b/2^s with a, b <= 127; "
+                             "use scorer='popc' for w_fp=%r, w_fn=%r" % (w_fp, w_fn))
+        assert scorer in ("tcgen05", "popc") and assoc in ("auto", "tcgen05", "popc")
+        self.scorer = scorer
+        self.assoc_kind = "tcgen05" if assoc == "auto" else assoc
+
+        self.words = device.words_for(self.n)
+        self.words_m = device.words_for(max(self.m_loc, 1))
+        self.ld = device.round_up(self.n, 128)                  # K extent of the cover planes
+        m_alloc = max(self.m_loc, 1)
+        self._ip, self._ix = device.upload_csr(Xl)
+        self.x_bits = device.pack_csr(self._ip, self._ix, self.m_loc, self.n)
+        self.c_bits = device.zeros((m_alloc, self.words), torch.int64)
+        self.tp_old = device.zeros((m_alloc,), torch.int32)
+        self.fp_old = device.zeros((m_alloc,), torch.int32)
+        self.alive = device.zeros((self.n,), torch.uint8)
+        self.basis_bits = device.zeros((self.n, self.words), torch.int64)
+        self.cand_pad = device.round_up(self.n, 128)
+        self.cand_plane = None
+        self.rows_plane = None
+        self.gain_p = device.zeros((self.cand_pad,), torch.int64)
+        self.gain_n = device.zeros((self.cand_pad,), torch.int64)
+        self.record = device.zeros((8,), torch.int64)           # [winner, score bits, used, sumP, sumN]
+        self.u_cols = []                                        # device bit vectors, one per chosen factor
+        self.cnt = None
+        self.tp_tot = 0
+        self.fp_tot = 0
+        self.launches = 0
+
+    # ---- association + basis (Asso.py:191-235) -------------------------------------------------
+    def build_basis(self, tau: float):
+        n, m_loc = self.n, self.m_loc
+        n_pad = device.round_up(n, 256)
+        cnt = device.zeros((n_pad, n_pad), torch.int32)
+        if m_loc > 0:
+            xt_bits = device.pack_csr(self._ip, self._ix, m_loc, n, transposed=True)
+            if self.assoc_kind == "tcgen05":
+                xt_plane = device.expand_bits_i8(xt_bits, n, m_loc, 1, 0, 256)
+                _native.call("bmf_assoc_counts_i8", xt_plane, n, n_pad, xt_plane.shape[1], cnt, n_pad)
+                del xt_plane
+            else:
+                _native.call("bmf_assoc_counts_popc", xt_bits, n, xt_bits.shape[1], cnt, n_pad)
+            self.launches += 3
+            del xt_bits
+        all_reduce_sum(cnt)
+        self.cnt = cnt
+        if self.scorer == "tcgen05":
+            self.cand_plane = device.zeros((self.cand_pad, self.ld), torch.int8)
+        _native.call("bmf_basis_threshold", cnt, n_pad, n, float(tau), self.basis_bits, self.words,
+                     self.cand_plane, self.ld, self.alive)
+        self.launches += 1
+        if self.scorer == "tcgen05":
+            self._rebuild_rows_plane()
+        return int(self.alive.sum().item())
+
+    def _rebuild_rows_plane(self):
+        """rows_plane[i][k] = 0 if covered, +wb if x, -wa otherwise (the signed operand of D = wb*P - wa*N)."""
+        self.rows_plane = device.expand_bits_i8(self.x_bits, self.m_loc, self.n, self.wb, -self.wa, 256,
+                                                mask=self.c_bits, out=self.rows_plane)
+        self.launches += 1
+
+    def assoc_host(self):
+        """The reference's `assoc` attribute (n x n float64) from the device counts."""
+        n = self.n
+        cnt = self.cnt[:n, :n].cpu().numpy().astype(np.float64)
+        s = np.diag(cnt).copy()
+        out = np.zeros_like(cnt)
+        nz = s > 0
+        out[nz] = cnt[nz] / s[nz][:, None]
+        return out
+
+    def basis_host(self):
+        """Remaining candidate rows (alive only, original order) as uint8 [nb, n]."""
+        B = device.bits_to_host(self.basis_bits, self.n)
+        return B[self.alive.cpu().numpy().astype(bool)]
+
+    # ---- one greedy step (Asso.py:62-110) ------------------------------------------------------
+    def score_all(self):
+        if self.scorer == "tcgen05":
+            _native.call("bmf_cover_score_i8", self.cand_plane, self.cand_pad, self.rows_plane,
+                         self.rows_plane.shape[0], self.ld, self.gain_p)
+        else:
+            _native.call("bmf_cover_score_popc", self.x_bits, self.c_bits, self.m_loc, self.n, self.words,
+                         self.basis_bits, self.alive, self.tp_old, self.fp_old, self.wa, self.wb, self.w_fp,
+                         self.w_fn, self.gain_p, self.gain_n)
+        self.launches += 1
+        all_reduce_sum(self.gain_p)
+        if not self.integer_mode:
+            all_reduce_sum(self.gain_n)
+
+    def select_and_apply(self, best_score: float):
+        """argmax + apply without a host round trip in between; one small D2H read at the end.
+        Returns (winner, score, n_used, sum_p, sum_n) with winner = -1 when nothing beats best_score."""
+        base_int = self.wb * self.tp_tot - self.wa * self.fp_tot
+        scale = 1.0 / float(1 << self.shift)
+        self.record.zero_()
+        _native.call("bmf_select_first_max", self.gain_p, self.gain_n if not self.integer_mode else None, self.alive,
+                     self.n, self.wa, self.wb, base_int, scale, self.w_fp, self.w_fn, self.tp_tot, self.fp_tot,
+                     float(best_score), self.record)
+        u_bits = device.zeros((self.words_m,), torch.int64)
+        _native.call("bmf_cover_apply", self.x_bits, self.c_bits, self.m_loc, self.n, self.words, self.basis_bits,
+                     self.alive, self.record, self.tp_old, self.fp_old, self.wa, self.wb, self.w_fp, self.w_fn,
+                     self.rows_plane, self.ld, u_bits, self.record[2:5])
+        self.launches += 2
+        if self.world > 1:
+            all_reduce_sum(self.record[2:5])
+        rec = self.record.cpu().numpy()
+        winner = int(rec[0])
+        if winner < 0:
+            return -1, float(best_score), 0, 0, 0
+        score = float(rec[1:2].view(np.float64)[0])
+        used, sp_, sn_ = int(rec[2]), int(rec[3]), int(rec[4])
+        self.u_cols.append(u_bits)
+        self.tp_tot += sp_
+        self.fp_tot += sn_
+        return winner, score, used, sp_, sn_
+
+    def basis_row_host(self, j: int) -> np.ndarray:
+        return device.words_to_dense(self.basis_bits[j:j + 1].cpu().numpy(), self.n)[0]
+
+    def used_column_host(self, idx: int) -> np.ndarray:
+        """Column idx of U (all ranks' rows) as uint8 [m]."""
+        local = device.words_to_dense(self.u_cols[idx].cpu().numpy().reshape(1, -1), self.m_loc)[0] \
+            if self.m_loc > 0 else np.zeros(0, np.uint8)
+        if self.world == 1:
+            return local
+        import torch.distributed as dist
+        parts = [None] * self.world
+        dist.all_gather_object(parts, local)
+        return np.concatenate(parts)
+
+    # ---- cover rebuilt from a factor list (after the reference's truncation quirk D1) -----------
+    def reset_cover(self, kept):
+        """Recompute c_bits / tp_old / fp_old / rows_plane from the factors in `kept`, a list of
+        (u_col index, basis row index): the reference recomputes X_pd from the (possibly
+        truncated) U, V at the top of every step (Asso.py:80, BaseModelTools.py:392-393)."""
+        self.c_bits.zero_()
+        self.tp_old.zero_()
+        self.fp_old.zero_()
+        self.tp_tot = self.fp_tot = 0
+        if kept and self.m_loc > 0:
+            k = len(kept)
+            kw = (k + 63) // 64
+            cols = [device.words_to_dense(self.u_cols[ui].cpu().numpy().reshape(1, -1), self.m_loc)[0]
+                    for (ui, _j) in kept]
+            uw = torch.from_numpy(device.dense_to_words(np.stack(cols, axis=1), words=kw)).to(device.dev())
+            vt = torch.stack([self.basis_bits[j] for (_ui, j) in kept]).contiguous()
+            _native.call("bmf_bool_product", uw, self.m_loc, kw, vt, k, self.words, self.c_bits)
+            counts = device.zeros((3,), torch.int64)
+            _native.call("bmf_confusion_bits", self.x_bits, self.c_bits, self.m_loc, self.words, counts,
+                         self.tp_old, self.fp_old)
+            self.launches += 2
+            all_reduce_sum(counts)
+            c = counts.cpu().numpy()
+            self.tp_tot, self.fp_tot = int(c[0]), int(c[1])
+        if self.scorer == "tcgen05":
+            self._rebuild_rows_plane()

@@ -1,0 +1,501 @@
+"""`Asso` and `AssoIter` with the reference's constructor / fit() API, computed on a B200.
+
+Host-side mirror of PyBMF/models/{BaseModel,BaseModelTools,Asso,AssoIter}.py: same parameters,
+attributes (`U`, `V` lil float64, `X_pd` csr int64, `logs` dict of DataFrames with the
+3-level (split, 0, name) columns, `assoc`, `basis`, `name`, `time`), same early-stop
+behaviour including the reference's quirks D1/D2, written fresh around the
+C-ABI kernels of libbmf_b200.so.  Nothing here falls back to a CPU implementation.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import re
+import time
+from itertools import product
+
+import numpy as np
+import pandas as pd
+import scipy.sparse as sp
+import torch
+from scipy.sparse import csr_matrix, hstack, lil_matrix
+
+from . import _native, device
+from . import utils as U_
+from .engine import CoverEngine, all_reduce_sum, dist_ctx, integer_weights
+
+CONFIG_KEYS = ("task", "seed", "display", "verbose", "scaling", "pixels", "show_logs", "save_model", "show_result")
+SILENT = bool(int(os.environ.get("PYBMF_B200_SILENT", "0")))
+
+
+def _say(*a):
+    if not SILENT:
+        print(*a)
+
+
+class BaseModel:
+    """fit() template of PyBMF/models/BaseModel.py:44-119 + BaseModelTools.py."""
+
+    # ---- parameters / configuration (BaseModelTools.py:16-175) -------------------------------
+    def check_params(self, **kwargs):
+        self.set_params(**kwargs)
+        self.set_config(**kwargs)
+
+    def set_params(self, **kwargs):
+        for name, value in kwargs.items():
+            if name in CONFIG_KEYS:
+                continue
+            setattr(self, name, value)
+            shown = len(value) if isinstance(value, list) else (value.shape if U_.ismat(value) else value)
+            _say("[I] {:<12} : {}".format(name, shown))
+
+    def set_config(self, **kwargs):
+        if "task" in kwargs:
+            task = kwargs["task"]
+            assert task in ["prediction", "reconstruction"], "Eval task must be 'prediction' or 'reconstruction'."
+            self.task = task
+            _say("[I] task         :", self.task)
+        if "seed" in kwargs:
+            seed = kwargs["seed"]
+            if seed is None and not hasattr(self, "seed"):
+                seed = int(time.time())
+            if seed is not None:
+                self.seed = seed
+                self.rng = np.random.RandomState(seed)
+                _say("[I] seed         :", self.seed)
+        for flag in ("verbose", "display"):
+            if not hasattr(self, flag):
+                setattr(self, flag, False)
+                _say("[I] {:<12} :".format(flag), False)
+            if flag in kwargs and kwargs[flag] != getattr(self, flag):
+                setattr(self, flag, kwargs[flag])
+                _say("[I] {:<12} :".format(flag), kwargs[flag])
+        self.scaling = kwargs["scaling"] if ("scaling" in kwargs and self.display) else 1.0
+        self.pixels = kwargs["pixels"] if ("pixels" in kwargs and self.display) else 2
+        for flag in ("show_logs", "save_model", "show_result"):      # default True, BaseModelTools.py:160-175
+            setattr(self, flag, kwargs.get(flag, True))
+            if flag in kwargs:
+                _say("[I] {:<12} :".format(flag), kwargs[flag])
+
+    def import_model(self, **kwargs):
+        """BaseModelTools.py:261-272."""
+        for attr, value in kwargs.items():
+            setattr(self, attr, value)
+            self.print_msg("Overwrote model parameter: {}".format(attr))
+
+    def print_msg(self, msg, type="I"):
+        if self.verbose:
+            _say("[{}] {}".format(type, msg))
+
+    # ---- data (BaseModel.py:123-150) ---------------------------------------------------------
+    def load_dataset(self, X_train, X_val=None, X_test=None):
+        if X_train is None:
+            raise TypeError("Missing training data.")
+        if X_val is None:
+            _say("[I] Missing validation data.")
+        if X_test is None:
+            _say("[W] Missing testing data.")
+        self.X_train = U_.to_sparse(X_train, "csr")
+        self.X_val = None if X_val is None else U_.to_sparse(X_val, "csr")
+        self.X_test = None if X_test is None else U_.to_sparse(X_test, "csr")
+        self.m, self.n = self.X_train.shape
+
+    def fit(self, X_train, X_val=None, X_test=None, **kwargs):
+        self.check_params(**kwargs)
+        self.load_dataset(X_train=X_train, X_val=X_val, X_test=X_test)
+        self.init_model()
+
+    def init_model(self):
+        self._init_factors()
+        self._init_logs()
+        self._start_timer()
+        self._make_name()
+
+    def _init_factors(self):
+        if hasattr(self, "U") or hasattr(self, "V"):
+            _say("[I] U, V existed. Skipping initialization.")
+            return
+        k = self.k if (hasattr(self, "k") and self.k is not None) else 1
+        self.U = lil_matrix((self.m, k))
+        self.V = lil_matrix((self.n, k))
+
+    def _init_logs(self):
+        if not hasattr(self, "logs"):
+            self.logs = {}
+
+    def _start_timer(self):
+        self.time = time.time()
+
+    def _stop_timer(self):
+        if not hasattr(self, "time"):
+            _say("[W] Timer not started.")
+            return
+        self.seconds = time.time() - self.time
+        hours, rest = divmod(self.seconds, 3600)
+        minutes, seconds = divmod(rest, 60)
+        text = ("%dh" % hours if hours > 0 else "") + ("%dm" % minutes if minutes > 0 else "") + "%ds" % seconds
+        _say("[I] time elapsed : ", text)
+        self.time = text
+
+    def _make_name(self):
+        if not hasattr(self, "name"):
+            cls = re.split(r"[`\-=~!@#$%^&*()_+\[\]{};'\\:\"|<,./<>?]", str(type(self)))[-3]
+            self.name = pd.Timestamp.now().strftime("%Y-%m-%d %H-%M-%S-%f ") + cls
+            _say("[I] name         :", self.name)
+
+    # ---- factors (BaseModelTools.py:366-405) --------------------------------------------------
+    def set_factors(self, k, u, v):
+        if self.U.shape[1] < k + 1:
+            self.extend_factors(k + 1)
+        self.U[:, k] = u
+        self.V[:, k] = v
+
+    def truncate_factors(self, k):
+        self.U = self.U[:, :k]
+        self.V = self.V[:, :k]
+
+    def extend_factors(self, k):
+        self.U = hstack([self.U, lil_matrix((self.m, k - self.U.shape[1]))]).tolil()
+        self.V = hstack([self.V, lil_matrix((self.n, k - self.V.shape[1]))]).tolil()
+
+    # ---- early stop (BaseModelTools.py:299-363), defects D1/D2 kept ----------------------------
+    def early_stop(self, error=None, diff=None, n_iter=None, n_factor=None, msg=None, k=None, verbose=True):
+        is_improving = True
+        if error is not None and hasattr(self, "tol") and error <= self.tol:
+            self._early_stop(msg="Error <= tolerance", verbose=verbose, k=k)
+            is_improving = False
+        if n_iter is not None and hasattr(self, "max_iter") and n_iter > self.max_iter:
+            self._early_stop(msg="Reach maximum iteration", verbose=verbose, k=k)
+            is_improving = False
+        if diff is not None and hasattr(self, "min_diff") and diff < self.min_diff:
+            self._early_stop(msg="Difference lower than threshold", verbose=verbose, k=k)
+            is_improving = False
+        if n_factor is not None and (hasattr(self, "k") and self.k is not None) and n_factor >= self.k:
+            self._early_stop(msg="Reach requested factor", verbose=verbose)
+            is_improving = False
+        if msg is not None:
+            # the reference calls _early_stop(msg=msg, k=k) without `verbose` here
+            # (BaseModelTools.py:338-341 vs :346) and therefore raises TypeError: same behaviour.
+            self._early_stop(msg=msg, k=k)
+            is_improving = False
+        return is_improving
+
+    def _early_stop(self, msg, verbose, k=None):
+        if verbose:
+            _say("[W] Stopped in advance: " + msg)
+        if k is not None:
+            if verbose:
+                _say("[W] Obtained {} factor(s).".format(k))
+            self.truncate_factors(k)
+
+    # ---- evaluation (BaseModel.py:209-277) ----------------------------------------------------
+    def evaluate(self, df_name, head_info={}, train_info={}, val_info={}, test_info={},
+                 metrics=["Recall", "Precision", "Accuracy", "F1"], train_metrics=None, val_metrics=None,
+                 test_metrics=None, verbose=False):
+        train_metrics = metrics if train_metrics is None else train_metrics
+        val_metrics = metrics if val_metrics is None else val_metrics
+        test_metrics = metrics if test_metrics is None else test_metrics
+        columns = U_.header(list(head_info.keys()), levels=3)
+        results = list(head_info.values())
+        for name, info, mets in (("train", train_info, train_metrics), ("val", val_info, val_metrics),
+                                 ("test", test_info, test_metrics)):
+            if getattr(self, "X_" + name) is None:
+                continue
+            c, r = self._evaluate(name, info, mets)
+            columns += c
+            results += r
+        U_.record(df_dict=self.logs, df_name=df_name, columns=columns, records=results, verbose=verbose)
+
+    def _evaluate(self, name, info, metrics):
+        counts = self._split_counts(name)
+        results = U_.metrics_from_counts(metrics, *counts)
+        columns = list(product([name], [0], list(info.keys()) + metrics))
+        return columns, list(info.values()) + results
+
+    def _split_counts(self, name):
+        """(TP, FP, FN, size) of the current factors against X_<name> under self.task
+        (evaluate_utils.py:32-52); counts come from bmf_confusion_factors / _triplets."""
+        X = getattr(self, "X_" + name)
+        Up, Vp = U_._pattern(self.U), U_._pattern(self.V)
+        uw, kw = U_._factor_words(Up)
+        if self.task == "reconstruction":                     # `self.task` unset -> AttributeError, as D6
+            G = U_._pattern(X)
+            m, n = G.shape
+            counts = device.zeros((3,), torch.int64)
+            vt = U_._bits_on_device(Vp.T.tocsr())
+            _native.call("bmf_confusion_factors", U_._bits_on_device(G), m, device.words_for(n), uw, kw, vt,
+                         Up.shape[1], counts, None, None)
+            tp, fp, fn = (int(v) for v in counts.cpu().numpy())
+            return tp, fp, fn, m * n
+        r, c, g = U_.to_triplet(X)
+        vw, _ = U_._factor_words(Vp)
+        counts = device.zeros((4,), torch.int64)
+        d = device.dev()
+        _native.call("bmf_confusion_triplets", torch.from_numpy(r.astype(np.int32)).to(d),
+                     torch.from_numpy(c.astype(np.int32)).to(d), torch.from_numpy((g != 0).astype(np.uint8)).to(d),
+                     len(g), uw, kw, vw, counts)
+        tp, fp, fn, _tn = (int(v) for v in counts.cpu().numpy())
+        return tp, fp, fn, len(g)
+
+    # ---- finish (BaseModel.py:104-119, BaseModelTools.py:217-259) ------------------------------
+    def finish(self, show_logs=True, save_model=True, show_result=True):
+        self._stop_timer()
+        if save_model:
+            self._save_model()
+        if show_result:
+            self._show_result()
+        if show_logs:
+            self._show_logs()
+
+    def _state_for_pickle(self):
+        return {k: v for k, v in self.__dict__.items() if not k.startswith("_dev")}
+
+    def __getstate__(self):
+        return self._state_for_pickle()
+
+    def _save_model(self, path=None, name=None):
+        name = self.name
+        if path is None:
+            root = os.path.join(os.path.expanduser("~"), ".pybmf", "saved_models")
+            os.makedirs(root, exist_ok=True)
+            path = os.path.join(root, name + ".pickle")
+        self.pickle_path = path
+        _ = self.X_pd                                           # the reference pickles X_pd with the rest
+        with open(path, "wb") as handle:
+            pickle.dump(self._state_for_pickle(), handle, protocol=pickle.HIGHEST_PROTOCOL)
+        _say("[I] model saved as: {}.pickle".format(name))
+
+    def _show_logs(self):
+        for log in self.logs.values():
+            if isinstance(log, pd.DataFrame):
+                with pd.option_context("display.max_rows", None, "display.max_columns", None):
+                    _say(log)
+
+    def _show_result(self):
+        _say("[W] show_result: matplotlib display is outside the accelerated path; skipped.")
+
+    def show_matrix(self, *a, **k):
+        _say("[W] show_matrix: matplotlib display is outside the accelerated path; skipped.")
+
+    # ---- lazily materialised containers --------------------------------------------------------
+    def __getattr__(self, name):
+        # only called when normal lookup fails: X_pd is produced on demand by the GPU product
+        d = self.__dict__
+        if name == "X_pd" and "U" in d and "V" in d:
+            d["X_pd"] = U_.get_prediction(U=self.U, V=self.V, boolean=True)
+            return d["X_pd"]
+        if name == "assoc" and "_dev_host_cnt" in d:            # Asso.py:207-212 from the device counts
+            cnt = d["_dev_host_cnt"].astype(np.float64)
+            s = np.diag(cnt).copy()
+            out = np.zeros_like(cnt)
+            out[s > 0] = cnt[s > 0] / s[s > 0][:, None]
+            d["assoc"] = lil_matrix(out)
+            return d["assoc"]
+        if name == "basis" and "_dev_host_basis" in d:          # candidates left after the fit (Asso.py:106-107)
+            d["basis"] = lil_matrix(d["_dev_host_basis"].astype(int))
+            return d["basis"]
+        raise AttributeError(name)
+
+    def predict_X(self, U=None, V=None, u=None, v=None, us=None, vs=None, boolean=True):
+        """BaseModel.py:153-191 (thresholds then Boolean product)."""
+        Um = (self.U if U is None else U).copy()
+        Vm = (self.V if V is None else V).copy()
+        if us is not None:
+            assert len(us) == Um.shape[1]
+            for i in range(Um.shape[1]):
+                Um[:, i] = U_.binarize(Um[:, i], us[i])
+        elif u is not None:
+            Um = U_.binarize(Um, u)
+        if vs is not None:
+            assert len(vs) == Vm.shape[1]
+            for i in range(Vm.shape[1]):
+                Vm[:, i] = U_.binarize(Vm[:, i], vs[i])
+        elif v is not None:
+            Vm = U_.binarize(Vm, v)
+        self.X_pd = U_.matmul(Um, Vm.T, boolean=boolean, sparse=True)
+
+
+def _column(vec, n):
+    """uint8 vector -> (n x 1) csr float64, the container set_factors() assigns from."""
+    idx = np.flatnonzero(vec)
+    return csr_matrix((np.ones(len(idx)), (idx, np.zeros(len(idx), dtype=np.int64))), shape=(n, 1))
+
+
+class Asso(BaseModel):
+    """The Asso algorithm (Miettinen et al., the discrete basis problem) -- PyBMF/models/Asso.py:10-140.
+
+    Parameters are the reference's: `tau`, `k=None`, `tol=0`, `w_fp=0.5`, `w_fn=None` (= 1 - w_fp).
+    Extra keyword-only knobs of this build (not in the reference): `scorer` in
+    {'auto', 'tcgen05', 'popc'} and `assoc_kernel` in {'auto', 'tcgen05', 'popc'} choose
+    between the tensor-core and the bit-packed popcount kernels (both sm_100a CUDA).
+    """
+
+    def __init__(self, tau, k=None, tol=0, w_fp=0.5, w_fn=None, *, scorer="auto", assoc_kernel="auto"):
+        self._scorer, self._assoc_kernel = scorer, assoc_kernel
+        self.check_params(tau=tau, k=k, tol=tol, w_fp=w_fp, w_fn=w_fn)
+
+    def fit(self, X_train, X_val=None, X_test=None, **kwargs):
+        super().fit(X_train, X_val, X_test, **kwargs)
+        try:
+            self._fit()
+        finally:
+            self._release_device()
+        self.__dict__.pop("X_pd", None)                        # recomputed lazily from the final U, V (Asso.py:44)
+        self.finish(show_logs=self.show_logs, save_model=self.save_model, show_result=self.show_result)
+
+    # ---- init_model: association matrix and candidate basis (Asso.py:48-59, 191-235) -----------
+    def init_model(self):
+        super().init_model()
+        w_fn = 1 - self.w_fp if self.w_fn is None else self.w_fn
+        self._dev = CoverEngine(self.X_train, self.w_fp, w_fn, scorer=self._scorer, assoc=self._assoc_kernel)
+        self._dev_nb = self._dev.build_basis(self.tau)
+        self.__dict__.pop("assoc", None)
+        self.__dict__.pop("basis", None)
+
+    def _release_device(self):
+        dev = self.__dict__.pop("_dev", None)
+        if dev is not None:
+            # keep what the lazy `assoc` / `basis` attributes need, as host arrays
+            self._dev_launches = dev.launches
+            if dev.n <= 8192 and dev.cnt is not None:
+                self._dev_host_cnt = dev.cnt[: dev.n, : dev.n].cpu().numpy()
+                self._dev_host_basis = dev.basis_host()
+        self.__dict__.pop("_dev_nb", None)
+
+    # ---- the greedy loop (Asso.py:62-140) ------------------------------------------------------
+    def _fit(self):
+        dev = self._dev
+        m, n = self.m, self.n
+        size = m * n
+        k = 0
+        is_improving = True
+        best_score = 0
+        kept = []                     # (engine column id, basis row) behind each column of self.U, None = zero column
+        n_basis = self._dev_nb
+        need_reset = False
+        while is_improving:
+            best_score = 0 if k == 0 else best_score
+            if n_basis == 0:
+                is_improving = self.early_stop(msg="Candidate list is empty", k=k)
+                break
+            if need_reset:                                   # factors were truncated (D1): cover = current U o V^T
+                dev.reset_cover([f for f in kept if f is not None])
+                need_reset = False
+            dev.score_all()
+            winner, score, used, sum_p, sum_n = dev.select_and_apply(best_score)
+            if winner < 0:
+                is_improving = self.early_stop(msg="No pattern found.", k=k)
+                break
+            best_score = score
+            col = dev.used_column_host(len(dev.u_cols) - 1)
+            row = dev.basis_row_host(winner)
+            self.set_factors(k, _column(col, m), _column(row, n))
+            while len(kept) < self.U.shape[1]:
+                kept.append(None)
+            kept[k] = (len(dev.u_cols) - 1, winner)
+            n_basis -= 1
+
+            tp, fp = dev.tp_tot, dev.fp_tot
+            fn = dev.sum_x - tp
+            score_05 = -0.5 * np.array(fp, dtype=np.int64) + 0.5 * np.array(tp, dtype=np.int64)   # Asso.py:119
+            desc_len = 1 * (self.U.sum() + self.V.sum()) + 1 * np.array(fp, dtype=np.int64) + 1 * np.array(fn, dtype=np.int64)
+            self._dev_counts = (tp, fp, fn, size)
+            self.evaluate(
+                df_name="updates", head_info={"k": k},
+                train_info={"score": best_score, "score_0.5": score_05, "desc_len": desc_len,
+                            "shape": [col.sum(), row.sum()]},
+                metrics=["TP", "TPR", "FP", "FPR", "FN", "FNR", "ERR", "ACC", "Recall", "Precision", "F1"],
+                verbose=self.verbose)
+            err = U_.rates(tp, fp, fn, size)["ERR"]
+            ncols_before = self.U.shape[1]
+            is_improving = self.early_stop(error=err, k=k)     # Asso.py:135 (0-based k: quirk D1)
+            if self.U.shape[1] != ncols_before:
+                kept = kept[: self.U.shape[1]]
+                need_reset = True
+            is_improving = self.early_stop(n_factor=k + 1)     # Asso.py:136 overwrites the flag
+            k += 1
+        self.__dict__.pop("_dev_counts", None)
+
+    def _split_counts(self, name):
+        # the training split's counts are already on the host (integer counters of the cover state)
+        if name == "train" and "_dev_counts" in self.__dict__ and self.task == "reconstruction":
+            return self._dev_counts
+        return super()._split_counts(name)
+
+
+class AssoIter(Asso):
+    """Asso with iterative refinement of the columns of U -- PyBMF/models/AssoIter.py:12-100."""
+
+    def __init__(self, model, w_fp=0.5, w_fn=None):
+        self.check_params(model=model, w_fp=w_fp, w_fn=w_fn)
+
+    def check_params(self, **kwargs):
+        super().check_params(**kwargs)
+        if "model" in kwargs:
+            model = kwargs.get("model")
+            self.import_model(k=model.k, U=model.U, V=model.V, logs=model.logs)   # by reference (D7)
+
+    def fit(self, X_train, X_val=None, X_test=None, **kwargs):
+        BaseModel.fit(self, X_train, X_val, X_test, **kwargs)
+        self.__dict__.pop("X_pd", None)
+        self._fit()
+        self.__dict__.pop("X_pd", None)
+        self.finish(show_logs=self.show_logs, save_model=self.save_model, show_result=self.show_result)
+
+    def init_model(self):
+        BaseModel.init_model(self)
+
+    def _fit(self):
+        _native.require_gpu()
+        m, n = self.m, self.n
+        size = m * n
+        w_fp = self.w_fp
+        w_fn = 1 - self.w_fp if self.w_fn is None else self.w_fn
+        iw = integer_weights(float(w_fp), float(w_fn))
+        wa, wb, _s = iw if iw else (0, 0, 0)
+        X = device.to_csr_pattern(self.X_train)
+        sum_x = int(X.nnz)
+        x_bits = U_._bits_on_device(X)
+        words = device.words_for(n)
+        kU = self.U.shape[1]
+        uw, kw = U_._factor_words(U_._pattern(self.U))
+        vt = U_._bits_on_device(U_._pattern(self.V).T.tocsr())
+        counts = device.zeros((3,), torch.int64)
+        _native.call("bmf_confusion_factors", x_bits, m, words, uw, kw, vt, kU, counts, None, None)
+        tp, fp, _fn = (int(v) for v in counts.cpu().numpy())
+        best_score = -w_fp * np.array(fp, dtype=np.int64) + w_fn * np.array(tp, dtype=np.int64)   # AssoIter.py:52
+        best_error = U_.rates(tp, fp, sum_x - tp, size)["ERR"]
+        n_stop = 0
+        is_improving = True
+        out = device.zeros((5,), torch.int64)
+        while is_improving:
+            for k in range(self.k):
+                if self.k > kU:                                                   # U[:, idx] in AssoIter.py:85-86
+                    raise IndexError("index (%d) out of range" % (self.k - 1))
+                out.zero_()
+                _native.call("bmf_refine_column", x_bits, m, n, words, uw, kw, vt, kU, k, wa, wb, float(w_fp),
+                             float(w_fn), out)
+                o = out.cpu().numpy()
+                tp, fp = int(o[0]), int(o[1])
+                score = -w_fp * np.array(fp, dtype=np.int64) + w_fn * np.array(tp, dtype=np.int64)
+                col = ((uw[:, k // 64] >> (k % 64)) & 1).to(torch.uint8).cpu().numpy()
+                self.U[:, k] = _column(col, m)                                    # AssoIter.py:60: always replaced
+                self.__dict__.pop("X_pd", None)
+                fn = sum_x - tp
+                error = U_.rates(tp, fp, fn, size)["ERR"]
+                if error < best_error:
+                    _say("[I] Refined column i: {}, error: {:.4f} -> {:.4f}, score: {:.2f} -> {:.2f}.".format(
+                        k, best_error, error, float(best_score), float(score)))
+                    best_error, best_score = error, score
+                    self._dev_counts = (tp, fp, fn, size)
+                    self.evaluate(df_name="refinements", head_info={"k": k},
+                                  train_info={"score": best_score, "error": best_error})
+                    n_stop = 0
+                else:
+                    n_stop += 1
+                    _say("[I] Skipped column i: {}.".format(k))
+                    if n_stop == self.k:
+                        _say("[I] Error stops decreasing.")
+                        is_improving = False
+                        break
+        self.__dict__.pop("_dev_counts", None)

@@ -1,0 +1,234 @@
+"""GPU: the reference-facing API (pybmf_b200.models.Asso / AssoIter, pybmf_b200.utils.*) against
+the golden vectors of the genuine reference and against the oracle on seeded inputs.
+Bars: U, V, integer counts and -- for weights of the form a/2^s -- every logged float are
+bit-exact; for other weights the logged `score` is compared with rtol 1e-12."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from conftest import LOG_COLS, load_golden  # noqa: E402
+from oracle import asso_oracle as O  # noqa: E402
+
+FIT_KW = dict(task="reconstruction", save_model=False, show_logs=False, show_result=False)
+EXACT_CASES = ["ex01_6", "c1_clean", "c1_noisy", "planted_w025"]
+GENERAL_CASES = ["planted_w02", "planted_w37"]
+
+
+@pytest.fixture(scope="module")
+def M():
+    from pybmf_b200 import _native, models
+    _native.require_gpu()
+    models.SILENT = True
+    return models
+
+
+def _dense(A):
+    return (np.asarray(A.todense()) != 0).astype(np.uint8)
+
+
+def _fit(M, c, **kw):
+    mdl = M.Asso(tau=c["tau"], k=c["k"], w_fp=c["w_fp"], w_fn=c["w_fn"], **kw)
+    mdl.fit(sp.csr_matrix(c["X"]), **FIT_KW)
+    return mdl
+
+
+def _check_logs(df, g, exact_score=True):
+    for col in LOG_COLS:
+        got = np.array([float(v) for v in df[("train", 0, col)]], dtype=np.float64)
+        if exact_score or col not in ("score",):
+            assert np.array_equal(got, g["log_" + col]), col
+        else:
+            np.testing.assert_allclose(got, g["log_" + col], rtol=1e-12, atol=0)
+    shape = np.array([[int(a), int(b)] for a, b in df[("train", 0, "shape")]], dtype=np.int64).reshape(-1, 2)
+    assert np.array_equal(shape, g["log_shape"])
+    assert list(df[("", "k", "")] if ("", "k", "") in df.columns else df.iloc[:, 1]) == list(range(len(df)))
+
+
+@pytest.mark.parametrize("name", EXACT_CASES)
+@pytest.mark.parametrize("scorer,assoc", [("tcgen05", "tcgen05"), ("popc", "popc")])
+def test_asso_matches_reference_bit_exact(M, name, scorer, assoc):
+    c = load_golden(name)
+    g = c["g"]
+    mdl = _fit(M, c, scorer=scorer, assoc_kernel=assoc)
+    assert mdl.U.shape == g["U"].shape and np.array_equal(_dense(mdl.U), g["U"])
+    assert mdl.V.shape == g["V"].shape and np.array_equal(_dense(mdl.V), g["V"])
+    assert sp.isspmatrix_lil(mdl.U) and mdl.U.dtype == np.float64
+    _check_logs(mdl.logs["updates"], g)
+    X_pd = mdl.X_pd
+    assert sp.isspmatrix_csr(X_pd) and X_pd.dtype == np.int64
+    assert np.array_equal(_dense(X_pd), O.bool_product(g["U"], g["V"]))
+
+
+@pytest.mark.parametrize("name", GENERAL_CASES)
+def test_asso_general_weights(M, name):
+    c = load_golden(name)
+    g = c["g"]
+    mdl = _fit(M, c)                                               # auto -> popcount scorer, fp64 row test
+    assert np.array_equal(_dense(mdl.U), g["U"]) and np.array_equal(_dense(mdl.V), g["V"])
+    _check_logs(mdl.logs["updates"], g, exact_score=False)
+    with pytest.raises(ValueError):
+        M.Asso(tau=c["tau"], k=c["k"], w_fp=c["w_fp"], w_fn=c["w_fn"], scorer="tcgen05").fit(
+            sp.csr_matrix(c["X"]), **FIT_KW)
+
+
+def test_known_answer_table_ex01_6(M):
+    """numbers typed from /root/reference/examples/ex01_6_logs.ipynb:253-361"""
+    c = load_golden("ex01_6")
+    df = _fit(M, c).logs["updates"]
+    assert [float(v) for v in df[("train", 0, "score")]] == [817.5, 1564.5, 2182.5, 2797.5, 2953.0]
+    assert [list(map(int, v)) for v in df[("train", 0, "shape")]] == [[71, 151], [63, 152], [24, 226], [24, 223], [23, 189]]
+    assert [int(v) for v in df[("train", 0, "TP")]] == [6178, 11713, 15043, 18334, 18938]
+
+
+def test_d2_no_pattern_raises_like_reference(M):
+    c = load_golden("d2_no_pattern")
+    g = c["g"]
+    mdl = M.Asso(tau=c["tau"], k=c["k"], w_fp=c["w_fp"])
+    with pytest.raises(TypeError):
+        mdl.fit(sp.csr_matrix(c["X"]), **FIT_KW)
+    assert mdl.U.shape == g["U"].shape and np.array_equal(_dense(mdl.U), g["U"])
+    _check_logs(mdl.logs["updates"], g)
+
+
+def test_empty_candidate_list_and_missing_data(M):
+    c = load_golden("planted_w025")
+    with pytest.raises(TypeError):                                  # tau >= 1 -> no basis row survives (D2 path)
+        M.Asso(tau=1.0, k=2).fit(sp.csr_matrix(c["X"]), **FIT_KW)
+    with pytest.raises(TypeError, match="Missing training data"):
+        M.Asso(tau=0.5, k=2).fit(None, **FIT_KW)
+    with pytest.raises(AssertionError):
+        M.Asso(tau=0.5, k=2).fit(sp.csr_matrix(c["X"]), task="bogus")
+
+
+@pytest.mark.parametrize("name", ["ex01_6", "c1_noisy", "planted_w02", "planted_w025"])
+def test_assoiter_matches_reference(M, name):
+    c = load_golden(name)
+    g = c["g"]
+    mdl = _fit(M, c)
+    it = M.AssoIter(model=mdl, w_fp=c["w_fp"], w_fn=c["w_fn"])
+    it.fit(sp.csr_matrix(c["X"]), **FIT_KW)
+    assert it.U is mdl.U                                            # reference quirk D7: refined in place
+    assert np.array_equal(_dense(it.U), g["iter_U"])
+    accepted = [int(r) for r, a in g["iter_trace"] if a == 1]
+    if accepted:
+        df = it.logs["refinements"]
+        assert [int(v) for v in df.iloc[:, 1]] == accepted
+        exact = O.integer_weights(c["w_fp"], c["w_fn"]) is not None
+        score = np.array([float(v) for v in df[("train", 0, "score")]])
+        if exact:
+            assert np.array_equal(score, g["iter_score"])
+        else:
+            np.testing.assert_allclose(score, g["iter_score"], rtol=1e-12)
+        assert np.array_equal(np.array([float(v) for v in df[("train", 0, "error")]]), g["iter_error"])
+        for col in ["Recall", "Precision", "Accuracy", "F1"]:
+            assert np.array_equal(np.array([float(v) for v in df[("train", 0, col)]]), g["iter_" + col])
+    else:
+        assert "refinements" not in it.logs
+
+
+def test_assoiter_after_truncation_raises_indexerror(M):
+    c = load_golden("c1_clean")
+    mdl = _fit(M, c)
+    assert mdl.U.shape == (1000, 4)                                 # quirk D1
+    with pytest.raises(IndexError):
+        M.AssoIter(model=mdl, w_fp=0.5).fit(sp.csr_matrix(c["X"]), **FIT_KW)
+
+
+def test_val_test_splits_and_prediction_task(M):
+    from pybmf_b200 import synth
+    X = synth.planted(150, 120, 4, 0.25, 0.25, 0.1, 0.02, seed=3)
+    rng = np.random.RandomState(0)
+    Xd = _dense(X)
+    val = sp.csr_matrix(Xd * (rng.rand(*Xd.shape) < 0.2))
+    # prediction task: stored triplets incl. explicit zeros (negative samples)
+    r = rng.randint(0, 150, 400); cc = rng.randint(0, 120, 400)
+    trip = sp.coo_matrix((Xd[r, cc].astype(float), (r, cc)), shape=Xd.shape)
+    for task, Xv in (("reconstruction", val), ("prediction", trip)):
+        mdl = M.Asso(tau=0.3, k=3, w_fp=0.5)
+        kw = dict(FIT_KW); kw["task"] = task
+        mdl.fit(X, X_val=Xv, X_test=Xv, **kw)
+        df = mdl.logs["updates"]
+        Ud, Vd = _dense(mdl.U), _dense(mdl.V)
+        for step in range(len(df)):
+            pd_ = O.bool_product(Ud[:, : step + 1], Vd[:, : step + 1])
+            if task == "reconstruction":
+                tp, fp, fn = O.confusion(_dense(Xv), pd_)
+                want = O.rates_from_counts(tp, fp, fn, Xd.size)
+            else:
+                coo = sp.coo_matrix(Xv); coo.sum_duplicates()
+                g = coo.data != 0; p = pd_[coo.row, coo.col] != 0
+                want = O.rates_from_counts(int((g & p).sum()), int((~g & p).sum()), int((g & ~p).sum()), len(g))
+            for split in ("val", "test"):
+                for col in ("TP", "FP", "FN", "TPR", "FPR", "ERR", "ACC", "Precision", "F1"):
+                    assert float(df[(split, 0, col)].iloc[step]) == float(want[col]), (task, split, col, step)
+
+
+def test_utils_route_to_kernels(M):
+    from pybmf_b200 import utils
+    rng = np.random.RandomState(4)
+    U = (rng.rand(210, 7) < 0.2).astype(int); V = (rng.rand(130, 7) < 0.2).astype(int)
+    gt = (rng.rand(210, 130) < 0.3).astype(int)
+    want = O.bool_product(U, V)
+    got = utils.matmul(sp.lil_matrix(U.astype(float)), sp.lil_matrix(V.astype(float)).T, sparse=True, boolean=True)
+    assert sp.isspmatrix_csr(got) and got.dtype == np.int64 and np.array_equal(_dense(got), want)
+    got_d = utils.matmul(U, V.T, boolean=True)
+    assert isinstance(got_d, np.ndarray) and got_d.dtype == np.int64 and np.array_equal(got_d, want)
+    assert np.array_equal(_dense(utils.get_prediction(sp.csr_matrix(U), sp.csr_matrix(V))), want)
+    with pytest.raises(AssertionError):
+        utils.matmul(U, V, boolean=True)
+    pd_ = sp.csr_matrix(want)
+    tp, fp, fn = O.confusion(gt, want)
+    assert int(utils.TP(sp.csr_matrix(gt), pd_)) == tp and int(utils.FP(sp.csr_matrix(gt), pd_)) == fp
+    assert int(utils.FN(sp.csr_matrix(gt), pd_)) == fn and int(utils.TN(gt, want)) == gt.size - tp - fp - fn
+    assert utils.TP(gt, want).shape == () and utils.TP(gt, want).dtype == np.int64
+    for axis in (0, 1):
+        a, b, c_ = O.confusion(gt, want, axis=axis)
+        assert np.array_equal(utils.TP(sp.csr_matrix(gt), pd_, axis=axis), a)
+        assert np.array_equal(utils.FP(sp.csr_matrix(gt), pd_, axis=axis), b)
+        assert np.array_equal(utils.FN(sp.csr_matrix(gt), pd_, axis=axis), c_)
+        assert np.array_equal(utils.coverage_score(gt, want, w_fp=0.2, axis=axis), -0.2 * b + 0.8 * a)
+    assert float(utils.coverage_score(gt, want, w_fp=0.5)) == -0.5 * fp + 0.5 * tp
+    r = O.rates_from_counts(tp, fp, fn, gt.size)
+    for name in ("TPR", "FPR", "PPV", "ACC", "ERR", "F1", "TNR", "FNR"):
+        assert float(getattr(utils, name)(sp.csr_matrix(gt), pd_)) == float(r[name])
+    assert float(utils.description_length(sp.csr_matrix(gt), sp.lil_matrix(U.astype(float)), sp.lil_matrix(V.astype(float)))) \
+        == float(U.sum() + V.sum() + fp + fn)
+    res = utils.eval(["TP", "FP", "Recall", "bogus"], "reconstruction", sp.csr_matrix(gt), U=sp.csr_matrix(U), V=sp.csr_matrix(V))
+    assert int(res[0]) == tp and int(res[1]) == fp and float(res[2]) == float(r["Recall"]) and res[3] is None
+    s = utils.add(sp.csr_matrix(gt), pd_, sparse=True, boolean=True)
+    assert s.dtype == np.float64 and np.array_equal(_dense(s), gt | want)
+    assert np.array_equal(_dense(utils.multiply(sp.csr_matrix(gt), pd_, boolean=True)), gt & want)
+
+
+def test_c2_shape_first_steps_match_oracle(M):
+    """BASELINE.json configs[1] shape (6040 x 3706, 4.5 %): first greedy steps against the oracle."""
+    from pybmf_b200 import synth
+    X = synth.config_c2()
+    mdl = M.Asso(tau=0.5, k=2, w_fp=0.5)
+    mdl.fit(X, **FIT_KW)
+    r = O.asso_fit(X, 2, 0.5, 0.5)
+    assert np.array_equal(_dense(mdl.U), r["U"]) and np.array_equal(_dense(mdl.V), r["V"])
+    df = mdl.logs["updates"]
+    for col in LOG_COLS:
+        assert [float(v) for v in df[("train", 0, col)]] == [float(l[col]) for l in r["logs"]], col
+
+
+def test_model_is_picklable_and_lazy_attrs(M, tmp_path):
+    import pickle
+    c = load_golden("planted_w025")
+    mdl = _fit(M, c)
+    blob = pickle.dumps(mdl)
+    back = pickle.loads(blob)
+    assert np.array_equal(_dense(back.U), _dense(mdl.U))
+    assert not any(k.startswith("_dev") for k in back.__dict__)
+    assoc = mdl.assoc
+    assert sp.isspmatrix_lil(assoc) and np.array_equal(assoc.toarray(), O.build_assoc(c["X"]))
+    B0, _ = O.build_basis(O.build_assoc(c["X"]), c["tau"])
+    assert mdl.basis.shape == (B0.shape[0] - c["k"], c["X"].shape[1])
+    mdl._save_model(path=str(tmp_path / "m.pickle"))
+    with open(tmp_path / "m.pickle", "rb") as fh:
+        d = pickle.load(fh)
+    assert "U" in d and "X_pd" in d

@@ -53,6 +53,10 @@ def test_expand_bits_i8(nat, rows, ncols, tile):
     want[:rows, :ncols] = np.where(A == 1, 3, -2)
     assert plane.shape == (device.round_up(rows, tile), device.round_up(ncols, 128))
     assert np.array_equal(plane, want)
+    K = _rand01(rng, rows, ncols, 0.3)                              # covered mask -> zeros
+    masked = device.expand_bits_i8(bits, rows, ncols, 3, -2, tile, mask=_dev(device.dense_to_words(K))).cpu().numpy()
+    want[:rows, :ncols][K == 1] = 0
+    assert np.array_equal(masked, want)
 
 
 @pytest.mark.parametrize("m,n", [(90, 70), (300, 500), (1000, 200)])
