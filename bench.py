@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Benchmark of the Asso hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|c1] [--impl reference]
+
+Metric: Asso cover-score throughput in Gop/s (algorithmic ops = 2*m*n*nb_t per greedy step,
+SURVEY.md section 8d) plus fit() seconds, on BASELINE.json's Netflix-shaped config (c4) by default.
+One "step" = one greedy Asso step over the whole (row-sharded) matrix: score every live
+candidate on the tensor cores -> one integer all-reduce -> argmax -> apply the winner.
+Inputs are resident in HBM for `value`; `e2e` is a whole Asso.fit() through the public API from a
+host scipy matrix (H2D, packing, association, k steps, D2H of factors and log counters).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (description, tau, w_fp, k of a fit)
+    "c4": ("Asso k=20 tau=0.5 w=[0.5,0.5], Netflix-shaped synthetic 480189x17770 @1.2% (BASELINE configs[3])", 0.5, 0.5, 20),
+    "c2": ("Asso k=20 tau=0.5 w=[0.5,0.5], MovieLens-1M-shaped synthetic 6040x3706 @4.5% (BASELINE configs[1])", 0.5, 0.5, 20),
+    "c1": ("Asso k=5 tau=0.5 w=[0.5,0.5], planted 1000x500 (BASELINE configs[0] shape)", 0.5, 0.5, 5),
+}
+
+
+def make_input(workload):
+    from pybmf_b200 import synth
+    if workload == "c4":
+        return synth.config_c4()
+    if workload == "c2":
+        return synth.config_c2()
+    return synth.planted(1000, 500, 5, 0.2, 0.2, 0.1, 0.02, seed=1000)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return p, "MEASURED_PEAKS.json"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        busy = [v for v in sm if v > 0.5 * (max(mx) if mx else 1)] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port timed on the host cores (a bounded sample of the same workload)
+# ----------------------------------------------------------------------------------------------
+def cpu_sample_setup(X, workload, tau):
+    """A bounded slice of the workload for the CPU arm: `rows` data rows x `cands` candidate rows.
+    The candidates are association rows of the sampled columns computed from the row sample."""
+    from oracle import asso_oracle as O
+    m, n = X.shape
+    rows, cands = {"c4": (2048, 1024), "c2": (2048, 1024), "c1": (1000, 500)}[workload]
+    rows, cands = min(rows, m), min(cands, n)
+    Xs = O.as_dense01(X[:rows])
+    A = O.build_assoc(Xs[:, :])[:cands]
+    B = (A > tau).astype(np.uint8)
+    C = np.zeros_like(Xs)
+    return Xs, C, B, "first %d rows x first %d candidate rows of the %s matrix, all %d columns" % (rows, cands, workload, n)
+
+
+def cpu_step(Xs, C, B, w_fp):
+    from oracle import asso_oracle as O
+    score, use, *_ = O.score_candidates(Xs, C, B, w_fp, None)
+    return 2.0 * Xs.shape[0] * Xs.shape[1] * B.shape[0], int(np.argmax(score))
+
+
+def run_cpu_arm(args, X, workload, tau, w_fp, standalone):
+    Xs, C, B, sample = cpu_sample_setup(X, workload, tau)
+    steps, warmup = (args.steps, args.warmup) if standalone else (2, 1)
+    for _ in range(warmup):
+        cpu_step(Xs, C, B, w_fp)
+    t0 = time.perf_counter()
+    ops = 0.0
+    for _ in range(steps):
+        o, _ = cpu_step(Xs, C, B, w_fp)
+        ops += o
+    dt = time.perf_counter() - t0
+    cores = os.cpu_count() or 1
+    return {"value": ops / dt / 1e9, "unit": "Gop/s", "cores": cores, "kind": "port",
+            "sample": sample + " per step; numpy/BLAS restatement oracle/asso_oracle.py (the Python reference cannot "
+                               "travel to the GPU box)", "seconds": dt, "steps": steps}
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=os.environ.get("BMF_BENCH_WORKLOAD", "c4"), choices=list(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scorer", default="tcgen05", choices=["tcgen05", "popc"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    desc, tau, w_fp, k_fit = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        X = make_input(args.workload)
+        cpu = run_cpu_arm(args, X, args.workload, tau, w_fp, standalone=True)
+        line = {"impl": "reference", "metric": "asso_cover_score_gops", "value": cpu["value"], "unit": "Gop/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * cpu["seconds"] / max(args.steps, 1), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32 BLAS counts + f64 weighting", "data": "synthetic",
+                "config": {"workload": desc, "m": X.shape[0], "n": X.shape[1], "nnz": int(X.nnz)},
+                "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cpu["value"], "unit": "Gop/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from pybmf_b200 import _native, models
+    from pybmf_b200.engine import CoverEngine
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    _native.require_gpu()
+    models.SILENT = True
+    peaks, peak_src = load_peaks()
+
+    X = make_input(args.workload)
+    m, n = X.shape
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident state: pack, association, basis (setup, timed separately) ---------------
+    barrier()
+    t0 = time.perf_counter()
+    eng = CoverEngine(X, w_fp, 1 - w_fp, scorer=args.scorer)
+    nb = eng.build_basis(tau)
+    barrier()
+    setup_s = time.perf_counter() - t0
+
+    stream = torch.cuda.current_stream()
+    score_ms, ops_per_step, nb_t = [], [], nb
+    best = 0.0
+
+    def greedy_step(timed):
+        nonlocal best, nb_t
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        eng.score_all()
+        e1.record(stream)
+        winner, score, used, sp_, sn_ = eng.select_and_apply(best)
+        if timed:
+            torch.cuda.synchronize()
+            score_ms.append(e0.elapsed_time(e1))
+            ops_per_step.append(2.0 * m * n * nb_t)
+        if winner >= 0:
+            best = score
+            nb_t -= 1
+
+    for _ in range(args.warmup):
+        greedy_step(False)
+    sampler = ClockSampler(local_rank)
+    launches0 = eng.launches
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        greedy_step(True)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+    elapsed_s = float(elapsed_ms.item()) / 1e3
+    launches = eng.launches - launches0
+    total_ops = float(sum(ops_per_step))
+    value = total_ops / elapsed_s / 1e9
+
+    # ---- roofline of the dominant kernel (gemm_i8_kernel<EPI_GAIN>), this rank's share -----------
+    kern_ms = statistics.mean(score_ms) if score_ms else float("nan")
+    ops_launch = statistics.mean(ops_per_step) / world if ops_per_step else 0.0     # rows are sharded evenly
+    achieved = ops_launch / (kern_ms / 1e3) / 1e12
+    peak_i8 = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_i8, "unit": "TFLOP/s", "frac": achieved / peak_i8,
+                "traffic": None, "kernel": "gemm_i8_kernel<EPI_GAIN> (tcgen05 kind::i8)" if args.scorer == "tcgen05" else "cover_score_popc_kernel",
+                "peak_source": "2 x bf16_tflops_sustained of %s (int8 dense = 2x bf16 on B200; int8 itself is not in that file)" % peak_src,
+                "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms * len(score_ms) / (elapsed_s * 1e3) if score_ms else None,
+                "algorithmic_ops_per_launch": ops_launch}
+    del eng
+    torch.cuda.empty_cache()
+
+    # ---- end to end: Asso.fit() through the public API from a host scipy matrix ------------------
+    e2e = None
+    if not args.no_e2e:
+        k_e2e = min(max(args.steps, 1), k_fit)
+        barrier()
+        t0 = time.perf_counter()
+        mdl = models.Asso(tau=tau, k=k_e2e, w_fp=w_fp, scorer=args.scorer)
+        err = None
+        try:
+            mdl.fit(X, task="reconstruction", save_model=False, show_logs=False, show_result=False)
+        except TypeError as e:                                  # the reference's D2 path ends the fit the same way
+            err = str(e)
+        torch.cuda.synchronize()
+        fit_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(fit_s, op=dist.ReduceOp.MAX)
+        fit_s = float(fit_s.item())
+        steps_done = len(mdl.logs["updates"]) if "updates" in mdl.logs else 0
+        ops_fit = sum(2.0 * m * n * (nb - t) for t in range(steps_done))
+        h2d = 8 * (X.shape[0] + 1) + 4 * int(X.nnz)             # indptr int64 + indices int32 (all ranks together)
+        d2h = steps_done * (8 * 8 + (m + 7) // 8 + 8 * ((n + 63) // 64))
+        e2e = {"value": ops_fit / fit_s / 1e9, "unit": "Gop/s", "fit_seconds": fit_s, "greedy_steps": steps_done,
+               "h2d_bytes_per_step": h2d / max(steps_done, 1), "d2h_bytes_per_step": d2h / max(steps_done, 1),
+               "includes": "csr H2D, bit packing, association X^T X + basis, %d greedy steps, U/V D2H, log rows" % steps_done,
+               "ended_with": err}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = run_cpu_arm(args, X, args.workload, tau, w_fp, standalone=False)
+
+    if rank == 0:
+        line = {"metric": "asso_cover_score_gops", "value": value, "unit": "Gop/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * elapsed_s / max(args.steps, 1), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "int8 x int8 -> int32 (counts), int64 gains, f64 score",
+                "data": "synthetic",
+                "config": {"workload": desc, "m": m, "n": n, "nnz": int(X.nnz), "candidates": nb, "scorer": args.scorer,
+                           "parallelism": "rows sharded over %d rank(s), one int64 all-reduce per step" % world,
+                           "l2": "operand planes (%.1f GB) exceed L2; no flush needed" % (m * float(n) / 1e9)},
+                "clocks": clocks, "gpu_launches": launches, "setup_seconds": setup_s,
+                "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+                "fit_seconds": e2e["fit_seconds"] if e2e else None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
