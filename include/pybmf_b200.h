@@ -138,6 +138,11 @@ int bmf_confusion_factors(const uint64_t* gt_bits, int64_t m, int64_t words, con
 /* same against a materialised prediction */
 int bmf_confusion_bits(const uint64_t* gt_bits, const uint64_t* pd_bits, int64_t m, int64_t words,
                        int64_t* counts, int32_t* row_tp, int32_t* row_fp, bmf_stream_t stream);
+/* add(boolean=True) / multiply(boolean=True), PyBMF/utils/boolean_utils.py:87-107 / 6-33, and the
+ * residual X AND NOT C of get_residual (PyBMF/utils/common.py:154-160):
+ * out = a OR b (op 0), a AND b (op 1), a AND NOT b (op 2) on [rows][words] bit matrices. */
+int bmf_bits_combine(const uint64_t* a_bits, const uint64_t* b_bits, int64_t rows, int64_t words, int op,
+                     uint64_t* out_bits, bmf_stream_t stream);
 /* eval(task='prediction'), PyBMF/utils/evaluate_utils.py:32-44: counts over stored triplets
  * (i, j, gt != 0); counts[0..3] += (TP, FP, FN, TN). */
 int bmf_confusion_triplets(const int32_t* rows, const int32_t* cols, const uint8_t* gt, int64_t nnz,

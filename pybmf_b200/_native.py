@@ -35,6 +35,7 @@ SIGNATURES = {
     "bmf_bool_product": [_p, _i64, _i64, _p, _i64, _i64, _p, _p],
     "bmf_confusion_factors": [_p, _i64, _i64, _p, _i64, _p, _i64, _p, _p, _p, _p],
     "bmf_confusion_bits": [_p, _p, _i64, _i64, _p, _p, _p, _p],
+    "bmf_bits_combine": [_p, _p, _i64, _i64, C.c_int, _p, _p],
     "bmf_confusion_triplets": [_p, _p, _p, _i64, _p, _i64, _p, _p, _p],
     "bmf_refine_column": [_p, _i64, _i64, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _f64, _f64, _p, _p],
 }

@@ -425,6 +425,20 @@ confusion_kernel(const uint64_t* __restrict__ gt, const uint64_t* __restrict__ p
   }
 }
 
+// elementwise Boolean algebra on bit rows: op 0 = OR (add), 1 = AND (multiply), 2 = AND-NOT (residual)
+__global__ void __launch_bounds__(256)
+bits_combine_kernel(const ulonglong2* __restrict__ a, const ulonglong2* __restrict__ b, int64_t pairs, int op,
+                    ulonglong2* __restrict__ out) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < pairs; t += (int64_t)gridDim.x * blockDim.x) {
+    const ulonglong2 x = __ldg(a + t), y = __ldg(b + t);
+    ulonglong2 r;
+    if (op == 0) { r.x = x.x | y.x; r.y = x.y | y.y; }
+    else if (op == 1) { r.x = x.x & y.x; r.y = x.y & y.y; }
+    else { r.x = x.x & ~y.x; r.y = x.y & ~y.y; }
+    out[t] = r;
+  }
+}
+
 __global__ void confusion_triplets_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ cols,
                                           const uint8_t* __restrict__ gt, int64_t nnz,
                                           const uint64_t* __restrict__ u_words, int64_t kw,
@@ -651,6 +665,20 @@ extern "C" int bmf_confusion_bits(const uint64_t* gt_bits, const uint64_t* pd_bi
       gt_bits, pd_bits, m, words, nullptr, 0, nullptr, reinterpret_cast<unsigned long long*>(counts), row_tp,
       row_fp);
   BMF_LAUNCH_CHECK("bmf_confusion_bits");
+  return 0;
+}
+
+extern "C" int bmf_bits_combine(const uint64_t* a_bits, const uint64_t* b_bits, int64_t rows, int64_t words, int op,
+                                uint64_t* out_bits, bmf_stream_t stream) {
+  BMF_REQUIRE(a_bits && b_bits && out_bits && rows > 0 && words > 0 && words % 2 == 0, "bmf_bits_combine: bad arguments");
+  BMF_REQUIRE(op >= 0 && op <= 2, "bmf_bits_combine: op must be 0 (or), 1 (and) or 2 (and-not)");
+  const int64_t pairs = rows * (words >> 1);
+  int64_t blocks = ceil_div(pairs, 256);
+  if (blocks > row_stream_grid() * 4) blocks = row_stream_grid() * 4;
+  bits_combine_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const ulonglong2*>(a_bits), reinterpret_cast<const ulonglong2*>(b_bits), pairs, op,
+      reinterpret_cast<ulonglong2*>(out_bits));
+  BMF_LAUNCH_CHECK("bmf_bits_combine");
   return 0;
 }
 

@@ -55,22 +55,25 @@ def words_to_dense(W: np.ndarray, ncols: int) -> np.ndarray:
 
 
 def to_csr_pattern(X) -> sp.csr_matrix:
-    """Non-zero pattern of X as canonical csr (sorted, no duplicates, no explicit zeros)."""
-    X = sp.csr_matrix(X)
-    X = X.copy()
-    X.sum_duplicates()
-    X.eliminate_zeros()
-    X.sort_indices()
+    """Non-zero pattern of X as canonical csr (sorted, no duplicates, no explicit zeros).
+    No copy is made when X is already a canonical csr without stored zeros (the common case)."""
+    X = X if sp.isspmatrix_csr(X) else sp.csr_matrix(X)
+    if not X.has_canonical_format:
+        X = X.copy()
+        X.sum_duplicates()
+    if X.nnz and np.count_nonzero(X.data) != X.nnz:
+        X = X.copy()
+        X.eliminate_zeros()
     return X
 
 
 # ---- device packing --------------------------------------------------------------------------
 def upload_csr(X: sp.csr_matrix):
-    """H2D copy of the pattern arrays through pinned staging (indptr int64, indices int32)."""
-    indptr = torch.from_numpy(np.ascontiguousarray(X.indptr.astype(np.int64)))
-    indices = torch.from_numpy(np.ascontiguousarray(X.indices.astype(np.int32)))
+    """H2D copy of the pattern arrays (indptr int64, indices int32); values are never read."""
     d = dev()
-    return (indptr.pin_memory().to(d, non_blocking=True), indices.pin_memory().to(d, non_blocking=True))
+    indptr = torch.from_numpy(np.ascontiguousarray(X.indptr.astype(np.int64, copy=False)))
+    indices = torch.from_numpy(np.ascontiguousarray(X.indices.astype(np.int32, copy=False)))
+    return indptr.to(d, non_blocking=True), indices.to(d, non_blocking=True)
 
 
 def pack_csr(indptr_d, indices_d, m: int, n: int, transposed: bool = False):

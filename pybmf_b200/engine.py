@@ -71,8 +71,9 @@ class CoverEngine:
         r0, r1 = self.plan.rows(self.rank)
         self.r0, self.r1 = r0, r1
         self.m_loc = r1 - r0
-        Xl = device.to_csr_pattern(X[r0:r1] if self.world > 1 else X)
-        self.sum_x = int(X.nnz) if self.world == 1 else int(device.to_csr_pattern(X).nnz)
+        Xp = device.to_csr_pattern(X)
+        Xl = Xp[r0:r1] if self.world > 1 else Xp
+        self.sum_x = int(Xp.nnz)
         self.w_fp, self.w_fn = float(w_fp), float(w_fn)
         iw = integer_weights(self.w_fp, self.w_fn)
         self.wa, self.wb, self.shift = iw if iw else (0, 0, 0)

@@ -157,22 +157,27 @@ def get_prediction(U, V, boolean=True, sparse=True):
 
 
 def _elementwise(X, Y, op):
+    """Bit-packed OR / AND / AND-NOT on the device (bmf_bits_combine); returns (bits, m, n)."""
+    _native.require_gpu()
     Xp, Yp = _pattern(X), _pattern(Y)
     assert Xp.shape == Yp.shape, "U and V should have the same shape"
-    return (Xp + Yp if op == "or" else Xp.multiply(Yp)).tocsr()
+    m, n = Xp.shape
+    out = device.zeros((max(m, 1), device.words_for(n)), torch.int64)
+    if m > 0:
+        _native.call("bmf_bits_combine", _bits_on_device(Xp), _bits_on_device(Yp), m, out.shape[1],
+                     {"or": 0, "and": 1, "andnot": 2}[op], out)
+    return out, m, n
 
 
 def add(X, Y, sparse=None, boolean=False):
     """`boolean_utils.add` (PyBMF/utils/boolean_utils.py:87-107): Boolean OR, returned as float64
-    (the reference casts `.astype(bool).astype(float)`).  Pattern union is pure index
-    bookkeeping on the host; no arithmetic of the hot path lives here (the cover update is fused
-    into bmf_cover_apply)."""
+    (the reference casts `.astype(bool).astype(float)`)."""
     if not boolean:
         raise NotImplementedError("only boolean=True is supported")
-    Z = _elementwise(X, Y, "or")
-    Z.data[:] = 1.0
-    Z = Z.astype(np.float64)
-    return check_sparse(Z, sparse=bool(sparse or issparse(X) or issparse(Y)))
+    bits, m, n = _elementwise(X, Y, "or")
+    if sparse or issparse(X) or issparse(Y):
+        return _bits_to_csr(bits, m, n, dtype=np.float64)
+    return device.bits_to_host(bits, n)[:m].astype(np.float64)
 
 
 def multiply(U, V, sparse=None, boolean=False):
@@ -180,10 +185,17 @@ def multiply(U, V, sparse=None, boolean=False):
     if not boolean:
         raise NotImplementedError("only boolean=True is supported")
     assert U.shape == V.shape, "U and V should have the same shape"
-    Z = _elementwise(U, V, "and").astype(np.int64)
+    bits, m, n = _elementwise(U, V, "and")
     if issparse(U) or issparse(V) or sparse:
-        return check_sparse(Z, sparse=sparse)
-    return check_sparse(Z.toarray().astype(int), sparse=sparse)
+        return check_sparse(_bits_to_csr(bits, m, n, dtype=np.int64), sparse=sparse)
+    return check_sparse(device.bits_to_host(bits, n)[:m].astype(int), sparse=sparse)
+
+
+def get_residual(X, U, V):
+    """`X AND NOT (U o V^T)` -- PyBMF/utils/common.py:154-160 (returns lil like the reference)."""
+    pattern = get_prediction(U, V, boolean=True)
+    bits, m, n = _elementwise(X, pattern, "andnot")
+    return lil_matrix(_bits_to_csr(bits, m, n, dtype=sp.csr_matrix(X).dtype))
 
 
 # --------------------------------------------------------------------------------------------

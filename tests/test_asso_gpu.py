@@ -201,6 +201,11 @@ def test_utils_route_to_kernels(M):
     s = utils.add(sp.csr_matrix(gt), pd_, sparse=True, boolean=True)
     assert s.dtype == np.float64 and np.array_equal(_dense(s), gt | want)
     assert np.array_equal(_dense(utils.multiply(sp.csr_matrix(gt), pd_, boolean=True)), gt & want)
+    d = utils.add(gt, want, boolean=True)
+    assert isinstance(d, np.ndarray) and d.dtype == np.float64 and np.array_equal(d, (gt | want).astype(float))
+    assert np.array_equal(utils.multiply(gt, want, boolean=True), gt & want)
+    res_ = utils.get_residual(sp.csr_matrix(gt), sp.csr_matrix(U), sp.csr_matrix(V))
+    assert sp.isspmatrix_lil(res_) and np.array_equal(_dense(res_), gt & (1 - want))
 
 
 def test_c2_shape_first_steps_match_oracle(M):
