@@ -13,6 +13,7 @@
 //   warp 0: TMA producer (one lane)      warp 1: TMEM allocator + MMA issuer (one lane)
 //   warps 2-5: epilogue (TMEM lane quadrant = warp_id % 4)
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "bmf_common.cuh"
 
@@ -320,7 +321,8 @@ static int launch_gemm(const int8_t* a, int64_t a_rows, const int8_t* b, int64_t
   const int mt = (int)(a_rows / BM), nt = (int)(b_rows / BN), kb = (int)(ld / BK);
   const int64_t tiles = (int64_t)mt * nt;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  const int group_m = 8;
+  int group_m = 8;                                        // candidate tiles per raster group (L2 reuse)
+  if (const char* e = getenv("BMF_GROUP_M")) { int v = atoi(e); if (v >= 1 && v <= 64) group_m = v; }
   gemm_i8_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, mt, nt, kb, group_m, gain, C, ldc);
   return check_cuda(cudaGetLastError(), "gemm_i8_kernel launch");
 }

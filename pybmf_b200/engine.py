@@ -159,7 +159,10 @@ class CoverEngine:
 
     # ---- one greedy step (Asso.py:62-110) ------------------------------------------------------
     def score_all(self):
-        if self.scorer == "tcgen05":
+        if self.m_loc == 0:                                   # a rank without rows only joins the exchange
+            self.gain_p.zero_()
+            self.gain_n.zero_()
+        elif self.scorer == "tcgen05":
             _native.call("bmf_cover_score_i8", self.cand_plane, self.cand_pad, self.rows_plane,
                          self.rows_plane.shape[0], self.ld, self.gain_p)
         else:
@@ -181,9 +184,10 @@ class CoverEngine:
                      self.n, self.wa, self.wb, base_int, scale, self.w_fp, self.w_fn, self.tp_tot, self.fp_tot,
                      float(best_score), self.record)
         u_bits = device.zeros((self.words_m,), torch.int64)
-        _native.call("bmf_cover_apply", self.x_bits, self.c_bits, self.m_loc, self.n, self.words, self.basis_bits,
-                     self.alive, self.record, self.tp_old, self.fp_old, self.wa, self.wb, self.w_fp, self.w_fn,
-                     self.rows_plane, self.ld, u_bits, self.record[2:5])
+        if self.m_loc > 0:
+            _native.call("bmf_cover_apply", self.x_bits, self.c_bits, self.m_loc, self.n, self.words, self.basis_bits,
+                         self.alive, self.record, self.tp_old, self.fp_old, self.wa, self.wb, self.w_fp, self.w_fn,
+                         self.rows_plane, self.ld, u_bits, self.record[2:5])
         self.launches += 2
         if self.world > 1:
             all_reduce_sum(self.record[2:5])
@@ -191,6 +195,8 @@ class CoverEngine:
         winner = int(rec[0])
         if winner < 0:
             return -1, float(best_score), 0, 0, 0
+        if self.m_loc == 0:
+            self.alive[winner] = 0                            # bmf_cover_apply does this on ranks that own rows
         score = float(rec[1:2].view(np.float64)[0])
         used, sp_, sn_ = int(rec[2]), int(rec[3]), int(rec[4])
         self.u_cols.append(u_bits)
@@ -201,16 +207,24 @@ class CoverEngine:
     def basis_row_host(self, j: int) -> np.ndarray:
         return device.words_to_dense(self.basis_bits[j:j + 1].cpu().numpy(), self.n)[0]
 
-    def used_column_host(self, idx: int) -> np.ndarray:
-        """Column idx of U (all ranks' rows) as uint8 [m]."""
-        local = device.words_to_dense(self.u_cols[idx].cpu().numpy().reshape(1, -1), self.m_loc)[0] \
-            if self.m_loc > 0 else np.zeros(0, np.uint8)
+    def gather_used_columns(self, ids) -> np.ndarray:
+        """Columns `ids` of U over ALL ranks' rows as uint8 [m, len(ids)] (one device all-gather)."""
+        if not ids:
+            return np.zeros((self.m, 0), np.uint8)
+        local = torch.stack([self.u_cols[i] for i in ids])                       # [c, words_m]
         if self.world == 1:
-            return local
+            return np.ascontiguousarray(device.words_to_dense(local.cpu().numpy(), self.m_loc).T)
         import torch.distributed as dist
-        parts = [None] * self.world
-        dist.all_gather_object(parts, local)
-        return np.concatenate(parts)
+        wmax = device.words_for(self.plan.rows(0)[1] - self.plan.rows(0)[0])
+        padded = device.zeros((len(ids), wmax), torch.int64)
+        padded[:, : local.shape[1]] = local
+        parts = [torch.empty_like(padded) for _ in range(self.world)]
+        dist.all_gather(parts, padded)
+        out = []
+        for r, part in enumerate(parts):
+            a0, a1 = self.plan.rows(r)
+            out.append(device.words_to_dense(part.cpu().numpy(), a1 - a0).T)
+        return np.ascontiguousarray(np.concatenate(out, axis=0))
 
     # ---- cover rebuilt from a factor list (after the reference's truncation quirk D1) -----------
     def reset_cover(self, kept):

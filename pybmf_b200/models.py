@@ -335,13 +335,66 @@ class Asso(BaseModel):
         self.check_params(tau=tau, k=k, tol=tol, w_fp=w_fp, w_fn=w_fn)
 
     def fit(self, X_train, X_val=None, X_test=None, **kwargs):
+        self.__dict__.pop("U", None)                           # a fit always starts from empty factors
+        self.__dict__.pop("V", None)
         super().fit(X_train, X_val, X_test, **kwargs)
         try:
             self._fit()
         finally:
+            self._materialize_factors(final=True)
             self._release_device()
         self.__dict__.pop("X_pd", None)                        # recomputed lazily from the final U, V (Asso.py:44)
         self.finish(show_logs=self.show_logs, save_model=self.save_model, show_result=self.show_result)
+
+    # ---- factors are kept as device bit columns during the fit and turned into the reference's
+    #      lil float64 containers when somebody reads them (BaseModelTools.py:274-288, 366-405) ----
+    def _init_factors(self):
+        ncols = self.k if (hasattr(self, "k") and self.k is not None) else 1
+        self._dev_kept = [None] * ncols                        # one entry per column of U / V, None = zero column
+
+    def truncate_factors(self, k):
+        if "_dev_kept" in self.__dict__:
+            self._dev_kept = self._dev_kept[:k]
+            self.__dict__.pop("U", None)
+            self.__dict__.pop("V", None)
+        else:
+            super().truncate_factors(k)
+
+    def _place_factor(self, k, entry):
+        kept = self._dev_kept
+        while len(kept) < k + 1:                               # extend_factors
+            kept.append(None)
+        kept[k] = entry
+        self.__dict__.pop("U", None)
+        self.__dict__.pop("V", None)
+
+    def _materialize_factors(self, final=False):
+        kept = self.__dict__.get("_dev_kept")
+        if kept is None:
+            return
+        dev = self.__dict__.get("_dev")
+        live = [(p, e) for p, e in enumerate(kept) if e is not None]
+        ncols = len(kept)
+        if live and dev is not None:
+            cols = dev.gather_used_columns([e["ui"] for _p, e in live])            # [m, len(live)] uint8
+            r, c = np.nonzero(cols)
+            pos = np.array([p for p, _e in live], dtype=np.int64)
+            Uc = csr_matrix((np.ones(len(r)), (r, pos[c])), shape=(self.m, ncols))
+            vr = [np.flatnonzero(e["row"]) for _p, e in live]
+            Vc = csr_matrix((np.ones(sum(len(v) for v in vr)),
+                             (np.concatenate(vr), np.repeat(pos, [len(v) for v in vr]))), shape=(self.n, ncols))
+        else:
+            Uc, Vc = csr_matrix((self.m, ncols)), csr_matrix((self.n, ncols))
+        self.__dict__["U"] = Uc.tolil()
+        self.__dict__["V"] = Vc.tolil()
+        if final:
+            self.__dict__.pop("_dev_kept", None)
+
+    def __getattr__(self, name):
+        if name in ("U", "V") and "_dev_kept" in self.__dict__:
+            self._materialize_factors()
+            return self.__dict__[name]
+        return super().__getattr__(name)
 
     # ---- init_model: association matrix and candidate basis (Asso.py:48-59, 191-235) -----------
     def init_model(self):
@@ -370,7 +423,6 @@ class Asso(BaseModel):
         k = 0
         is_improving = True
         best_score = 0
-        kept = []                     # (engine column id, basis row) behind each column of self.U, None = zero column
         n_basis = self._dev_nb
         need_reset = False
         while is_improving:
@@ -379,7 +431,7 @@ class Asso(BaseModel):
                 is_improving = self.early_stop(msg="Candidate list is empty", k=k)
                 break
             if need_reset:                                   # factors were truncated (D1): cover = current U o V^T
-                dev.reset_cover([f for f in kept if f is not None])
+                dev.reset_cover([(e["ui"], e["j"]) for e in self._dev_kept if e is not None])
                 need_reset = False
             dev.score_all()
             winner, score, used, sum_p, sum_n = dev.select_and_apply(best_score)
@@ -387,30 +439,29 @@ class Asso(BaseModel):
                 is_improving = self.early_stop(msg="No pattern found.", k=k)
                 break
             best_score = score
-            col = dev.used_column_host(len(dev.u_cols) - 1)
             row = dev.basis_row_host(winner)
-            self.set_factors(k, _column(col, m), _column(row, n))
-            while len(kept) < self.U.shape[1]:
-                kept.append(None)
-            kept[k] = (len(dev.u_cols) - 1, winner)
+            rowsum = int(row.sum())
+            self._place_factor(k, {"ui": len(dev.u_cols) - 1, "j": winner, "used": used, "rowsum": rowsum, "row": row})
             n_basis -= 1
 
             tp, fp = dev.tp_tot, dev.fp_tot
             fn = dev.sum_x - tp
-            score_05 = -0.5 * np.array(fp, dtype=np.int64) + 0.5 * np.array(tp, dtype=np.int64)   # Asso.py:119
-            desc_len = 1 * (self.U.sum() + self.V.sum()) + 1 * np.array(fp, dtype=np.int64) + 1 * np.array(fn, dtype=np.int64)
+            tp_a, fp_a, fn_a = (np.array(v, dtype=np.int64) for v in (tp, fp, fn))
+            score_05 = -0.5 * fp_a + 0.5 * tp_a                                     # Asso.py:119
+            u_sum = np.float64(sum(e["used"] for e in self._dev_kept if e is not None))
+            v_sum = np.float64(sum(e["rowsum"] for e in self._dev_kept if e is not None))
+            desc_len = 1 * (u_sum + v_sum) + 1 * fp_a + 1 * fn_a                    # Asso.py:120
             self._dev_counts = (tp, fp, fn, size)
             self.evaluate(
                 df_name="updates", head_info={"k": k},
                 train_info={"score": best_score, "score_0.5": score_05, "desc_len": desc_len,
-                            "shape": [col.sum(), row.sum()]},
+                            "shape": [used, rowsum]},
                 metrics=["TP", "TPR", "FP", "FPR", "FN", "FNR", "ERR", "ACC", "Recall", "Precision", "F1"],
                 verbose=self.verbose)
             err = U_.rates(tp, fp, fn, size)["ERR"]
-            ncols_before = self.U.shape[1]
+            ncols_before = len(self._dev_kept)
             is_improving = self.early_stop(error=err, k=k)     # Asso.py:135 (0-based k: quirk D1)
-            if self.U.shape[1] != ncols_before:
-                kept = kept[: self.U.shape[1]]
+            if len(self._dev_kept) != ncols_before:
                 need_reset = True
             is_improving = self.early_stop(n_factor=k + 1)     # Asso.py:136 overwrites the flag
             k += 1
@@ -444,6 +495,9 @@ class AssoIter(Asso):
 
     def init_model(self):
         BaseModel.init_model(self)
+
+    def _init_factors(self):
+        BaseModel._init_factors(self)
 
     def _fit(self):
         _native.require_gpu()
