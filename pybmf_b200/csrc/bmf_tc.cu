@@ -321,10 +321,244 @@ static int launch_gemm(const int8_t* a, int64_t a_rows, const int8_t* b, int64_t
   const int mt = (int)(a_rows / BM), nt = (int)(b_rows / BN), kb = (int)(ld / BK);
   const int64_t tiles = (int64_t)mt * nt;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  int group_m = 8;                                        // candidate tiles per raster group (L2 reuse)
+  int group_m = 16;                                       // candidate tiles per raster group (L2 reuse)
   if (const char* e = getenv("BMF_GROUP_M")) { int v = atoi(e); if (v >= 1 && v <= 64) group_m = v; }
   gemm_i8_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, mt, nt, kb, group_m, gain, C, ldc);
   return check_cuda(cudaGetLastError(), "gemm_i8_kernel launch");
+}
+
+
+// =================================================================================================
+// 2-SM variant: a CTA pair (cluster 2x1x1 on one TPC) computes a 256 x 256 tile with
+// tcgen05.mma.cta_group::2 (UMMA M = 256).  Each CTA stages ITS 128 candidate rows and ITS half
+// (128) of the tile's data rows, so every operand byte is fetched from L2 once per pair instead of
+// once per CTA, the per-CTA stage shrinks to 32 KB and the ring deepens to 6 stages.  Only the
+// leader CTA issues MMAs; TMA transactions of both CTAs complete on the leader's "full" barrier,
+// tcgen05.commit multicasts "empty"/"accumulator full" to both CTAs, and the epilogue warps of both
+// CTAs (each draining its own 128 TMEM lanes) arrive remotely on the leader's "accumulator empty".
+// =================================================================================================
+namespace sm2 {
+constexpr int BM2 = 256;                 // candidates per pair tile
+constexpr int HALF = 128;                // rows each CTA stages per operand
+constexpr int STAGES2 = 6;
+constexpr int OP_BYTES = HALF * BK;      // 16 KB
+constexpr int STAGE_BYTES2 = 2 * OP_BYTES;
+constexpr int SMEM_BYTES2 = STAGES2 * STAGE_BYTES2 + 1024 + 256;
+constexpr uint32_t IDESC_I8_2SM = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                  ((uint32_t)(BM2 >> 4) << 24);
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-pair bit of a shared::cluster address
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_2sm(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_i8_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t local_bar) {
+  // arrive on the barrier at the same offset in CTA rank 0 of the pair
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(local_bar));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_i8_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   int mt_total, int nt_total, int kb_total, int group_m, unsigned long long* __restrict__ gain,
+                   int32_t* __restrict__ C, int64_t ldc) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE_BYTES2);
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES2 + 4);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES2 + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES2 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES2 + 2 + a); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int64_t pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int64_t total_tiles = (int64_t)mt_total * nt_total;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();                                     // barriers of BOTH CTAs are initialised and visible
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_base_slot);
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs: own 128 candidate rows + own 128 data rows) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = pair; t < total_tiles; t += num_pairs) {
+        int mt, nt;
+        tile_coords(t, mt_total, nt_total, group_m, mt, nt);
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t leader_full = full_bar(stage) & PEER_MASK;
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES2);     // bytes of both CTAs
+          const uint32_t a_dst = smem_base + stage * STAGE_BYTES2;
+          tma_load_2d_2sm(a_dst, &tmap_a, leader_full, kb * BK, mt * BM2 + (int)rank * HALF);
+          tma_load_2d_2sm(a_dst + OP_BYTES, &tmap_b, leader_full, kb * BK, nt * BN + (int)rank * HALF);
+          if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (leader && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t t = pair; t < total_tiles; t += num_pairs) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_base + stage * STAGE_BYTES2;
+          const uint64_t da = make_smem_desc(a_addr), db = make_smem_desc(a_addr + OP_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            tcgen05_mma_i8_2sm(d_tmem, da + (uint64_t)(k * (UMMA_K >> 4)), db + (uint64_t)(k * (UMMA_K >> 4)),
+                               IDESC_I8_2SM, (uint32_t)((kb | k) != 0));
+          tcgen05_commit_2sm(empty_bar(stage));           // frees the slot in BOTH CTAs
+          if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+        }
+        tcgen05_commit_2sm(tfull_bar(acc));               // accumulator halves ready in BOTH CTAs
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue warps (both CTAs; CTA r owns candidates [r*128, r*128+128) of the tile) =====
+    const int quad = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t t = pair; t < total_tiles; t += num_pairs) {
+      int mt, nt;
+      tile_coords(t, mt_total, nt_total, group_m, mt, nt);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      const int64_t row = (int64_t)mt * BM2 + (int64_t)rank * HALF + quad * 32 + lane;
+      long long relu_sum = 0;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+        if (EPI == EPI_GAIN) {
+          int part = 0;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) part += max((int)v[q], 0);
+          relu_sum += part;
+        } else {
+          int4* dst = reinterpret_cast<int4*>(C + row * ldc + (int64_t)nt * BN + c * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            dst[q] = make_int4((int)v[4 * q], (int)v[4 * q + 1], (int)v[4 * q + 2], (int)v[4 * q + 3]);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tempty_bar(acc)); // 8 arrivals (4 warps x 2 CTAs) free the accumulator
+      if (EPI == EPI_GAIN && relu_sum != 0) atomicAdd(gain + row, (unsigned long long)relu_sum);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();                                     // nobody leaves while the pair still shares smem / TMEM
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+template <int EPI>
+static int launch_gemm_2sm(const int8_t* a, int64_t a_rows, const int8_t* b, int64_t b_rows, int64_t ld,
+                           unsigned long long* gain, int32_t* C, int64_t ldc, cudaStream_t stream) {
+  CUtensorMap ma, mb;
+  int rc = make_plane_map(&ma, a, a_rows, ld, HALF);
+  if (rc) return rc;
+  rc = make_plane_map(&mb, b, b_rows, ld, HALF);
+  if (rc) return rc;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[EPI]) {
+    rc = check_cuda(cudaFuncSetAttribute(gemm_i8_2sm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES2),
+                    "cudaFuncSetAttribute(gemm_i8_2sm_kernel)");
+    if (rc) return rc;
+    attr_set[EPI] = true;
+  }
+  const int mt = (int)(a_rows / BM2), nt = (int)(b_rows / BN), kb = (int)(ld / BK);
+  const int64_t tiles = (int64_t)mt * nt;
+  const int pairs_max = num_sms() / 2;
+  const int pairs = (int)(tiles < pairs_max ? tiles : pairs_max);
+  int group_m = 8;                                        // 256-row candidate tiles per raster group
+  if (const char* e = getenv("BMF_GROUP_M2")) { int v = atoi(e); if (v >= 1 && v <= 64) group_m = v; }
+  gemm_i8_2sm_kernel<EPI><<<2 * pairs, NUM_THREADS, SMEM_BYTES2, stream>>>(ma, mb, mt, nt, kb, group_m, gain, C, ldc);
+  return check_cuda(cudaGetLastError(), "gemm_i8_2sm_kernel launch");
+}
+}  // namespace sm2
+
+// variant: 0 = auto (2-SM when the candidate rows are a multiple of 256), 1 = 1-SM, 2 = 2-SM
+template <int EPI>
+static int dispatch_gemm(int variant, const int8_t* a, int64_t a_rows, const int8_t* b, int64_t b_rows, int64_t ld,
+                         unsigned long long* gain, int32_t* C, int64_t ldc, cudaStream_t stream) {
+  if (const char* e = getenv("BMF_GEMM_VARIANT")) { int v = atoi(e); if (v == 1 || v == 2) variant = v; }
+  const bool ok2 = (a_rows % sm2::BM2) == 0;
+  if (variant == 2 && !ok2) {
+    set_error("2-SM int8 kernel needs the candidate rows padded to a multiple of 256 (got %lld)", (long long)a_rows);
+    return BMF_E_ARG;
+  }
+  if (variant == 2 || (variant == 0 && ok2))
+    return sm2::launch_gemm_2sm<EPI>(a, a_rows, b, b_rows, ld, gain, C, ldc, stream);
+  return launch_gemm<EPI>(a, a_rows, b, b_rows, ld, gain, C, ldc, stream);
 }
 
 }  // namespace tc
@@ -339,7 +573,7 @@ extern "C" int bmf_gemm_i8_nt(const int8_t* a_plane, int64_t a_rows_pad, const i
   BMF_REQUIRE(b_rows_pad > 0 && b_rows_pad % tc::BN == 0, "bmf_gemm_i8_nt: b rows must be a positive multiple of 256");
   BMF_REQUIRE(ld > 0 && ld % tc::BK == 0, "bmf_gemm_i8_nt: ld must be a positive multiple of 128");
   BMF_REQUIRE(ldc >= b_rows_pad && ldc % 4 == 0, "bmf_gemm_i8_nt: ldc must cover b rows and be a multiple of 4");
-  return tc::launch_gemm<tc::EPI_STORE>(a_plane, a_rows_pad, b_plane, b_rows_pad, ld, nullptr, c, ldc, as_stream(stream));
+  return tc::dispatch_gemm<tc::EPI_STORE>(0, a_plane, a_rows_pad, b_plane, b_rows_pad, ld, nullptr, c, ldc, as_stream(stream));
 }
 
 extern "C" int bmf_assoc_counts_i8(const int8_t* xt_plane, int64_t n, int64_t n_pad, int64_t ld, int32_t* cnt,
@@ -348,8 +582,7 @@ extern "C" int bmf_assoc_counts_i8(const int8_t* xt_plane, int64_t n, int64_t n_
   BMF_REQUIRE(n_pad >= n && n_pad % tc::BN == 0, "bmf_assoc_counts_i8: n_pad must be a multiple of 256 covering n");
   BMF_REQUIRE(ld > 0 && ld % tc::BK == 0, "bmf_assoc_counts_i8: ld must be a positive multiple of 128");
   BMF_REQUIRE(ldc >= n_pad && ldc % 4 == 0, "bmf_assoc_counts_i8: ldc must be >= n_pad and a multiple of 4");
-  const int64_t a_rows = ceil_div(n, tc::BM) * tc::BM;    // <= n_pad
-  return tc::launch_gemm<tc::EPI_STORE>(xt_plane, a_rows, xt_plane, n_pad, ld, nullptr, cnt, ldc, as_stream(stream));
+  return tc::dispatch_gemm<tc::EPI_STORE>(0, xt_plane, n_pad, xt_plane, n_pad, ld, nullptr, cnt, ldc, as_stream(stream));
 }
 
 extern "C" int bmf_cover_score_i8(const int8_t* cand_plane, int64_t cand_pad, const int8_t* rows_plane,
@@ -360,6 +593,6 @@ extern "C" int bmf_cover_score_i8(const int8_t* cand_plane, int64_t cand_pad, co
   BMF_REQUIRE(ld > 0 && ld % tc::BK == 0, "bmf_cover_score_i8: ld must be a positive multiple of 128");
   int rc = check_cuda(cudaMemsetAsync(gain, 0, sizeof(int64_t) * cand_pad, as_stream(stream)), "bmf_cover_score_i8");
   if (rc) return rc;
-  return tc::launch_gemm<tc::EPI_GAIN>(cand_plane, cand_pad, rows_plane, rows_pad, ld,
-                                       reinterpret_cast<unsigned long long*>(gain), nullptr, 0, as_stream(stream));
+  return tc::dispatch_gemm<tc::EPI_GAIN>(0, cand_plane, cand_pad, rows_plane, rows_pad, ld,
+                                         reinterpret_cast<unsigned long long*>(gain), nullptr, 0, as_stream(stream));
 }

@@ -98,7 +98,7 @@ class CoverEngine:
         self.fp_old = device.zeros((m_alloc,), torch.int32)
         self.alive = device.zeros((self.n,), torch.uint8)
         self.basis_bits = device.zeros((self.n, self.words), torch.int64)
-        self.cand_pad = device.round_up(self.n, 128)
+        self.cand_pad = device.round_up(self.n, 256)           # multiple of 256 -> the 2-SM (cta_group::2) kernel
         self.cand_plane = None
         self.rows_plane = None
         self.gain_p = device.zeros((self.cand_pad,), torch.int64)

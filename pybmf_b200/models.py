@@ -281,8 +281,12 @@ class BaseModel:
     def __getattr__(self, name):
         # only called when normal lookup fails: X_pd is produced on demand by the GPU product
         d = self.__dict__
-        if name == "X_pd" and "U" in d and "V" in d:
-            d["X_pd"] = U_.get_prediction(U=self.U, V=self.V, boolean=True)
+        if name == "X_pd":
+            try:
+                U, V = self.U, self.V
+            except AttributeError:
+                raise AttributeError(name) from None
+            d["X_pd"] = U_.get_prediction(U=U, V=V, boolean=True)
             return d["X_pd"]
         if name == "assoc" and "_dev_host_cnt" in d:            # Asso.py:207-212 from the device counts
             cnt = d["_dev_host_cnt"].astype(np.float64)
@@ -355,8 +359,8 @@ class Asso(BaseModel):
     def truncate_factors(self, k):
         if "_dev_kept" in self.__dict__:
             self._dev_kept = self._dev_kept[:k]
-            self.__dict__.pop("U", None)
-            self.__dict__.pop("V", None)
+            for name in ("U", "V", "_host_factors"):
+                self.__dict__.pop(name, None)
         else:
             super().truncate_factors(k)
 
@@ -365,10 +369,12 @@ class Asso(BaseModel):
         while len(kept) < k + 1:                               # extend_factors
             kept.append(None)
         kept[k] = entry
-        self.__dict__.pop("U", None)
-        self.__dict__.pop("V", None)
+        for name in ("U", "V", "_host_factors"):
+            self.__dict__.pop(name, None)
 
     def _materialize_factors(self, final=False):
+        """Device bit columns -> host csr (cheap); the reference's lil float64 containers are built
+        from that csr the first time `U` / `V` is read (csr -> lil of a 480189-row matrix costs ~0.5 s)."""
         kept = self.__dict__.get("_dev_kept")
         if kept is None:
             return
@@ -385,16 +391,29 @@ class Asso(BaseModel):
                              (np.concatenate(vr), np.repeat(pos, [len(v) for v in vr]))), shape=(self.n, ncols))
         else:
             Uc, Vc = csr_matrix((self.m, ncols)), csr_matrix((self.n, ncols))
-        self.__dict__["U"] = Uc.tolil()
-        self.__dict__["V"] = Vc.tolil()
+        self.__dict__.pop("U", None)
+        self.__dict__.pop("V", None)
+        self._host_factors = (Uc, Vc)
         if final:
             self.__dict__.pop("_dev_kept", None)
 
     def __getattr__(self, name):
-        if name in ("U", "V") and "_dev_kept" in self.__dict__:
-            self._materialize_factors()
-            return self.__dict__[name]
+        d = self.__dict__
+        if name in ("U", "V"):
+            if "_dev_kept" in d and "_dev" in d:
+                self._materialize_factors()
+            if "_host_factors" in d:
+                Uc, Vc = d["_host_factors"]
+                d["U"], d["V"] = Uc.tolil(), Vc.tolil()
+                if "_dev_kept" not in d:
+                    del d["_host_factors"]
+                return d[name]
         return super().__getattr__(name)
+
+    def _state_for_pickle(self):
+        if "_host_factors" in self.__dict__:
+            _ = self.U                                          # pickles carry the lil factors like the reference's
+        return {k: v for k, v in self.__dict__.items() if not k.startswith("_dev") and k != "_host_factors"}
 
     # ---- init_model: association matrix and candidate basis (Asso.py:48-59, 191-235) -----------
     def init_model(self):

@@ -70,11 +70,24 @@ def test_assoc_counts_popc(nat, m, n):
     assert np.array_equal(cnt.cpu().numpy().astype(np.int64), O.assoc_counts(A))
 
 
+@pytest.fixture
+def gemm_variant(request, monkeypatch):
+    """BMF_GEMM_VARIANT: 1 = one CTA per tile (cta_group::1), 2 = CTA pair (cta_group::2)."""
+    monkeypatch.setenv("BMF_GEMM_VARIANT", str(request.param))
+    return request.param
+
+
+@pytest.mark.parametrize("gemm_variant", [1, 2], indirect=True)
 @pytest.mark.parametrize("ma,nb,k", [(128, 256, 128), (128, 256, 512), (256, 512, 384), (384, 256, 1152),
-                                      (1280, 2304, 640)])
-def test_gemm_i8_tcgen05_exact(nat, ma, nb, k):
+                                      (256, 256, 128), (512, 768, 2048), (1280, 2304, 640), (19200, 2560, 256)])
+def test_gemm_i8_tcgen05_exact(nat, ma, nb, k, gemm_variant):
     """tcgen05 kind::i8 + TMA + TMEM primitive on random signed int8 (catches descriptor/swizzle bugs)."""
     _native, device = nat
+    if gemm_variant == 2 and ma % 256:
+        with pytest.raises(ValueError):
+            _native.call("bmf_gemm_i8_nt", device.zeros((ma, k), torch.int8), ma, device.zeros((nb, k), torch.int8), nb,
+                         k, device.zeros((ma, nb), torch.int32), nb)
+        return
     rng = np.random.RandomState(ma + nb + k)
     A = rng.randint(-128, 128, size=(ma, k)).astype(np.int8)
     B = rng.randint(-128, 128, size=(nb, k)).astype(np.int8)
@@ -85,8 +98,9 @@ def test_gemm_i8_tcgen05_exact(nat, ma, nb, k):
     assert np.array_equal(c.cpu().numpy().astype(np.int64), want)
 
 
+@pytest.mark.parametrize("gemm_variant", [1, 2], indirect=True)
 @pytest.mark.parametrize("m,n", [(300, 500), (700, 130)])
-def test_assoc_counts_i8_matches_popc_and_oracle(nat, m, n):
+def test_assoc_counts_i8_matches_popc_and_oracle(nat, m, n, gemm_variant):
     _native, device = nat
     rng = np.random.RandomState(m * 3 + n)
     A = _rand01(rng, m, n, 0.15)
@@ -155,9 +169,10 @@ def test_cover_score_popc(nat, m, n, w):
         assert np.array_equal(gn.cpu().numpy()[live], (N * use).sum(axis=0)[live])
 
 
+@pytest.mark.parametrize("gemm_variant", [1, 2], indirect=True)
 @pytest.mark.parametrize("m,n,w", [(70, 50, (0.5, 0.5)), (300, 200, (0.25, 0.75)), (600, 700, (0.5, 0.5)),
-                                   (1000, 500, (0.375, 0.5))])
-def test_cover_score_i8_tcgen05(nat, m, n, w):
+                                   (1000, 500, (0.375, 0.5)), (5000, 2100, (0.5, 0.5))])
+def test_cover_score_i8_tcgen05(nat, m, n, w, gemm_variant):
     _native, device = nat
     X, C, B, alive = _cover_inputs(m * 7 + n, m, n)
     wa, wb, _ = O.integer_weights(*w)
@@ -166,7 +181,7 @@ def test_cover_score_i8_tcgen05(nat, m, n, w):
     ld = device.round_up(n, 128)
     rows_plane = np.zeros((device.round_up(m, 256), ld), np.int8)
     rows_plane[:m, :n] = rows
-    cand_plane = np.zeros((device.round_up(n, 128), ld), np.int8)
+    cand_plane = np.zeros((device.round_up(n, 256), ld), np.int8)
     cand_plane[:n, :n] = B
     gain = device.zeros((cand_plane.shape[0],), torch.int64)
     _native.call("bmf_cover_score_i8", _dev(cand_plane), cand_plane.shape[0], _dev(rows_plane), rows_plane.shape[0],
