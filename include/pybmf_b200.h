@@ -54,12 +54,12 @@ int bmf_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int bmf_pack_csr(const int64_t* indptr, const int32_t* indices, int64_t m, int64_t n,
                  int transposed, uint64_t* bits, int64_t words, bmf_stream_t stream);
 int bmf_fill_zero(void* ptr, int64_t bytes, bmf_stream_t stream);
-/* bits[rows][words] -> int8 plane[rows_pad][ld]: value `one` where the bit is set,
- * `zero` where it is clear and the column < ncols, 0 in all padding and wherever
- * mask_bits (nullable, same layout; the covered mask) has a 1. */
+/* bits[rows][words] -> int8 plane[rows_pad][ld]: value `masked` wherever mask_bits (nullable,
+ * same layout; the covered mask) has a 1, else `one` where the bit is set and `zero` where it is
+ * clear; 0 in all padding (columns >= ncols, rows >= rows). */
 int bmf_expand_bits_i8(const uint64_t* bits, const uint64_t* mask_bits, int64_t rows, int64_t ncols,
-                       int64_t words, int8_t one, int8_t zero, int8_t* plane, int64_t rows_pad,
-                       int64_t ld, bmf_stream_t stream);
+                       int64_t words, int8_t one, int8_t zero, int8_t masked, int8_t* plane,
+                       int64_t rows_pad, int64_t ld, bmf_stream_t stream);
 
 /* ---- association matrix: build_assoc, PyBMF/models/Asso.py:191-213 -------------------
  * cnt[i][j] = |col_i AND col_j| = (X^T X)[i][j], int32, leading dimension ldc.
@@ -80,7 +80,7 @@ int bmf_assoc_counts_i8(const int8_t* xt_plane, int64_t n, int64_t n_pad, int64_
  * (nullable) receives the same rows as int8 0/1, [n_pad(128)][ld]. */
 int bmf_basis_threshold(const int32_t* cnt, int64_t ldc, int64_t n, double tau, uint64_t* basis_bits,
                         int64_t words, int8_t* cand_plane, int64_t ld, uint8_t* alive,
-                        bmf_stream_t stream);
+                        int32_t* row_pop /* nullable: |b_i| per row */, bmf_stream_t stream);
 
 /* ---- greedy cover-gain scoring: the hot loop Asso.py:83-95 -> get_vector Asso.py:144-188,
  *      coverage_score PyBMF/utils/metrics.py:189-201 ------------------------------------
@@ -97,11 +97,17 @@ int bmf_cover_score_popc(const uint64_t* x_bits, const uint64_t* c_bits, int64_t
                          const int32_t* tp_old, const int32_t* fp_old, int32_t wa, int32_t wb,
                          double w_fp, double w_fn, int64_t* gain_p, int64_t* gain_n,
                          bmf_stream_t stream);
-/* tcgen05 kind::i8 variant, integer mode only: rows_plane[i][k] = (~c & x) ? wb : (~c & ~x) ? -wa : 0,
- * cand_plane = 0/1 basis rows; gain[j] = sum_i relu(sum_k cand[j][k]*rows[i][k]).
+/* tcgen05 kind::i8 variant, integer mode only.  cand_plane = 0/1 basis rows and
+ *   gain[j] = sum_i relu(sign * sum_k cand[j][k]*rows[i][k] - bias_scale * cand_pop[j]).
+ * Two equivalent operand encodings give D = wb*P - wa*N:
+ *   signed   : rows[i][k] = sign*wb (uncovered one), -sign*wa (uncovered zero), 0 (covered); cand_pop = NULL
+ *   zero-dominant: rows[i][k] = wa+wb (uncovered one), 0 (uncovered zero), wa (covered), sign = +1,
+ *              cand_pop[j] = |b_j|, bias_scale = wa   (since N = |b_j| - |b_j & c_i| - P);
+ *              the dominant operand value is 0, which lowers tensor-core switching power.
  * gain has cand_pad entries. */
 int bmf_cover_score_i8(const int8_t* cand_plane, int64_t cand_pad, const int8_t* rows_plane,
-                       int64_t rows_pad, int64_t ld, int64_t* gain, bmf_stream_t stream);
+                       int64_t rows_pad, int64_t ld, int32_t sign, const int32_t* cand_pop,
+                       int32_t bias_scale, int64_t* gain, bmf_stream_t stream);
 
 /* argmax of Asso.py:94: first j (lowest index) among alive candidates whose score is
  * strictly greater than `best_score` and than every earlier score.
@@ -116,13 +122,13 @@ int bmf_select_first_max(const int64_t* gain_p, const int64_t* gain_n, const uin
 /* set_factors + cover update for the chosen candidate (Asso.py:103-110): recompute
  * use(i) for basis row *winner (device int64; <0 = no-op), write u_bits (bit i of a
  * ceil(m/64)-word vector, caller-zeroed), OR the row into c_bits where used, add P/N to
- * tp_old/fp_old, zero the used rows' entries of rows_plane (nullable) on the row's
- * support, clear alive[winner].  totals[0..2] += (#used rows, sum P, sum N). */
+ * tp_old/fp_old, set the used rows' newly covered entries of rows_plane (nullable) to
+ * covered_value, clear alive[winner].  totals[0..2] += (#used rows, sum P, sum N). */
 int bmf_cover_apply(const uint64_t* x_bits, uint64_t* c_bits, int64_t m, int64_t n, int64_t words,
                     const uint64_t* basis_bits, uint8_t* alive, const int64_t* winner, int32_t* tp_old,
                     int32_t* fp_old, int32_t wa, int32_t wb, double w_fp, double w_fn,
-                    int8_t* rows_plane, int64_t ld, uint64_t* u_bits, int64_t* totals,
-                    bmf_stream_t stream);
+                    int8_t* rows_plane, int64_t ld, int8_t covered_value, uint64_t* u_bits,
+                    int64_t* totals, bmf_stream_t stream);
 
 /* ---- Boolean product and confusion counts ------------------------------------------------
  * get_prediction / matmul(boolean=True): PyBMF/utils/common.py:98-107, boolean_utils.py:61-84.

@@ -23,15 +23,15 @@ SIGNATURES = {
     "bmf_device_info": [_p, _p, _p],
     "bmf_fill_zero": [_p, _i64, _p],
     "bmf_pack_csr": [_p, _p, _i64, _i64, C.c_int, _p, _i64, _p],
-    "bmf_expand_bits_i8": [_p, _p, _i64, _i64, _i64, _i8, _i8, _p, _i64, _i64, _p],
+    "bmf_expand_bits_i8": [_p, _p, _i64, _i64, _i64, _i8, _i8, _i8, _p, _i64, _i64, _p],
     "bmf_assoc_counts_popc": [_p, _i64, _i64, _p, _i64, _p],
     "bmf_gemm_i8_nt": [_p, _i64, _p, _i64, _i64, _p, _i64, _p],
     "bmf_assoc_counts_i8": [_p, _i64, _i64, _i64, _p, _i64, _p],
-    "bmf_basis_threshold": [_p, _i64, _i64, _f64, _p, _i64, _p, _i64, _p, _p],
+    "bmf_basis_threshold": [_p, _i64, _i64, _f64, _p, _i64, _p, _i64, _p, _p, _p],
     "bmf_cover_score_popc": [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _i32, _i32, _f64, _f64, _p, _p, _p],
-    "bmf_cover_score_i8": [_p, _i64, _p, _i64, _i64, _p, _p],
+    "bmf_cover_score_i8": [_p, _i64, _p, _i64, _i64, _i32, _p, _i32, _p, _p],
     "bmf_select_first_max": [_p, _p, _p, _i64, _i32, _i32, _i64, _f64, _f64, _f64, _i64, _i64, _f64, _p, _p],
-    "bmf_cover_apply": [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i32, _i32, _f64, _f64, _p, _i64, _p, _p, _p],
+    "bmf_cover_apply": [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i32, _i32, _f64, _f64, _p, _i64, _i8, _p, _p, _p],
     "bmf_bool_product": [_p, _i64, _i64, _p, _i64, _i64, _p, _p],
     "bmf_confusion_factors": [_p, _i64, _i64, _p, _i64, _p, _i64, _p, _p, _p, _p],
     "bmf_confusion_bits": [_p, _p, _i64, _i64, _p, _p, _p, _p],

@@ -29,7 +29,7 @@ __global__ void pack_csr_kernel(const int64_t* __restrict__ indptr, const int32_
 
 // 16 bits -> 16 int8 per thread, one 128-bit store
 __global__ void expand_bits_i8_kernel(const uint64_t* __restrict__ bits, const uint64_t* __restrict__ mask,
-                                      int64_t rows, int64_t ncols, int64_t words, int one, int zero,
+                                      int64_t rows, int64_t ncols, int64_t words, int one, int zero, int masked,
                                       int8_t* __restrict__ plane, int64_t rows_pad, int64_t ld) {
   const int64_t chunks = ld >> 4;
   const int64_t total = rows_pad * chunks;
@@ -44,7 +44,8 @@ __global__ void expand_bits_i8_kernel(const uint64_t* __restrict__ bits, const u
       const uint32_t k16 = (mask != nullptr && w < words) ? (uint32_t)((mask[r * words + w] >> (c0 & 63)) & 0xffffu) : 0u;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        int v = (c0 + i < ncols && !((k16 >> i) & 1u)) ? (((b16 >> i) & 1u) ? one : zero) : 0;
+        int v = 0;
+        if (c0 + i < ncols) v = ((k16 >> i) & 1u) ? masked : (((b16 >> i) & 1u) ? one : zero);
         out[i >> 2] |= (uint32_t)(uint8_t)(int8_t)v << ((i & 3) * 8);
       }
     }
@@ -114,14 +115,14 @@ __global__ void __launch_bounds__(256) assoc_counts_popc_kernel(const uint64_t* 
 __global__ void basis_threshold_kernel(const int32_t* __restrict__ cnt, int64_t ldc, int64_t n, double tau,
                                        uint64_t* __restrict__ basis_bits, int64_t words,
                                        int8_t* __restrict__ cand_plane, int64_t ld,
-                                       uint8_t* __restrict__ alive) {
+                                       uint8_t* __restrict__ alive, int32_t* __restrict__ row_pop) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t i = warp0; i < n; i += nwarps) {
     const int32_t si = cnt[i * ldc + i];
     const double s = (double)si;
-    int any = 0;
+    int any = 0, pop = 0;
     for (int64_t w = 0; w < words; ++w) {       // each pass: 2 x 32 columns -> one word
       uint64_t word = 0;
 #pragma unroll
@@ -135,10 +136,14 @@ __global__ void basis_threshold_kernel(const int32_t* __restrict__ cnt, int64_t 
       }
       if (lane == 0) basis_bits[i * words + w] = word;
       any |= (word != 0);
+      pop += __popcll(word);
     }
     if (cand_plane != nullptr)                     // tail of the padded row beyond words*64
       for (int64_t j = words * 64 + lane; j < ld; j += 32) cand_plane[i * ld + j] = 0;
-    if (lane == 0) alive[i] = any ? 1 : 0;
+    if (lane == 0) {
+      alive[i] = any ? 1 : 0;
+      if (row_pop != nullptr) row_pop[i] = pop;
+    }
   }
 }
 
@@ -299,8 +304,8 @@ cover_apply_kernel(const uint64_t* __restrict__ xb, uint64_t* __restrict__ cb, i
                    int64_t words, const uint64_t* __restrict__ basis, uint8_t* __restrict__ alive,
                    const int64_t* __restrict__ winner, int32_t* __restrict__ tp_old,
                    int32_t* __restrict__ fp_old, int wa, int wb, double neg_w_fp, double w_fn,
-                   int8_t* __restrict__ rows_plane, int64_t ld, unsigned long long* __restrict__ u_bits,
-                   unsigned long long* __restrict__ totals) {
+                   int8_t* __restrict__ rows_plane, int64_t ld, int covered_value,
+                   unsigned long long* __restrict__ u_bits, unsigned long long* __restrict__ totals) {
   const int64_t j = *winner;
   if (j < 0) return;
   const uint64_t* __restrict__ b = basis + j * words;
@@ -329,8 +334,8 @@ cover_apply_kernel(const uint64_t* __restrict__ xb, uint64_t* __restrict__ cb, i
       if (rows_plane != nullptr) {
         uint64_t s0 = v.x & ~c.x, s1 = v.y & ~c.y;                      // newly covered columns
         int8_t* rowp = rows_plane + i * ld + p * 128;
-        while (s0) { const int k = __ffsll((long long)s0) - 1; s0 &= s0 - 1; rowp[k] = 0; }
-        while (s1) { const int k = __ffsll((long long)s1) - 1; s1 &= s1 - 1; rowp[64 + k] = 0; }
+        while (s0) { const int k = __ffsll((long long)s0) - 1; s0 &= s0 - 1; rowp[k] = (int8_t)covered_value; }
+        while (s1) { const int k = __ffsll((long long)s1) - 1; s1 &= s1 - 1; rowp[64 + k] = (int8_t)covered_value; }
       }
       c.x |= v.x;
       c.y |= v.y;
@@ -536,8 +541,8 @@ extern "C" int bmf_pack_csr(const int64_t* indptr, const int32_t* indices, int64
 }
 
 extern "C" int bmf_expand_bits_i8(const uint64_t* bits, const uint64_t* mask_bits, int64_t rows, int64_t ncols,
-                                  int64_t words, int8_t one, int8_t zero, int8_t* plane, int64_t rows_pad,
-                                  int64_t ld, bmf_stream_t stream) {
+                                  int64_t words, int8_t one, int8_t zero, int8_t masked, int8_t* plane,
+                                  int64_t rows_pad, int64_t ld, bmf_stream_t stream) {
   BMF_REQUIRE(bits && plane, "bmf_expand_bits_i8: null pointer");
   BMF_REQUIRE(ld % 128 == 0 && ld >= ncols && rows_pad >= rows && rows >= 0, "bmf_expand_bits_i8: bad ld / rows_pad");
   if (rows_pad == 0) return 0;
@@ -545,7 +550,7 @@ extern "C" int bmf_expand_bits_i8(const uint64_t* bits, const uint64_t* mask_bit
   int64_t blocks = ceil_div(total, 256);
   if (blocks > (int64_t)num_sms() * 64) blocks = (int64_t)num_sms() * 64;
   expand_bits_i8_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(bits, mask_bits, rows, ncols, words, one,
-                                                                       zero, plane, rows_pad, ld);
+                                                                       zero, masked, plane, rows_pad, ld);
   BMF_LAUNCH_CHECK("bmf_expand_bits_i8");
   return 0;
 }
@@ -561,13 +566,13 @@ extern "C" int bmf_assoc_counts_popc(const uint64_t* xt_bits, int64_t n, int64_t
 
 extern "C" int bmf_basis_threshold(const int32_t* cnt, int64_t ldc, int64_t n, double tau,
                                    uint64_t* basis_bits, int64_t words, int8_t* cand_plane, int64_t ld,
-                                   uint8_t* alive, bmf_stream_t stream) {
+                                   uint8_t* alive, int32_t* row_pop, bmf_stream_t stream) {
   BMF_REQUIRE(cnt && basis_bits && alive && n > 0 && ldc >= n, "bmf_basis_threshold: bad arguments");
   BMF_REQUIRE(words % 2 == 0 && words * 64 >= n, "bmf_basis_threshold: words must be even and cover n");
   BMF_REQUIRE(cand_plane == nullptr || (ld % 128 == 0 && ld >= n), "bmf_basis_threshold: bad ld");
   int64_t blocks = ceil_div(n, 8);
   basis_threshold_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(cnt, ldc, n, tau, basis_bits, words,
-                                                                        cand_plane, ld, alive);
+                                                                        cand_plane, ld, alive, row_pop);
   BMF_LAUNCH_CHECK("bmf_basis_threshold");
   return 0;
 }
@@ -616,7 +621,7 @@ extern "C" int bmf_select_first_max(const int64_t* gain_p, const int64_t* gain_n
 extern "C" int bmf_cover_apply(const uint64_t* x_bits, uint64_t* c_bits, int64_t m, int64_t n, int64_t words,
                                const uint64_t* basis_bits, uint8_t* alive, const int64_t* winner,
                                int32_t* tp_old, int32_t* fp_old, int32_t wa, int32_t wb, double w_fp,
-                               double w_fn, int8_t* rows_plane, int64_t ld, uint64_t* u_bits,
+                               double w_fn, int8_t* rows_plane, int64_t ld, int8_t covered_value, uint64_t* u_bits,
                                int64_t* totals, bmf_stream_t stream) {
   BMF_REQUIRE(x_bits && c_bits && basis_bits && alive && winner && tp_old && fp_old && u_bits && totals,
               "bmf_cover_apply: null pointer");
@@ -626,7 +631,7 @@ extern "C" int bmf_cover_apply(const uint64_t* x_bits, uint64_t* c_bits, int64_t
   if (blocks > row_stream_grid()) blocks = row_stream_grid();
   cover_apply_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
       x_bits, c_bits, m, n, words, basis_bits, alive, winner, tp_old, fp_old, wa, wb, -w_fp, w_fn, rows_plane,
-      ld, reinterpret_cast<unsigned long long*>(u_bits), reinterpret_cast<unsigned long long*>(totals));
+      ld, (int)covered_value, reinterpret_cast<unsigned long long*>(u_bits), reinterpret_cast<unsigned long long*>(totals));
   BMF_LAUNCH_CHECK("bmf_cover_apply");
   return 0;
 }

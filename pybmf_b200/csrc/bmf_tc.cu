@@ -135,8 +135,9 @@ __device__ __forceinline__ void tile_coords(int64_t t, int mt_total, int nt_tota
 template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               int mt_total, int nt_total, int kb_total, int group_m, unsigned long long* __restrict__ gain,
-               int32_t* __restrict__ C, int64_t ldc) {
+               int mt_total, int nt_total, int kb_total, int group_m, int sign,
+               const int32_t* __restrict__ cand_pop, int bias_scale,
+               unsigned long long* __restrict__ gain, int32_t* __restrict__ C, int64_t ldc) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -230,6 +231,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       const int64_t row = (int64_t)mt * BM + quad * 32 + lane;
+      const int bias = (EPI == EPI_GAIN && cand_pop != nullptr) ? bias_scale * cand_pop[row] : 0;
       long long relu_sum = 0;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
@@ -238,7 +240,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (EPI == EPI_GAIN) {
           int part = 0;                                   // 32 * 127 * K fits int32 for K < 5e5
 #pragma unroll
-          for (int q = 0; q < 32; ++q) part += max((int)v[q], 0);
+          for (int q = 0; q < 32; ++q) part += max(sign * (int)v[q] - bias, 0);
           relu_sum += part;
         } else {
           int4* dst = reinterpret_cast<int4*>(C + row * ldc + (int64_t)nt * BN + c * 32);
@@ -304,8 +306,9 @@ static int make_plane_map(CUtensorMap* map, const int8_t* plane, int64_t rows, i
 }
 
 template <int EPI>
-static int launch_gemm(const int8_t* a, int64_t a_rows, const int8_t* b, int64_t b_rows, int64_t ld,
-                       unsigned long long* gain, int32_t* C, int64_t ldc, cudaStream_t stream) {
+static int launch_gemm(const int8_t* a, int64_t a_rows, const int8_t* b, int64_t b_rows, int64_t ld, int sign,
+                       const int32_t* cand_pop, int bias_scale, unsigned long long* gain, int32_t* C, int64_t ldc,
+                       cudaStream_t stream) {
   CUtensorMap ma, mb;
   int rc = make_plane_map(&ma, a, a_rows, ld, BM);
   if (rc) return rc;
@@ -323,7 +326,7 @@ static int launch_gemm(const int8_t* a, int64_t a_rows, const int8_t* b, int64_t
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   int group_m = 16;                                       // candidate tiles per raster group (L2 reuse)
   if (const char* e = getenv("BMF_GROUP_M")) { int v = atoi(e); if (v >= 1 && v <= 64) group_m = v; }
-  gemm_i8_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, mt, nt, kb, group_m, gain, C, ldc);
+  gemm_i8_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, mt, nt, kb, group_m, sign, cand_pop, bias_scale, gain, C, ldc);
   return check_cuda(cudaGetLastError(), "gemm_i8_kernel launch");
 }
 
@@ -388,8 +391,9 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t local_bar) {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_i8_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   int mt_total, int nt_total, int kb_total, int group_m, unsigned long long* __restrict__ gain,
-                   int32_t* __restrict__ C, int64_t ldc) {
+                   int mt_total, int nt_total, int kb_total, int group_m, int sign,
+                   const int32_t* __restrict__ cand_pop, int bias_scale,
+                   unsigned long long* __restrict__ gain, int32_t* __restrict__ C, int64_t ldc) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE_BYTES2);
@@ -486,6 +490,7 @@ gemm_i8_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       const int64_t row = (int64_t)mt * BM2 + (int64_t)rank * HALF + quad * 32 + lane;
+      const int bias = (EPI == EPI_GAIN && cand_pop != nullptr) ? bias_scale * cand_pop[row] : 0;
       long long relu_sum = 0;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
@@ -494,7 +499,7 @@ gemm_i8_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         if (EPI == EPI_GAIN) {
           int part = 0;
 #pragma unroll
-          for (int q = 0; q < 32; ++q) part += max((int)v[q], 0);
+          for (int q = 0; q < 32; ++q) part += max(sign * (int)v[q] - bias, 0);
           relu_sum += part;
         } else {
           int4* dst = reinterpret_cast<int4*>(C + row * ldc + (int64_t)nt * BN + c * 32);
@@ -521,8 +526,9 @@ gemm_i8_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 }
 
 template <int EPI>
-static int launch_gemm_2sm(const int8_t* a, int64_t a_rows, const int8_t* b, int64_t b_rows, int64_t ld,
-                           unsigned long long* gain, int32_t* C, int64_t ldc, cudaStream_t stream) {
+static int launch_gemm_2sm(const int8_t* a, int64_t a_rows, const int8_t* b, int64_t b_rows, int64_t ld, int sign,
+                           const int32_t* cand_pop, int bias_scale, unsigned long long* gain, int32_t* C,
+                           int64_t ldc, cudaStream_t stream) {
   CUtensorMap ma, mb;
   int rc = make_plane_map(&ma, a, a_rows, ld, HALF);
   if (rc) return rc;
@@ -539,9 +545,9 @@ static int launch_gemm_2sm(const int8_t* a, int64_t a_rows, const int8_t* b, int
   const int64_t tiles = (int64_t)mt * nt;
   const int pairs_max = num_sms() / 2;
   const int pairs = (int)(tiles < pairs_max ? tiles : pairs_max);
-  int group_m = 8;                                        // 256-row candidate tiles per raster group
+  int group_m = 16;                                       // 256-row candidate tiles per raster group
   if (const char* e = getenv("BMF_GROUP_M2")) { int v = atoi(e); if (v >= 1 && v <= 64) group_m = v; }
-  gemm_i8_2sm_kernel<EPI><<<2 * pairs, NUM_THREADS, SMEM_BYTES2, stream>>>(ma, mb, mt, nt, kb, group_m, gain, C, ldc);
+  gemm_i8_2sm_kernel<EPI><<<2 * pairs, NUM_THREADS, SMEM_BYTES2, stream>>>(ma, mb, mt, nt, kb, group_m, sign, cand_pop, bias_scale, gain, C, ldc);
   return check_cuda(cudaGetLastError(), "gemm_i8_2sm_kernel launch");
 }
 }  // namespace sm2
@@ -549,7 +555,8 @@ static int launch_gemm_2sm(const int8_t* a, int64_t a_rows, const int8_t* b, int
 // variant: 0 = auto (2-SM when the candidate rows are a multiple of 256), 1 = 1-SM, 2 = 2-SM
 template <int EPI>
 static int dispatch_gemm(int variant, const int8_t* a, int64_t a_rows, const int8_t* b, int64_t b_rows, int64_t ld,
-                         unsigned long long* gain, int32_t* C, int64_t ldc, cudaStream_t stream) {
+                         int sign, const int32_t* cand_pop, int bias_scale, unsigned long long* gain, int32_t* C,
+                         int64_t ldc, cudaStream_t stream) {
   if (const char* e = getenv("BMF_GEMM_VARIANT")) { int v = atoi(e); if (v == 1 || v == 2) variant = v; }
   const bool ok2 = (a_rows % sm2::BM2) == 0;
   if (variant == 2 && !ok2) {
@@ -557,8 +564,8 @@ static int dispatch_gemm(int variant, const int8_t* a, int64_t a_rows, const int
     return BMF_E_ARG;
   }
   if (variant == 2 || (variant == 0 && ok2))
-    return sm2::launch_gemm_2sm<EPI>(a, a_rows, b, b_rows, ld, gain, C, ldc, stream);
-  return launch_gemm<EPI>(a, a_rows, b, b_rows, ld, gain, C, ldc, stream);
+    return sm2::launch_gemm_2sm<EPI>(a, a_rows, b, b_rows, ld, sign, cand_pop, bias_scale, gain, C, ldc, stream);
+  return launch_gemm<EPI>(a, a_rows, b, b_rows, ld, sign, cand_pop, bias_scale, gain, C, ldc, stream);
 }
 
 }  // namespace tc
@@ -573,7 +580,7 @@ extern "C" int bmf_gemm_i8_nt(const int8_t* a_plane, int64_t a_rows_pad, const i
   BMF_REQUIRE(b_rows_pad > 0 && b_rows_pad % tc::BN == 0, "bmf_gemm_i8_nt: b rows must be a positive multiple of 256");
   BMF_REQUIRE(ld > 0 && ld % tc::BK == 0, "bmf_gemm_i8_nt: ld must be a positive multiple of 128");
   BMF_REQUIRE(ldc >= b_rows_pad && ldc % 4 == 0, "bmf_gemm_i8_nt: ldc must cover b rows and be a multiple of 4");
-  return tc::dispatch_gemm<tc::EPI_STORE>(0, a_plane, a_rows_pad, b_plane, b_rows_pad, ld, nullptr, c, ldc, as_stream(stream));
+  return tc::dispatch_gemm<tc::EPI_STORE>(0, a_plane, a_rows_pad, b_plane, b_rows_pad, ld, 1, nullptr, 0, nullptr, c, ldc, as_stream(stream));
 }
 
 extern "C" int bmf_assoc_counts_i8(const int8_t* xt_plane, int64_t n, int64_t n_pad, int64_t ld, int32_t* cnt,
@@ -582,17 +589,19 @@ extern "C" int bmf_assoc_counts_i8(const int8_t* xt_plane, int64_t n, int64_t n_
   BMF_REQUIRE(n_pad >= n && n_pad % tc::BN == 0, "bmf_assoc_counts_i8: n_pad must be a multiple of 256 covering n");
   BMF_REQUIRE(ld > 0 && ld % tc::BK == 0, "bmf_assoc_counts_i8: ld must be a positive multiple of 128");
   BMF_REQUIRE(ldc >= n_pad && ldc % 4 == 0, "bmf_assoc_counts_i8: ldc must be >= n_pad and a multiple of 4");
-  return tc::dispatch_gemm<tc::EPI_STORE>(0, xt_plane, n_pad, xt_plane, n_pad, ld, nullptr, cnt, ldc, as_stream(stream));
+  return tc::dispatch_gemm<tc::EPI_STORE>(0, xt_plane, n_pad, xt_plane, n_pad, ld, 1, nullptr, 0, nullptr, cnt, ldc, as_stream(stream));
 }
 
 extern "C" int bmf_cover_score_i8(const int8_t* cand_plane, int64_t cand_pad, const int8_t* rows_plane,
-                                  int64_t rows_pad, int64_t ld, int64_t* gain, bmf_stream_t stream) {
+                                  int64_t rows_pad, int64_t ld, int32_t sign, const int32_t* cand_pop, int32_t bias_scale,
+                                  int64_t* gain, bmf_stream_t stream) {
+  BMF_REQUIRE(sign == 1 || sign == -1, "bmf_cover_score_i8: sign must be +1 or -1");
   BMF_REQUIRE(cand_plane && rows_plane && gain, "bmf_cover_score_i8: null pointer");
   BMF_REQUIRE(cand_pad > 0 && cand_pad % tc::BM == 0, "bmf_cover_score_i8: cand_pad must be a positive multiple of 128");
   BMF_REQUIRE(rows_pad > 0 && rows_pad % tc::BN == 0, "bmf_cover_score_i8: rows_pad must be a positive multiple of 256");
   BMF_REQUIRE(ld > 0 && ld % tc::BK == 0, "bmf_cover_score_i8: ld must be a positive multiple of 128");
   int rc = check_cuda(cudaMemsetAsync(gain, 0, sizeof(int64_t) * cand_pad, as_stream(stream)), "bmf_cover_score_i8");
   if (rc) return rc;
-  return tc::dispatch_gemm<tc::EPI_GAIN>(0, cand_plane, cand_pad, rows_plane, rows_pad, ld,
+  return tc::dispatch_gemm<tc::EPI_GAIN>(0, cand_plane, cand_pad, rows_plane, rows_pad, ld, sign, cand_pop, bias_scale,
                                          reinterpret_cast<unsigned long long*>(gain), nullptr, 0, as_stream(stream));
 }

@@ -86,12 +86,12 @@ def pack_csr(indptr_d, indices_d, m: int, n: int, transposed: bool = False):
     return bits
 
 
-def expand_bits_i8(bits, rows: int, ncols: int, one: int, zero: int, row_tile: int, mask=None, out=None):
-    """Bit matrix -> int8 plane [round_up(rows,row_tile), round_up(ncols,128)]; 0 where `mask` is set."""
+def expand_bits_i8(bits, rows: int, ncols: int, one: int, zero: int, row_tile: int, mask=None, out=None, masked=0):
+    """Bit matrix -> int8 plane [round_up(rows,row_tile), round_up(ncols,128)]; `masked` where `mask` is set."""
     ld = round_up(max(ncols, 1), 128)
     rows_pad = round_up(max(rows, 1), row_tile)
     plane = empty((rows_pad, ld), torch.int8) if out is None else out
-    _native.call("bmf_expand_bits_i8", bits, mask, rows, ncols, bits.shape[1], one, zero, plane, rows_pad, ld)
+    _native.call("bmf_expand_bits_i8", bits, mask, rows, ncols, bits.shape[1], one, zero, masked, plane, rows_pad, ld)
     return plane
 
 

@@ -8,6 +8,8 @@ totals and takes the identical lowest-index strict argmax
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import scipy.sparse as sp
 import torch
@@ -85,6 +87,15 @@ class CoverEngine:
                              "use scorer='popc' for w_fp=%r, w_fn=%r" % (w_fp, w_fn))
         assert scorer in ("tcgen05", "popc") and assoc in ("auto", "tcgen05", "popc")
         self.scorer = scorer
+        # operand encoding of the rows plane (all give D = wb*P - wa*N exactly, see include/pybmf_b200.h):
+        #   "zero"  : uncovered one -> wa+wb, uncovered zero -> 0, covered -> wa, bias wa*|b_j| in the epilogue
+        #   "signed": uncovered one -> +wb,   uncovered zero -> -wa, covered -> 0
+        enc = os.environ.get("BMF_PLANE_ENCODING", "zero")
+        if enc == "zero" and self.wa + self.wb > 127:
+            enc = "signed"
+        self.encoding = enc
+        self.plane_sign = -1 if enc == "signed-" else 1
+        self.cand_pop = None
         self.assoc_kind = "tcgen05" if assoc == "auto" else assoc
 
         self.words = device.words_for(self.n)
@@ -129,8 +140,9 @@ class CoverEngine:
         self.cnt = cnt
         if self.scorer == "tcgen05":
             self.cand_plane = device.zeros((self.cand_pad, self.ld), torch.int8)
+        self.cand_pop = device.zeros((self.cand_pad,), torch.int32)
         _native.call("bmf_basis_threshold", cnt, n_pad, n, float(tau), self.basis_bits, self.words,
-                     self.cand_plane, self.ld, self.alive)
+                     self.cand_plane, self.ld, self.alive, self.cand_pop)
         self.launches += 1
         if self.scorer == "tcgen05":
             self._rebuild_rows_plane()
@@ -138,9 +150,17 @@ class CoverEngine:
 
     def _rebuild_rows_plane(self):
         """rows_plane[i][k] = 0 if covered, +wb if x, -wa otherwise (the signed operand of D = wb*P - wa*N)."""
-        self.rows_plane = device.expand_bits_i8(self.x_bits, self.m_loc, self.n, self.wb, -self.wa, 256,
-                                                mask=self.c_bits, out=self.rows_plane)
+        one, zero, covered = self._plane_values()
+        self.rows_plane = device.expand_bits_i8(self.x_bits, self.m_loc, self.n, one, zero, 256,
+                                                mask=self.c_bits, out=self.rows_plane, masked=covered)
         self.launches += 1
+
+    def _plane_values(self):
+        """(uncovered one, uncovered zero, covered) byte values of the rows plane."""
+        if self.encoding == "zero":
+            return self.wa + self.wb, 0, self.wa
+        sg = self.plane_sign
+        return sg * self.wb, -sg * self.wa, 0
 
     def assoc_host(self):
         """The reference's `assoc` attribute (n x n float64) from the device counts."""
@@ -164,7 +184,8 @@ class CoverEngine:
             self.gain_n.zero_()
         elif self.scorer == "tcgen05":
             _native.call("bmf_cover_score_i8", self.cand_plane, self.cand_pad, self.rows_plane,
-                         self.rows_plane.shape[0], self.ld, self.gain_p)
+                         self.rows_plane.shape[0], self.ld, self.plane_sign,
+                         self.cand_pop if self.encoding == "zero" else None, self.wa, self.gain_p)
         else:
             _native.call("bmf_cover_score_popc", self.x_bits, self.c_bits, self.m_loc, self.n, self.words,
                          self.basis_bits, self.alive, self.tp_old, self.fp_old, self.wa, self.wb, self.w_fp,
@@ -187,7 +208,8 @@ class CoverEngine:
         if self.m_loc > 0:
             _native.call("bmf_cover_apply", self.x_bits, self.c_bits, self.m_loc, self.n, self.words, self.basis_bits,
                          self.alive, self.record, self.tp_old, self.fp_old, self.wa, self.wb, self.w_fp, self.w_fn,
-                         self.rows_plane, self.ld, u_bits, self.record[2:5])
+                         self.rows_plane, self.ld, self._plane_values()[2] if self.scorer == "tcgen05" else 0,
+                         u_bits, self.record[2:5])
         self.launches += 2
         if self.world > 1:
             all_reduce_sum(self.record[2:5])

@@ -53,10 +53,12 @@ def test_expand_bits_i8(nat, rows, ncols, tile):
     want[:rows, :ncols] = np.where(A == 1, 3, -2)
     assert plane.shape == (device.round_up(rows, tile), device.round_up(ncols, 128))
     assert np.array_equal(plane, want)
-    K = _rand01(rng, rows, ncols, 0.3)                              # covered mask -> zeros
-    masked = device.expand_bits_i8(bits, rows, ncols, 3, -2, tile, mask=_dev(device.dense_to_words(K))).cpu().numpy()
-    want[:rows, :ncols][K == 1] = 0
-    assert np.array_equal(masked, want)
+    K = _rand01(rng, rows, ncols, 0.3)                              # covered mask -> `masked` value
+    for mv in (0, 5):
+        masked = device.expand_bits_i8(bits, rows, ncols, 3, -2, tile, mask=_dev(device.dense_to_words(K)),
+                                       masked=mv).cpu().numpy()
+        want[:rows, :ncols][K == 1] = mv
+        assert np.array_equal(masked, want)
 
 
 @pytest.mark.parametrize("m,n", [(90, 70), (300, 500), (1000, 200)])
@@ -126,8 +128,10 @@ def test_basis_threshold(nat, tau):
     bits = device.zeros((n, words), torch.int64)
     plane = device.zeros((device.round_up(n, 128), ld), torch.int8)
     alive = device.zeros((n,), torch.uint8)
-    _native.call("bmf_basis_threshold", cnt, n, n, float(tau), bits, words, plane, ld, alive)
+    pop = device.zeros((n,), torch.int32)
+    _native.call("bmf_basis_threshold", cnt, n, n, float(tau), bits, words, plane, ld, alive, pop)
     want = (O.build_assoc(A) > tau).astype(np.uint8)
+    assert np.array_equal(pop.cpu().numpy(), want.sum(axis=1))
     assert np.array_equal(device.bits_to_host(bits, n), want)
     assert np.array_equal(plane.cpu().numpy()[:n, :n], want.astype(np.int8))
     assert plane.cpu().numpy()[:, n:].sum() == 0 and plane.cpu().numpy()[n:].sum() == 0
@@ -183,10 +187,21 @@ def test_cover_score_i8_tcgen05(nat, m, n, w, gemm_variant):
     rows_plane[:m, :n] = rows
     cand_plane = np.zeros((device.round_up(n, 256), ld), np.int8)
     cand_plane[:n, :n] = B
-    gain = device.zeros((cand_plane.shape[0],), torch.int64)
-    _native.call("bmf_cover_score_i8", _dev(cand_plane), cand_plane.shape[0], _dev(rows_plane), rows_plane.shape[0],
-                 ld, gain)
     G = O.integer_gains(X, C, B, wa, wb)
+    for sign in (1, -1):                                            # signed encodings
+        gain = device.zeros((cand_plane.shape[0],), torch.int64)
+        _native.call("bmf_cover_score_i8", _dev(cand_plane), cand_plane.shape[0], _dev(sign * rows_plane),
+                     rows_plane.shape[0], ld, sign, None, 0, gain)
+        got = gain.cpu().numpy()
+        assert np.array_equal(got[:n], G) and got[n:].sum() == 0
+    # zero-dominant encoding: uncovered one -> wa+wb, covered -> wa, uncovered zero -> 0, bias wa*|b_j|
+    zplane = np.zeros_like(rows_plane)
+    zplane[:m, :n] = np.where(C == 1, wa, np.where(X == 1, wa + wb, 0))
+    pop = np.zeros(cand_plane.shape[0], np.int32)
+    pop[:n] = B.sum(axis=1)
+    gain = device.zeros((cand_plane.shape[0],), torch.int64)
+    _native.call("bmf_cover_score_i8", _dev(cand_plane), cand_plane.shape[0], _dev(zplane), rows_plane.shape[0], ld, 1,
+                 _dev(pop), wa, gain)
     got = gain.cpu().numpy()
     assert np.array_equal(got[:n], G) and got[n:].sum() == 0
 
@@ -242,7 +257,7 @@ def test_cover_apply(nat, w):
     tot = device.zeros((3,), torch.int64)
     win = _dev(np.array([j], np.int64))
     _native.call("bmf_cover_apply", _dev(device.dense_to_words(X)), c_d, m, n, words, _dev(device.dense_to_words(B)),
-                 alive_d, win, tp_d, fp_d, wa, wb, w_fp, w_fn, rows_d, ld, ub, tot)
+                 alive_d, win, tp_d, fp_d, wa, wb, w_fp, w_fn, rows_d, ld, 9, ub, tot)
     Cn = C | (u[:, None].astype(np.uint8) & B[j][None, :])
     assert np.array_equal(device.bits_to_host(c_d, n), Cn)
     assert np.array_equal(device.words_to_dense(ub.cpu().numpy().reshape(1, -1), m)[0], u.astype(np.uint8))
@@ -250,13 +265,13 @@ def test_cover_apply(nat, w):
     assert np.array_equal(tp_d.cpu().numpy(), tpn) and np.array_equal(fp_d.cpu().numpy(), fpn)
     assert list(tot.cpu().numpy()) == [int(u.sum()), int(P[u, 0].sum()), int(N[u, 0].sum())]
     want_rows = rows.copy()
-    want_rows[:m, :n][Cn == 1] = 0
+    want_rows[:m, :n][(Cn == 1) & (C == 0)] = 9                     # newly covered entries take covered_value
     assert np.array_equal(rows_d.cpu().numpy(), want_rows)
     assert alive_d.cpu().numpy()[j] == 0 and alive_d.cpu().numpy().sum() == n - 1
     # winner < 0 is a no-op
     before = c_d.clone()
     _native.call("bmf_cover_apply", _dev(device.dense_to_words(X)), c_d, m, n, words, _dev(device.dense_to_words(B)),
-                 alive_d, _dev(np.array([-1], np.int64)), tp_d, fp_d, wa, wb, w_fp, w_fn, rows_d, ld, ub, tot)
+                 alive_d, _dev(np.array([-1], np.int64)), tp_d, fp_d, wa, wb, w_fp, w_fn, rows_d, ld, 9, ub, tot)
     assert torch.equal(before, c_d)
 
 
