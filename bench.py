@@ -60,7 +60,12 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
 
+    def mark(self):
+        """Samples taken from now on belong to the timed region."""
+        self.first = len(self.rows)
+
     def start(self):
+        self.first = 0
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -81,10 +86,11 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             pass
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        rows = self.rows[self.first:] or self.rows[-1:]
+        sm = [float(r[0]) for r in rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in rows)]
         busy = [v for v in sm if v > 0.5 * (max(mx) if mx else 1)] or sm
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
@@ -130,6 +136,119 @@ def run_cpu_arm(args, X, workload, tau, w_fp, standalone):
                                "travel to the GPU box)", "seconds": dt, "steps": steps}
 
 
+def run_product_sweep(args, rank, world, local_rank, real_stdout):
+    """BASELINE.json configs[4]: bit-packed Boolean product U o V^T and the TP/FP/FN counts behind
+    evaluate(), m up to 1M, n up to 100k, k = 64, rows sharded over the ranks (no data-path collective,
+    three int64 counters are all-reduced).  One step = one materialised product + one confusion pass
+    against the product recomputed on the fly.  Algorithmic bytes: m*n/8 written + m*n/8 read."""
+    import torch
+    import torch.distributed as dist
+    from pybmf_b200 import _native, device
+    from pybmf_b200.engine import ShardPlan, all_reduce_sum
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    _native.require_gpu()
+    peaks, peak_src = load_peaks()
+    k = 64
+    points = [(10_000, 1_000), (100_000, 10_000), (1_000_000, 10_000), (100_000, 100_000), (1_000_000, 100_000)]
+    if args.points:
+        points = points[: args.points]
+    results = []
+    stream = torch.cuda.current_stream()
+    for (m, n) in points:
+        r0, r1 = ShardPlan(m, world).rows(rank)
+        m_loc = max(r1 - r0, 1)
+        words = device.words_for(n)
+        g = torch.Generator(device="cuda")
+        g.manual_seed(5 + rank)
+
+        def bern(shape, ands):                                  # int64 words with bit density 2^-ands
+            w = torch.randint(-2 ** 63, 2 ** 63 - 1, shape, dtype=torch.int64, device="cuda", generator=g)
+            for _ in range(ands - 1):
+                w &= torch.randint(-2 ** 63, 2 ** 63 - 1, shape, dtype=torch.int64, device="cuda", generator=g)
+            return w
+        uw = bern((m_loc, 1), 5)                                # U ~ Bern(2/64) per bit
+        gv = torch.Generator(device="cuda"); gv.manual_seed(77)  # V is replicated: same seed on every rank
+        vt = torch.randint(-2 ** 63, 2 ** 63 - 1, (k, words), dtype=torch.int64, device="cuda", generator=gv)
+        for _ in range(4):
+            vt &= torch.randint(-2 ** 63, 2 ** 63 - 1, (k, words), dtype=torch.int64, device="cuda", generator=gv)
+        if n % 64:
+            vt[:, (n // 64)] &= (1 << (n % 64)) - 1
+        vt[:, (n + 63) // 64:] = 0
+        pd = device.zeros((m_loc, words), torch.int64)
+        _native.call("bmf_bool_product", uw, m_loc, 1, vt, k, words, pd)
+        x = pd.clone()                                           # ground truth = product with ~6 % of the bits flipped
+        for c0 in range(0, m_loc, 65536):
+            blk = x[c0:c0 + 65536]
+            blk ^= bern(blk.shape, 4)
+        if n % 64:
+            x[:, (n // 64)] &= (1 << (n % 64)) - 1
+        x[:, (n + 63) // 64:] = 0
+        counts = device.zeros((3,), torch.int64)
+        counts2 = device.zeros((3,), torch.int64)
+
+        def step():
+            _native.call("bmf_bool_product", uw, m_loc, 1, vt, k, words, pd)
+            counts.zero_()
+            _native.call("bmf_confusion_factors", x, m_loc, words, uw, 1, vt, k, counts, None, None)
+        for _ in range(max(args.warmup, 1)):
+            step()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev[0].record(stream)
+        for _ in range(args.steps):
+            _native.call("bmf_bool_product", uw, m_loc, 1, vt, k, words, pd)
+        ev[1].record(stream)
+        for _ in range(args.steps):
+            counts.zero_()
+            _native.call("bmf_confusion_factors", x, m_loc, words, uw, 1, vt, k, counts, None, None)
+        ev[2].record(stream)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # size-independent checks: the two confusion kernels agree, and TP + FN = |X|, TP + FP = |product|
+        _native.call("bmf_confusion_bits", x, pd, m_loc, words, counts2, None, None)
+        ok = bool(torch.equal(counts, counts2))
+        all_reduce_sum(counts)
+        tp, fp, fn = (int(v) for v in counts.cpu().numpy())
+        bytes_one = m * words * 8.0                              # one bit matrix, all ranks
+        prod_gbs = bytes_one * args.steps / (t[0].item() / 1e3) / 1e9
+        conf_gbs = bytes_one * args.steps / (t[1].item() / 1e3) / 1e9
+        results.append({"m": m, "n": n, "k": k, "product_ms": t[0].item() / args.steps, "confusion_ms": t[1].item() / args.steps,
+                        "product_gbs": prod_gbs, "confusion_gbs": conf_gbs, "tp": tp, "fp": fp, "fn": fn,
+                        "kernels_agree": ok})
+        del x, pd, uw, vt
+        torch.cuda.empty_cache()
+    if rank == 0:
+        last = results[-1]
+        hbm = float(peaks.get("hbm_gbs", 6650.0)) * world
+        step_ms = last["product_ms"] + last["confusion_ms"]
+        bytes_step = 2.0 * last["m"] * device.words_for(last["n"]) * 8
+        value = bytes_step / (step_ms / 1e3) / 1e9
+        line = {"metric": "bool_product_confusion_gbs", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u64 bit words", "data": "synthetic",
+                "config": {"workload": "Boolean product + TP/FP/FN sweep, k=64 (BASELINE configs[4]); headline = largest point",
+                           "m": last["m"], "n": last["n"], "l2": "bit matrices of the large points exceed L2"},
+                "roofline": {"bound": "hbm", "achieved": value / world, "peak": hbm / world, "unit": "GB/s",
+                             "frac": value / hbm, "traffic": None, "kernel": "bool_product_kernel + confusion_kernel<true>",
+                             "peak_source": peak_src},
+                "sweep": results, "gpu_launches": 2 * args.steps * len(results)}
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def measure_cublas_int8(torch, nn=8192, reps=10):
     """Context only: cuBLAS int8 GEMM (torch._int_mm) on this box, best of `reps`, Top/s."""
     try:
@@ -156,17 +275,22 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default=os.environ.get("BMF_BENCH_WORKLOAD", "c4"), choices=list(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("BMF_BENCH_WORKLOAD", "c4"), choices=list(WORKLOADS) + ["c5"])
+    ap.add_argument("--points", type=int, default=0, help="c5 only: number of sweep points to run (0 = all)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scorer", default="tcgen05", choices=["tcgen05", "popc"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
-    desc, tau, w_fp, k_fit = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "c5":
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
+        return run_product_sweep(args, rank, world, local_rank, real_stdout)
+    desc, tau, w_fp, k_fit = WORKLOADS[args.workload]
 
     if args.impl == "reference":
         if rank != 0:
@@ -182,6 +306,10 @@ def main():
                 "e2e": {"value": cpu["value"], "unit": "Gop/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
+
+    # exactly ONE line may reach stdout: libraries (NCCL's version banner, torchrun) write to fd 1 too
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -230,12 +358,13 @@ def main():
             best = score
             nb_t -= 1
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                             # nvidia-smi needs ~0.2 s to come up: start it early
     for _ in range(args.warmup):
         greedy_step(False)
-    sampler = ClockSampler(local_rank)
     launches0 = eng.launches
     barrier()
-    sampler.start()
+    sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):
@@ -310,7 +439,10 @@ def main():
                 "clocks": clocks, "gpu_launches": launches, "setup_seconds": setup_s,
                 "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
                 "fit_seconds": e2e["fit_seconds"] if e2e else None}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
     return 0

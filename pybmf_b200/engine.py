@@ -73,9 +73,11 @@ class CoverEngine:
         r0, r1 = self.plan.rows(self.rank)
         self.r0, self.r1 = r0, r1
         self.m_loc = r1 - r0
-        Xp = device.to_csr_pattern(X)
-        Xl = Xp[r0:r1] if self.world > 1 else Xp
-        self.sum_x = int(Xp.nnz)
+        # each rank canonicalises only ITS rows; the total number of ones is one scalar all-reduce
+        Xl = device.to_csr_pattern(X[r0:r1] if self.world > 1 else X)
+        nnz = torch.tensor([int(Xl.nnz)], dtype=torch.int64, device=device.dev())
+        all_reduce_sum(nnz)
+        self.sum_x = int(nnz.item())
         self.w_fp, self.w_fn = float(w_fp), float(w_fn)
         iw = integer_weights(self.w_fp, self.w_fn)
         self.wa, self.wb, self.shift = iw if iw else (0, 0, 0)
