@@ -226,6 +226,16 @@ def run_product_sweep(args, rank, world, local_rank, real_stdout):
                         "kernels_agree": ok})
         del x, pd, uw, vt
         torch.cuda.empty_cache()
+    ceilings = None
+    if rank == 0:
+        # context: what a pure write / pure read stream reaches on this box with library kernels
+        buf = torch.empty((1 << 30,), dtype=torch.int64, device="cuda")           # 8 GiB
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        buf.zero_(); buf.sum(); torch.cuda.synchronize()
+        e[0].record(); buf.zero_(); e[1].record(); buf.sum(); e[2].record(); torch.cuda.synchronize()
+        ceilings = {"memset_write_only_gbs": buf.numel() * 8 / (e[0].elapsed_time(e[1]) / 1e3) / 1e9,
+                    "sum_read_only_gbs": buf.numel() * 8 / (e[1].elapsed_time(e[2]) / 1e3) / 1e9}
+        del buf
     if rank == 0:
         last = results[-1]
         hbm = float(peaks.get("hbm_gbs", 6650.0)) * world
@@ -240,7 +250,7 @@ def run_product_sweep(args, rank, world, local_rank, real_stdout):
                 "roofline": {"bound": "hbm", "achieved": value / world, "peak": hbm / world, "unit": "GB/s",
                              "frac": value / hbm, "traffic": None, "kernel": "bool_product_kernel + confusion_kernel<true>",
                              "peak_source": peak_src},
-                "sweep": results, "gpu_launches": 2 * args.steps * len(results)}
+                "sweep": results, "library_stream_ceilings": ceilings, "gpu_launches": 2 * args.steps * len(results)}
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
