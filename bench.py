@@ -153,8 +153,10 @@ def run_product_sweep(args, rank, world, local_rank, real_stdout):
     peaks, peak_src = load_peaks()
     k = 64
     points = [(10_000, 1_000), (100_000, 10_000), (1_000_000, 10_000), (100_000, 100_000), (1_000_000, 100_000)]
-    if args.points:
+    if args.points > 0:
         points = points[: args.points]
+    elif args.points < 0:
+        points = points[args.points:]                            # e.g. --points -1: only the largest
     results = []
     stream = torch.cuda.current_stream()
     for (m, n) in points:
@@ -188,11 +190,12 @@ def run_product_sweep(args, rank, world, local_rank, real_stdout):
         x[:, (n + 63) // 64:] = 0
         counts = device.zeros((3,), torch.int64)
         counts2 = device.zeros((3,), torch.int64)
+        _native.call("bmf_confusion_bits", x, x, m_loc, words, -1, counts2, None, None)
+        x_ones = int(counts2[0].item())                          # |X| of this rank's rows (the csr nnz in real use)
 
         def step():
             _native.call("bmf_bool_product", uw, m_loc, 1, vt, k, words, pd)
-            counts.zero_()
-            _native.call("bmf_confusion_factors", x, m_loc, words, uw, 1, vt, k, counts, None, None)
+            _native.call("bmf_confusion_factors", x, m_loc, words, uw, 1, vt, k, x_ones, counts, None, None)
         for _ in range(max(args.warmup, 1)):
             step()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -204,8 +207,7 @@ def run_product_sweep(args, rank, world, local_rank, real_stdout):
             _native.call("bmf_bool_product", uw, m_loc, 1, vt, k, words, pd)
         ev[1].record(stream)
         for _ in range(args.steps):
-            counts.zero_()
-            _native.call("bmf_confusion_factors", x, m_loc, words, uw, 1, vt, k, counts, None, None)
+            _native.call("bmf_confusion_factors", x, m_loc, words, uw, 1, vt, k, x_ones, counts, None, None)
         ev[2].record(stream)
         if world > 1:
             dist.barrier()
@@ -214,7 +216,7 @@ def run_product_sweep(args, rank, world, local_rank, real_stdout):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         # size-independent checks: the two confusion kernels agree, and TP + FN = |X|, TP + FP = |product|
-        _native.call("bmf_confusion_bits", x, pd, m_loc, words, counts2, None, None)
+        _native.call("bmf_confusion_bits", x, pd, m_loc, words, -1, counts2, None, None)            # counts |gt| itself
         ok = bool(torch.equal(counts, counts2))
         all_reduce_sum(counts)
         tp, fp, fn = (int(v) for v in counts.cpu().numpy())

@@ -137,13 +137,16 @@ int bmf_cover_apply(const uint64_t* x_bits, uint64_t* c_bits, int64_t m, int64_t
 int bmf_bool_product(const uint64_t* u_words, int64_t m, int64_t kw, const uint64_t* vt_bits,
                      int64_t k, int64_t words, uint64_t* pd_bits, bmf_stream_t stream);
 /* TP/FP/FN of PyBMF/utils/metrics.py:56-76 against the product computed on the fly
- * (never materialised).  counts[0..2] += (TP, FP, FN); row_tp/row_fp nullable int32[m]. */
+ * (never materialised).  counts[0..2] = (TP, FP, FN) (overwritten); row_tp/row_fp nullable int32[m].
+ * gt_ones = number of ones in gt_bits when the caller knows it (the csr nnz), which saves the
+ * kernel a third of its popcounts; pass -1 to have it counted. */
 int bmf_confusion_factors(const uint64_t* gt_bits, int64_t m, int64_t words, const uint64_t* u_words,
-                          int64_t kw, const uint64_t* vt_bits, int64_t k, int64_t* counts,
+                          int64_t kw, const uint64_t* vt_bits, int64_t k, int64_t gt_ones, int64_t* counts,
                           int32_t* row_tp, int32_t* row_fp, bmf_stream_t stream);
 /* same against a materialised prediction */
 int bmf_confusion_bits(const uint64_t* gt_bits, const uint64_t* pd_bits, int64_t m, int64_t words,
-                       int64_t* counts, int32_t* row_tp, int32_t* row_fp, bmf_stream_t stream);
+                       int64_t gt_ones, int64_t* counts, int32_t* row_tp, int32_t* row_fp,
+                       bmf_stream_t stream);
 /* add(boolean=True) / multiply(boolean=True), PyBMF/utils/boolean_utils.py:87-107 / 6-33, and the
  * residual X AND NOT C of get_residual (PyBMF/utils/common.py:154-160):
  * out = a OR b (op 0), a AND b (op 1), a AND NOT b (op 2) on [rows][words] bit matrices. */

@@ -2,6 +2,8 @@
 // covered-mask update, Boolean product, confusion counts, AssoIter column refinement.
 // All of these are streaming integer kernels bound by HBM bandwidth or by the integer
 // pipe (POPC); rows are 16-byte aligned so every row stream uses 128-bit loads.
+#include <stdlib.h>
+
 #include "bmf_common.cuh"
 
 namespace bmf {
@@ -321,10 +323,10 @@ cover_apply_kernel(const uint64_t* __restrict__ xb, uint64_t* __restrict__ cb, i
       const ulonglong2 c = *reinterpret_cast<const ulonglong2*>(cb + i * words + 2 * p);
       const ulonglong2 v = ld_words2(b + 2 * p);
       P += __popcll(x.x & ~c.x & v.x) + __popcll(x.y & ~c.y & v.y);
-      N += __popcll(~x.x & ~c.x & v.x) + __popcll(~x.y & ~c.y & v.y);   // v has zero pad bits
+      N += __popcll(~c.x & v.x) + __popcll(~c.y & v.y);                 // |v & ~c| (v has zero pad bits), minus P below
     }
     P = warp_sum(P);
-    N = warp_sum(N);
+    N = warp_sum(N) - P;
     const int tpo = tp_old[i], fpo = fp_old[i];
     if (!row_uses(wa, wb, neg_w_fp, w_fn, tpo, fpo, P, N)) continue;    // warp-uniform
     for (int64_t p = lane; p < pairs; p += 32) {
@@ -410,7 +412,12 @@ bool_product_kernel(const uint64_t* __restrict__ u_words, int64_t m, int64_t kw,
   }
 }
 
-template <bool FROM_FACTORS>
+// Confusion counts.  Per word only TWO (three when |gt| is not known) popcounts are taken:
+// TP = |gt & pd| and |pd| (FP = |pd| - TP); FN = |gt| - TP with |gt| either supplied by the caller
+// (the number of stored ones, free on the host) or counted (COUNT_GT).  The integer (POPC/ALU) pipe is
+// the busiest unit of this kernel, so the main loop runs without bounds checks on whole groups of
+// 4 x 32 pairs with pointer increments, and a checked tail handles the last < 128 pairs of a row.
+template <bool FROM_FACTORS, bool COUNT_GT>
 __global__ void __launch_bounds__(256)
 confusion_kernel(const uint64_t* __restrict__ gt, const uint64_t* __restrict__ pd_bits, int64_t m,
                  int64_t words, const uint64_t* __restrict__ u_words, int64_t kw,
@@ -420,41 +427,91 @@ confusion_kernel(const uint64_t* __restrict__ gt, const uint64_t* __restrict__ p
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t pairs = words >> 1;
-  long long t_tp = 0, t_fp = 0, t_fn = 0;
+  const int64_t full = pairs / (32 * PU);                    // unchecked groups per row
+  long long t_tp = 0, t_pd = 0, t_gt = 0;
   for (int64_t i = warp0; i < m; i += nwarps) {
-    int tp = 0, fp = 0, fn = 0;
-    for (int64_t p0 = lane; p0 < pairs; p0 += 32 * PU) {
+    int tp = 0, np = 0, ng = 0;
+    const ulonglong2* gp = reinterpret_cast<const ulonglong2*>(gt + i * words) + lane;
+    const ulonglong2* dp = FROM_FACTORS ? nullptr : reinterpret_cast<const ulonglong2*>(pd_bits + i * words) + lane;
+    const uint64_t* uw = FROM_FACTORS ? u_words + i * kw : nullptr;
+    for (int64_t it = 0; it < full; ++it) {
       ulonglong2 g[PU], d[PU];
 #pragma unroll
-      for (int u = 0; u < PU; ++u) {                         // issue the HBM loads of the whole group first
-        const int64_t p = p0 + 32 * u;
-        g[u] = make_ulonglong2(0ull, 0ull);
-        if (p < pairs) g[u] = __ldcs(reinterpret_cast<const ulonglong2*>(gt + i * words + 2 * p));
-        if (!FROM_FACTORS) {
-          d[u] = make_ulonglong2(0ull, 0ull);
-          if (p < pairs) d[u] = __ldcs(reinterpret_cast<const ulonglong2*>(pd_bits + i * words + 2 * p));
+      for (int u = 0; u < PU; ++u) g[u] = __ldcs(gp + 32 * u);
+      if (!FROM_FACTORS) {
+#pragma unroll
+        for (int u = 0; u < PU; ++u) d[u] = __ldcs(dp + 32 * u);
+        dp += 32 * PU;
+      } else {
+#pragma unroll
+        for (int u = 0; u < PU; ++u) d[u] = make_ulonglong2(0ull, 0ull);
+        for (int64_t q = 0; q < kw; ++q) {
+          uint64_t sel = uw[q];
+          while (sel) {
+            const int l = __ffsll((long long)sel) - 1;
+            sel &= sel - 1;
+            const ulonglong2* vp = reinterpret_cast<const ulonglong2*>(vt + (q * 64 + l) * words) + it * (32 * PU) + lane;
+#pragma unroll
+            for (int u = 0; u < PU; ++u) {
+              const ulonglong2 v = __ldg(vp + 32 * u);
+              d[u].x |= v.x;
+              d[u].y |= v.y;
+            }
+          }
         }
       }
-      if (FROM_FACTORS) product_quad(u_words + i * kw, kw, vt, words, p0, pairs, -1, d);
+      gp += 32 * PU;
 #pragma unroll
       for (int u = 0; u < PU; ++u) {
         tp += __popcll(g[u].x & d[u].x) + __popcll(g[u].y & d[u].y);
-        fp += __popcll(~g[u].x & d[u].x) + __popcll(~g[u].y & d[u].y);
-        fn += __popcll(g[u].x & ~d[u].x) + __popcll(g[u].y & ~d[u].y);
+        np += __popcll(d[u].x) + __popcll(d[u].y);
+        if (COUNT_GT) ng += __popcll(g[u].x) + __popcll(g[u].y);
       }
     }
-    tp = warp_sum(tp); fp = warp_sum(fp); fn = warp_sum(fn);
+    {                                                         // checked tail
+      const int64_t p0 = full * (32 * PU) + lane;
+      if (full * (32 * PU) < pairs) {
+        ulonglong2 g[PU], d[PU];
+#pragma unroll
+        for (int u = 0; u < PU; ++u) {
+          const int64_t p = p0 + 32 * u;
+          g[u] = make_ulonglong2(0ull, 0ull);
+          d[u] = make_ulonglong2(0ull, 0ull);
+          if (p < pairs) {
+            g[u] = __ldcs(reinterpret_cast<const ulonglong2*>(gt + i * words + 2 * p));
+            if (!FROM_FACTORS) d[u] = __ldcs(reinterpret_cast<const ulonglong2*>(pd_bits + i * words + 2 * p));
+          }
+        }
+        if (FROM_FACTORS) product_quad(uw, kw, vt, words, p0, pairs, -1, d);
+#pragma unroll
+        for (int u = 0; u < PU; ++u) {
+          tp += __popcll(g[u].x & d[u].x) + __popcll(g[u].y & d[u].y);
+          np += __popcll(d[u].x) + __popcll(d[u].y);
+          if (COUNT_GT) ng += __popcll(g[u].x) + __popcll(g[u].y);
+        }
+      }
+    }
+    tp = warp_sum(tp);
+    np = warp_sum(np);
+    if (COUNT_GT) ng = warp_sum(ng);
     if (lane == 0) {
       if (row_tp != nullptr) row_tp[i] = tp;
-      if (row_fp != nullptr) row_fp[i] = fp;
-      t_tp += tp; t_fp += fp; t_fn += fn;
+      if (row_fp != nullptr) row_fp[i] = np - tp;
+      t_tp += tp; t_pd += np; t_gt += ng;
     }
   }
-  if (lane == 0 && (t_tp | t_fp | t_fn)) {
+  if (lane == 0 && (t_pd | t_gt)) {
     atomicAdd(counts + 0, (unsigned long long)t_tp);
-    atomicAdd(counts + 1, (unsigned long long)t_fp);
-    atomicAdd(counts + 2, (unsigned long long)t_fn);
+    atomicAdd(counts + 1, (unsigned long long)t_pd);
+    if (COUNT_GT) atomicAdd(counts + 2, (unsigned long long)t_gt);
   }
+}
+
+// counts = (TP, |pd|, |gt| or unused) -> (TP, FP, FN)
+__global__ void confusion_finalize_kernel(long long* __restrict__ counts, long long gt_ones) {
+  const long long tp = counts[0], pd = counts[1], g = gt_ones >= 0 ? gt_ones : counts[2];
+  counts[1] = pd - tp;
+  counts[2] = g - tp;
 }
 
 // elementwise Boolean algebra on bit rows: op 0 = OR (add), 1 = AND (multiply), 2 = AND-NOT (residual)
@@ -523,12 +580,12 @@ refine_column_kernel(const uint64_t* __restrict__ xb, int64_t m, int64_t n, int6
         if (p >= pairs) continue;
         const ulonglong2 v = ld_words2(vcol + 2 * p);
         tpo += __popcll(x[u].x & c[u].x) + __popcll(x[u].y & c[u].y);
-        fpo += __popcll(~x[u].x & c[u].x) + __popcll(~x[u].y & c[u].y);
+        fpo += __popcll(c[u].x) + __popcll(c[u].y);                      // |c|, minus tpo below
         P += __popcll(x[u].x & ~c[u].x & v.x) + __popcll(x[u].y & ~c[u].y & v.y);
-        N += __popcll(~x[u].x & ~c[u].x & v.x) + __popcll(~x[u].y & ~c[u].y & v.y);
+        N += __popcll(~c[u].x & v.x) + __popcll(~c[u].y & v.y);          // |v & ~c|, minus P below
       }
     }
-    tpo = warp_sum(tpo); fpo = warp_sum(fpo); P = warp_sum(P); N = warp_sum(N);
+    tpo = warp_sum(tpo); fpo = warp_sum(fpo) - tpo; P = warp_sum(P); N = warp_sum(N) - P;
     const bool use = row_uses(wa, wb, neg_w_fp, w_fn, tpo, fpo, P, N);
     __syncwarp();
     if (lane == 0) {
@@ -685,30 +742,42 @@ extern "C" int bmf_bool_product(const uint64_t* u_words, int64_t m, int64_t kw, 
   return 0;
 }
 
-extern "C" int bmf_confusion_factors(const uint64_t* gt_bits, int64_t m, int64_t words, const uint64_t* u_words,
-                                     int64_t kw, const uint64_t* vt_bits, int64_t k, int64_t* counts,
-                                     int32_t* row_tp, int32_t* row_fp, bmf_stream_t stream) {
-  BMF_REQUIRE(gt_bits && u_words && counts && m > 0 && kw > 0 && k <= kw * 64, "bmf_confusion_factors: bad arguments");
-  BMF_REQUIRE(words > 0 && words % 2 == 0 && (k == 0 || vt_bits), "bmf_confusion_factors: bad words / vt_bits");
+template <bool FROM_FACTORS>
+static int launch_confusion(const uint64_t* gt_bits, const uint64_t* pd_bits, int64_t m, int64_t words,
+                            const uint64_t* u_words, int64_t kw, const uint64_t* vt_bits, int64_t gt_ones,
+                            int64_t* counts, int32_t* row_tp, int32_t* row_fp, cudaStream_t st, const char* who) {
+  int rc = check_cuda(cudaMemsetAsync(counts, 0, 3 * sizeof(int64_t), st), who);
+  if (rc) return rc;
+  unsigned long long* c = reinterpret_cast<unsigned long long*>(counts);
   int64_t blocks = ceil_div(m, 8);
   if (blocks > row_stream_grid()) blocks = row_stream_grid();
-  confusion_kernel<true><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
-      gt_bits, nullptr, m, words, u_words, kw, vt_bits, reinterpret_cast<unsigned long long*>(counts), row_tp,
-      row_fp);
-  BMF_LAUNCH_CHECK("bmf_confusion_factors");
-  return 0;
+  if (gt_ones >= 0)
+    confusion_kernel<FROM_FACTORS, false><<<(unsigned)blocks, 256, 0, st>>>(gt_bits, pd_bits, m, words, u_words, kw,
+                                                                          vt_bits, c, row_tp, row_fp);
+  else
+    confusion_kernel<FROM_FACTORS, true><<<(unsigned)blocks, 256, 0, st>>>(gt_bits, pd_bits, m, words, u_words, kw,
+                                                                         vt_bits, c, row_tp, row_fp);
+  rc = check_cuda(cudaGetLastError(), who);
+  if (rc) return rc;
+  confusion_finalize_kernel<<<1, 1, 0, st>>>(reinterpret_cast<long long*>(counts), (long long)gt_ones);
+  return check_cuda(cudaGetLastError(), who);
+}
+
+extern "C" int bmf_confusion_factors(const uint64_t* gt_bits, int64_t m, int64_t words, const uint64_t* u_words,
+                                     int64_t kw, const uint64_t* vt_bits, int64_t k, int64_t gt_ones,
+                                     int64_t* counts, int32_t* row_tp, int32_t* row_fp, bmf_stream_t stream) {
+  BMF_REQUIRE(gt_bits && u_words && counts && m > 0 && kw > 0 && k <= kw * 64, "bmf_confusion_factors: bad arguments");
+  BMF_REQUIRE(words > 0 && words % 2 == 0 && (k == 0 || vt_bits), "bmf_confusion_factors: bad words / vt_bits");
+  return launch_confusion<true>(gt_bits, nullptr, m, words, u_words, kw, vt_bits, gt_ones, counts, row_tp, row_fp,
+                                as_stream(stream), "bmf_confusion_factors");
 }
 
 extern "C" int bmf_confusion_bits(const uint64_t* gt_bits, const uint64_t* pd_bits, int64_t m, int64_t words,
-                                  int64_t* counts, int32_t* row_tp, int32_t* row_fp, bmf_stream_t stream) {
+                                  int64_t gt_ones, int64_t* counts, int32_t* row_tp, int32_t* row_fp,
+                                  bmf_stream_t stream) {
   BMF_REQUIRE(gt_bits && pd_bits && counts && m > 0 && words > 0 && words % 2 == 0, "bmf_confusion_bits: bad arguments");
-  int64_t blocks = ceil_div(m, 8);
-  if (blocks > row_stream_grid()) blocks = row_stream_grid();
-  confusion_kernel<false><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
-      gt_bits, pd_bits, m, words, nullptr, 0, nullptr, reinterpret_cast<unsigned long long*>(counts), row_tp,
-      row_fp);
-  BMF_LAUNCH_CHECK("bmf_confusion_bits");
-  return 0;
+  return launch_confusion<false>(gt_bits, pd_bits, m, words, nullptr, 0, nullptr, gt_ones, counts, row_tp, row_fp,
+                                 as_stream(stream), "bmf_confusion_bits");
 }
 
 extern "C" int bmf_bits_combine(const uint64_t* a_bits, const uint64_t* b_bits, int64_t rows, int64_t words, int op,

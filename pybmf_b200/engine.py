@@ -268,7 +268,7 @@ class CoverEngine:
             vt = torch.stack([self.basis_bits[j] for (_ui, j) in kept]).contiguous()
             _native.call("bmf_bool_product", uw, self.m_loc, kw, vt, k, self.words, self.c_bits)
             counts = device.zeros((3,), torch.int64)
-            _native.call("bmf_confusion_bits", self.x_bits, self.c_bits, self.m_loc, self.words, counts,
+            _native.call("bmf_confusion_bits", self.x_bits, self.c_bits, self.m_loc, self.words, -1, counts,
                          self.tp_old, self.fp_old)
             self.launches += 2
             all_reduce_sum(counts)

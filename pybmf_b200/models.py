@@ -224,7 +224,7 @@ class BaseModel:
             counts = device.zeros((3,), torch.int64)
             vt = U_._bits_on_device(Vp.T.tocsr())
             _native.call("bmf_confusion_factors", U_._bits_on_device(G), m, device.words_for(n), uw, kw, vt,
-                         Up.shape[1], counts, None, None)
+                         Up.shape[1], int(G.nnz), counts, None, None)
             tp, fp, fn = (int(v) for v in counts.cpu().numpy())
             return tp, fp, fn, m * n
         r, c, g = U_.to_triplet(X)
@@ -534,7 +534,7 @@ class AssoIter(Asso):
         uw, kw = U_._factor_words(U_._pattern(self.U))
         vt = U_._bits_on_device(U_._pattern(self.V).T.tocsr())
         counts = device.zeros((3,), torch.int64)
-        _native.call("bmf_confusion_factors", x_bits, m, words, uw, kw, vt, kU, counts, None, None)
+        _native.call("bmf_confusion_factors", x_bits, m, words, uw, kw, vt, kU, sum_x, counts, None, None)
         tp, fp, _fn = (int(v) for v in counts.cpu().numpy())
         best_score = -w_fp * np.array(fp, dtype=np.int64) + w_fn * np.array(tp, dtype=np.int64)   # AssoIter.py:52
         best_error = U_.rates(tp, fp, sum_x - tp, size)["ERR"]

@@ -217,7 +217,7 @@ def confusion_counts(gt, pd, axis=None):
     row_fp = device.zeros((max(m, 1),), torch.int32)
     if m > 0:
         gb, pb = _bits_on_device(G), _bits_on_device(P)
-        _native.call("bmf_confusion_bits", gb, pb, m, words, counts, row_tp, row_fp)
+        _native.call("bmf_confusion_bits", gb, pb, m, words, int(G.nnz), counts, row_tp, row_fp)
     if axis is None:
         tp, fp, fn = (int(v) for v in counts.cpu().numpy())
         return tp, fp, fn
@@ -374,7 +374,7 @@ def eval(metrics, task, X_gt, X_pd=None, U=None, V=None):
         counts = device.zeros((3,), torch.int64)
         vt = _bits_on_device(Vp.T.tocsr())
         _native.call("bmf_confusion_factors", _bits_on_device(G), m, device.words_for(n), uw, kw, vt, Up.shape[1],
-                     counts, None, None)
+                     int(G.nnz), counts, None, None)
         tp, fp, fn = (int(v) for v in counts.cpu().numpy())
         return metrics_from_counts(metrics, tp, fp, fn, m * n)
     r, c, g = to_triplet(X_gt)

@@ -275,7 +275,7 @@ def test_cover_apply(nat, w):
     assert torch.equal(before, c_d)
 
 
-@pytest.mark.parametrize("m,n,k", [(50, 70, 1), (300, 500, 5), (257, 129, 64), (100, 200, 70)])
+@pytest.mark.parametrize("m,n,k", [(50, 70, 1), (300, 500, 5), (257, 129, 64), (100, 200, 70), (40, 20000, 9)])
 def test_bool_product_and_confusion(nat, m, n, k):
     _native, device = nat
     rng = np.random.RandomState(m + n + k)
@@ -293,15 +293,15 @@ def test_bool_product_and_confusion(nat, m, n, k):
     assert np.array_equal(pd.cpu().numpy(), device.dense_to_words(want))
     tp, fp, fn = O.confusion(X, want)
     rtp, rfp, _ = O.confusion(X, want, axis=1)
-    for mode in ("factors", "bits"):
-        counts = device.zeros((3,), torch.int64)
+    for mode, ones in (("factors", -1), ("bits", -1), ("factors", int(X.sum())), ("bits", int(X.sum()))):
+        counts = device.zeros((3,), torch.int64) + 12345            # overwritten, not accumulated
         row_tp = device.zeros((m,), torch.int32)
         row_fp = device.zeros((m,), torch.int32)
         if mode == "factors":
             _native.call("bmf_confusion_factors", _dev(device.dense_to_words(X)), m, words, _dev(uw), kw, _dev(vt), k,
-                         counts, row_tp, row_fp)
+                         ones, counts, row_tp, row_fp)
         else:
-            _native.call("bmf_confusion_bits", _dev(device.dense_to_words(X)), pd, m, words, counts, row_tp, row_fp)
+            _native.call("bmf_confusion_bits", _dev(device.dense_to_words(X)), pd, m, words, ones, counts, row_tp, row_fp)
         assert list(counts.cpu().numpy()) == [int(tp), int(fp), int(fn)]
         assert np.array_equal(row_tp.cpu().numpy(), rtp) and np.array_equal(row_fp.cpu().numpy(), rfp)
 
