@@ -221,6 +221,25 @@ def test_c2_shape_first_steps_match_oracle(M):
         assert [float(v) for v in df[("train", 0, col)]] == [float(l[col]) for l in r["logs"]], col
 
 
+def test_c3_shape_assoiter_matches_oracle(M):
+    """BASELINE.json configs[2]: AssoIter on the 6040 x 3706 shape, refinement trace against the oracle."""
+    from pybmf_b200 import synth
+    X = synth.config_c2()
+    mdl = M.Asso(tau=0.5, k=4, w_fp=0.5)
+    mdl.fit(X, **FIT_KW)
+    U0, V0 = _dense(mdl.U), _dense(mdl.V)
+    ref = O.asso_iter_fit(X, U0, V0, 4, 0.5)
+    it = M.AssoIter(model=mdl, w_fp=0.5)
+    it.fit(X, **FIT_KW)
+    assert np.array_equal(_dense(it.U), ref["U"])
+    accepted = [c for c, a in ref["trace"] if a]
+    if accepted:
+        df = it.logs["refinements"]
+        assert [int(v) for v in df.iloc[:, 1]] == accepted
+        assert [float(v) for v in df[("train", 0, "score")]] == [r["score"] for r in ref["refinements"]]
+        assert [float(v) for v in df[("train", 0, "error")]] == [r["error"] for r in ref["refinements"]]
+
+
 def test_model_is_picklable_and_lazy_attrs(M, tmp_path):
     import pickle
     c = load_golden("planted_w025")
