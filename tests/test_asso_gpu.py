@@ -240,6 +240,77 @@ def test_c3_shape_assoiter_matches_oracle(M):
         assert [float(v) for v in df[("train", 0, "error")]] == [r["error"] for r in ref["refinements"]]
 
 
+def test_transposed_model(M):
+    """PyBMF/models/TransposedModel.py: Asso on X^T with swapped factors."""
+    c = load_golden("planted_w025")
+    X = sp.csr_matrix(c["X"])
+    inner = M.Asso(tau=c["tau"], k=c["k"], w_fp=c["w_fp"])
+    tm = M.TransposedModel(model=inner)
+    tm.fit(X, **FIT_KW)
+    r = O.asso_fit(c["X"].T, c["k"], c["tau"], c["w_fp"], c["w_fn"])
+    assert np.array_equal(_dense(tm.U), r["V"]) and np.array_equal(_dense(tm.V), r["U"])
+
+
+def test_c4_full_size_properties(M):
+    """BASELINE.json configs[3] at FULL size (480189 x 17770): size-independent properties.
+    (a) the tensor-core scorer (both GEMM variants) and the popcount scorer agree bit for bit on all gains;
+    (b) after applying the winner, the per-row counters equal an independent confusion pass, and the
+        covered mask equals the Boolean product of the chosen factor;
+    (c) row shards sum to the whole (the multi-GPU algebra)."""
+    import os
+    from pybmf_b200 import _native, device, synth
+    from pybmf_b200.engine import CoverEngine
+    X = synth.config_c4()
+    eng = CoverEngine(X, 0.5, 0.5, scorer="tcgen05")
+    nb = eng.build_basis(0.5)
+    assert nb == int(eng.alive.sum().item()) and nb > 17000
+    eng.score_all()
+    g_pair = eng.gain_p.clone()
+    os.environ["BMF_GEMM_VARIANT"] = "1"
+    try:
+        eng.score_all()
+    finally:
+        del os.environ["BMF_GEMM_VARIANT"]
+    assert torch.equal(g_pair, eng.gain_p)                          # cta_group::2 == cta_group::1
+    gp = device.zeros((eng.cand_pad,), torch.int64)
+    _native.call("bmf_cover_score_popc", eng.x_bits, eng.c_bits, eng.m_loc, eng.n, eng.words, eng.basis_bits,
+                 eng.alive, eng.tp_old, eng.fp_old, 1, 1, 0.5, 0.5, gp, None)
+    live = eng.alive.bool()
+    assert torch.equal(gp[: eng.n][live], g_pair[: eng.n][live])    # tensor cores == AND+POPC
+    # (c) shard algebra on the popcount kernel: three row slices sum to the whole
+    parts = torch.zeros_like(gp)
+    m = eng.m_loc
+    for a, b in ((0, 160000), (160000, 320000), (320000, m)):
+        gpart = device.zeros((eng.cand_pad,), torch.int64)
+        _native.call("bmf_cover_score_popc", eng.x_bits[a:b], eng.c_bits[a:b], b - a, eng.n, eng.words, eng.basis_bits,
+                     eng.alive, eng.tp_old[a:b], eng.fp_old[a:b], 1, 1, 0.5, 0.5, gpart, None)
+        parts += gpart
+    assert torch.equal(parts, gp)
+    # (b) apply and cross-check the state with independent kernels
+    winner, score, used, sp_, sn_ = eng.select_and_apply(0.0)
+    assert winner >= 0 and used > 0 and score == 0.5 * int(g_pair[winner].item())
+    counts = device.zeros((3,), torch.int64)
+    rtp = device.zeros((m,), torch.int32)
+    rfp = device.zeros((m,), torch.int32)
+    _native.call("bmf_confusion_bits", eng.x_bits, eng.c_bits, m, eng.words, eng.sum_x, counts, rtp, rfp)
+    assert torch.equal(rtp, eng.tp_old) and torch.equal(rfp, eng.fp_old)
+    c = counts.cpu().numpy()
+    assert int(c[0]) == eng.tp_tot == sp_ and int(c[1]) == eng.fp_tot == sn_ and int(c[0]) + int(c[2]) == eng.sum_x
+    uw = eng.u_cols[0]
+    ucol = torch.from_numpy(device.words_to_dense(uw.cpu().numpy().reshape(1, -1), m)[0].astype(np.int64)).cuda()
+    assert int(ucol.sum().item()) == used
+    pd = device.zeros((m, eng.words), torch.int64)
+    _native.call("bmf_bool_product", ucol.reshape(-1, 1).contiguous(), m, 1, eng.basis_bits[winner:winner + 1].contiguous(),
+                 1, eng.words, pd)
+    assert torch.equal(pd, eng.c_bits)
+    # the next step's gains agree again between the two scorers (operand plane was updated in place)
+    eng.score_all()
+    _native.call("bmf_cover_score_popc", eng.x_bits, eng.c_bits, m, eng.n, eng.words, eng.basis_bits, eng.alive,
+                 eng.tp_old, eng.fp_old, 1, 1, 0.5, 0.5, gp, None)
+    live = eng.alive.bool()
+    assert torch.equal(gp[: eng.n][live], eng.gain_p[: eng.n][live])
+
+
 def test_model_is_picklable_and_lazy_attrs(M, tmp_path):
     import pickle
     c = load_golden("planted_w025")
