@@ -291,6 +291,9 @@ def main():
     ap.add_argument("--points", type=int, default=0, help="c5 only: number of sweep points to run (0 = all)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scorer", default="tcgen05", choices=["tcgen05", "popc"])
+    ap.add_argument("--w-fp", type=float, default=None,
+                    help="override the workload's w_fp (w_fn = 1 - w_fp); a non-dyadic value such as 0.2 runs the "
+                         "general-weights scorer (two contractions per element, credited 2*m*n*nb like the others)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -303,6 +306,9 @@ def main():
         os.dup2(2, 1)
         return run_product_sweep(args, rank, world, local_rank, real_stdout)
     desc, tau, w_fp, k_fit = WORKLOADS[args.workload]
+    if args.w_fp is not None:
+        w_fp = float(args.w_fp)
+        desc = desc.replace("w=[0.5,0.5]", "w=[%g,%g]" % (w_fp, 1 - w_fp))
 
     if args.impl == "reference":
         if rank != 0:
@@ -397,8 +403,14 @@ def main():
     ops_launch = statistics.mean(ops_per_step) / world if ops_per_step else 0.0     # rows are sharded evenly
     achieved = ops_launch / (kern_ms / 1e3) / 1e12
     peak_i8 = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+    if args.scorer != "tcgen05":
+        kernel_name = "cover_score_popc_kernel"
+    elif eng.encoding == "pq":
+        kernel_name = "gemm_i8_2sm_kernel<EPI_GAIN2> (tcgen05 kind::i8, cta_group::2; P and Q contractions = 2x hardware ops)"
+    else:
+        kernel_name = "gemm_i8_2sm_kernel<EPI_GAIN> (tcgen05 kind::i8, cta_group::2)"
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_i8, "unit": "TFLOP/s", "frac": achieved / peak_i8,
-                "traffic": None, "kernel": "gemm_i8_kernel<EPI_GAIN> (tcgen05 kind::i8)" if args.scorer == "tcgen05" else "cover_score_popc_kernel",
+                "traffic": None, "kernel": kernel_name,
                 "peak_source": "2 x bf16_tflops (burst) of %s: kind::i8 runs at twice the bf16 rate and int8 is not in that file; "
                                "0/+-1 operands draw less power than cuBLAS's random bf16 so SM clocks stay near max" % peak_src,
                 "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms * len(score_ms) / (elapsed_s * 1e3) if score_ms else None,

@@ -109,6 +109,19 @@ int bmf_cover_score_i8(const int8_t* cand_plane, int64_t cand_pad, const int8_t*
                        int64_t rows_pad, int64_t ld, int32_t sign, const int32_t* cand_pop,
                        int32_t bias_scale, int64_t* gain, bmf_stream_t stream);
 
+/* tcgen05 kind::i8 variant for GENERAL weights (any fp64 w_fp, w_fn; e.g. the reference notebooks' w_fp = 0.2).
+ * pq_plane interleaves, per block of 128 data rows, 128 rows of P_i = x_i & ~c_i and 128 rows of Q_i = c_i
+ * (0/1 bytes; plane row of data row i = (i/128)*256 + i%128 for P, +128 for Q; 2*ceil(m/128)*128 rows of ld bytes,
+ * written by bmf_expand_bits_pq and kept current by bmf_cover_apply_general).  One contraction then yields
+ * P = |b_j & x_i & ~c_i| and Q = |b_j & c_i| side by side in the accumulator, N = cand_pop[j] - Q - P, and the
+ * fused epilogue evaluates use(i,j) with the literal fp64 expression above:
+ *   gain_p[j] = sum_{use} P, gain_n[j] = sum_{use} N   (cand_pad entries each, overwritten). */
+int bmf_expand_bits_pq(const uint64_t* x_bits, const uint64_t* c_bits, int64_t rows, int64_t ncols, int64_t words,
+                       int8_t* pq_plane, int64_t ld, bmf_stream_t stream);
+int bmf_cover_score_i8_general(const int8_t* cand_plane, int64_t cand_pad, const int8_t* pq_plane, int64_t m,
+                               int64_t ld, const int32_t* cand_pop, const int32_t* tp_old, const int32_t* fp_old,
+                               double w_fp, double w_fn, int64_t* gain_p, int64_t* gain_n, bmf_stream_t stream);
+
 /* argmax of Asso.py:94: first j (lowest index) among alive candidates whose score is
  * strictly greater than `best_score` and than every earlier score.
  * integer mode: score_j = (double)(base_int + gain_p[j]) * scale
@@ -129,6 +142,12 @@ int bmf_cover_apply(const uint64_t* x_bits, uint64_t* c_bits, int64_t m, int64_t
                     int32_t* fp_old, int32_t wa, int32_t wb, double w_fp, double w_fn,
                     int8_t* rows_plane, int64_t ld, int8_t covered_value, uint64_t* u_bits,
                     int64_t* totals, bmf_stream_t stream);
+
+/* same in general mode with the interleaved P/Q operand plane: newly covered entries get P = 0, Q = 1 */
+int bmf_cover_apply_general(const uint64_t* x_bits, uint64_t* c_bits, int64_t m, int64_t n, int64_t words,
+                            const uint64_t* basis_bits, uint8_t* alive, const int64_t* winner, int32_t* tp_old,
+                            int32_t* fp_old, double w_fp, double w_fn, int8_t* pq_plane, int64_t ld,
+                            uint64_t* u_bits, int64_t* totals, bmf_stream_t stream);
 
 /* ---- Boolean product and confusion counts ------------------------------------------------
  * get_prediction / matmul(boolean=True): PyBMF/utils/common.py:98-107, boolean_utils.py:61-84.

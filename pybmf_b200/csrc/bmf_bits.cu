@@ -55,6 +55,34 @@ __global__ void expand_bits_i8_kernel(const uint64_t* __restrict__ bits, const u
   }
 }
 
+// x bits + covered mask -> the interleaved P/Q operand of the general-weights tensor-core scorer:
+// per block of 128 data rows, 128 rows of P_i = x_i & ~c_i followed by 128 rows of Q_i = c_i (0/1 bytes);
+// plane row of data row i: (i / 128) * 256 + (i % 128) for P, + 128 for Q.  Padding rows / columns are 0.
+__global__ void expand_bits_pq_kernel(const uint64_t* __restrict__ xb, const uint64_t* __restrict__ cb,
+                                      int64_t rows, int64_t ncols, int64_t words, int8_t* __restrict__ plane,
+                                      int64_t plane_rows, int64_t ld) {
+  const int64_t chunks = ld >> 4;
+  const int64_t total = plane_rows * chunks;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pr = t / chunks, ch = t - pr * chunks;
+    const int64_t c0 = ch << 4;
+    const int64_t r = (pr >> 8) * 128 + (pr & 127);
+    const bool is_q = (pr & 128) != 0;
+    uint32_t out[4] = {0, 0, 0, 0};
+    const int64_t w = c0 >> 6;
+    if (r < rows && c0 < ncols && w < words) {
+      const uint32_t x16 = (uint32_t)((xb[r * words + w] >> (c0 & 63)) & 0xffffu);
+      const uint32_t c16 = (uint32_t)((cb[r * words + w] >> (c0 & 63)) & 0xffffu);
+      const uint32_t b16 = is_q ? c16 : (x16 & ~c16);
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (c0 + i < ncols) out[i >> 2] |= ((b16 >> i) & 1u) << ((i & 3) * 8);
+    }
+    *reinterpret_cast<uint4*>(plane + pr * ld + c0) = make_uint4(out[0], out[1], out[2], out[3]);
+  }
+}
+
 // =========================================================================================
 // popcount contraction tiles.  Block = 256 threads computes a 64 x 64 tile of
 // (row i of A) x (row j of B); thread (ty, tx) owns rows ty*4+r and columns c*16+tx so that
@@ -306,7 +334,7 @@ cover_apply_kernel(const uint64_t* __restrict__ xb, uint64_t* __restrict__ cb, i
                    int64_t words, const uint64_t* __restrict__ basis, uint8_t* __restrict__ alive,
                    const int64_t* __restrict__ winner, int32_t* __restrict__ tp_old,
                    int32_t* __restrict__ fp_old, int wa, int wb, double neg_w_fp, double w_fn,
-                   int8_t* __restrict__ rows_plane, int64_t ld, int covered_value,
+                   int8_t* __restrict__ rows_plane, int64_t ld, int covered_value, int pq_layout,
                    unsigned long long* __restrict__ u_bits, unsigned long long* __restrict__ totals) {
   const int64_t j = *winner;
   if (j < 0) return;
@@ -335,9 +363,16 @@ cover_apply_kernel(const uint64_t* __restrict__ xb, uint64_t* __restrict__ cb, i
       const ulonglong2 v = ld_words2(b + 2 * p);
       if (rows_plane != nullptr) {
         uint64_t s0 = v.x & ~c.x, s1 = v.y & ~c.y;                      // newly covered columns
-        int8_t* rowp = rows_plane + i * ld + p * 128;
-        while (s0) { const int k = __ffsll((long long)s0) - 1; s0 &= s0 - 1; rowp[k] = (int8_t)covered_value; }
-        while (s1) { const int k = __ffsll((long long)s1) - 1; s1 &= s1 - 1; rowp[64 + k] = (int8_t)covered_value; }
+        if (!pq_layout) {
+          int8_t* rowp = rows_plane + i * ld + p * 128;
+          while (s0) { const int k = __ffsll((long long)s0) - 1; s0 &= s0 - 1; rowp[k] = (int8_t)covered_value; }
+          while (s1) { const int k = __ffsll((long long)s1) - 1; s1 &= s1 - 1; rowp[64 + k] = (int8_t)covered_value; }
+        } else {                                                         // P plane: no longer uncovered; Q plane: covered
+          int8_t* rowp = rows_plane + ((i >> 7) * 256 + (i & 127)) * ld + p * 128;
+          int8_t* rowq = rowp + 128 * ld;
+          while (s0) { const int k = __ffsll((long long)s0) - 1; s0 &= s0 - 1; rowp[k] = 0; rowq[k] = 1; }
+          while (s1) { const int k = __ffsll((long long)s1) - 1; s1 &= s1 - 1; rowp[64 + k] = 0; rowq[64 + k] = 1; }
+        }
       }
       c.x |= v.x;
       c.y |= v.y;
@@ -713,11 +748,11 @@ extern "C" int bmf_select_first_max(const int64_t* gain_p, const int64_t* gain_n
   return 0;
 }
 
-extern "C" int bmf_cover_apply(const uint64_t* x_bits, uint64_t* c_bits, int64_t m, int64_t n, int64_t words,
-                               const uint64_t* basis_bits, uint8_t* alive, const int64_t* winner,
-                               int32_t* tp_old, int32_t* fp_old, int32_t wa, int32_t wb, double w_fp,
-                               double w_fn, int8_t* rows_plane, int64_t ld, int8_t covered_value, uint64_t* u_bits,
-                               int64_t* totals, bmf_stream_t stream) {
+static int launch_cover_apply(const uint64_t* x_bits, uint64_t* c_bits, int64_t m, int64_t n, int64_t words,
+                              const uint64_t* basis_bits, uint8_t* alive, const int64_t* winner, int32_t* tp_old,
+                              int32_t* fp_old, int32_t wa, int32_t wb, double w_fp, double w_fn, int8_t* rows_plane,
+                              int64_t ld, int covered_value, int pq_layout, uint64_t* u_bits, int64_t* totals,
+                              bmf_stream_t stream) {
   BMF_REQUIRE(x_bits && c_bits && basis_bits && alive && winner && tp_old && fp_old && u_bits && totals,
               "bmf_cover_apply: null pointer");
   BMF_REQUIRE(m > 0 && n > 0 && words % 2 == 0 && words * 64 >= n, "bmf_cover_apply: bad shape");
@@ -726,8 +761,41 @@ extern "C" int bmf_cover_apply(const uint64_t* x_bits, uint64_t* c_bits, int64_t
   if (blocks > row_stream_grid()) blocks = row_stream_grid();
   cover_apply_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
       x_bits, c_bits, m, n, words, basis_bits, alive, winner, tp_old, fp_old, wa, wb, -w_fp, w_fn, rows_plane,
-      ld, (int)covered_value, reinterpret_cast<unsigned long long*>(u_bits), reinterpret_cast<unsigned long long*>(totals));
+      ld, covered_value, pq_layout, reinterpret_cast<unsigned long long*>(u_bits),
+      reinterpret_cast<unsigned long long*>(totals));
   BMF_LAUNCH_CHECK("bmf_cover_apply");
+  return 0;
+}
+
+extern "C" int bmf_cover_apply(const uint64_t* x_bits, uint64_t* c_bits, int64_t m, int64_t n, int64_t words,
+                               const uint64_t* basis_bits, uint8_t* alive, const int64_t* winner,
+                               int32_t* tp_old, int32_t* fp_old, int32_t wa, int32_t wb, double w_fp,
+                               double w_fn, int8_t* rows_plane, int64_t ld, int8_t covered_value, uint64_t* u_bits,
+                               int64_t* totals, bmf_stream_t stream) {
+  return launch_cover_apply(x_bits, c_bits, m, n, words, basis_bits, alive, winner, tp_old, fp_old, wa, wb, w_fp,
+                            w_fn, rows_plane, ld, (int)covered_value, 0, u_bits, totals, stream);
+}
+
+extern "C" int bmf_cover_apply_general(const uint64_t* x_bits, uint64_t* c_bits, int64_t m, int64_t n, int64_t words,
+                                       const uint64_t* basis_bits, uint8_t* alive, const int64_t* winner,
+                                       int32_t* tp_old, int32_t* fp_old, double w_fp, double w_fn, int8_t* pq_plane,
+                                       int64_t ld, uint64_t* u_bits, int64_t* totals, bmf_stream_t stream) {
+  BMF_REQUIRE(pq_plane != nullptr, "bmf_cover_apply_general: null pq_plane");
+  return launch_cover_apply(x_bits, c_bits, m, n, words, basis_bits, alive, winner, tp_old, fp_old, 0, 0, w_fp,
+                            w_fn, pq_plane, ld, 0, 1, u_bits, totals, stream);
+}
+
+extern "C" int bmf_expand_bits_pq(const uint64_t* x_bits, const uint64_t* c_bits, int64_t rows, int64_t ncols,
+                                  int64_t words, int8_t* pq_plane, int64_t ld, bmf_stream_t stream) {
+  BMF_REQUIRE(x_bits && c_bits && pq_plane, "bmf_expand_bits_pq: null pointer");
+  BMF_REQUIRE(rows > 0 && ld % 128 == 0 && ld >= ncols && words * 64 >= ncols, "bmf_expand_bits_pq: bad shape / ld");
+  const int64_t plane_rows = 2 * ceil_div(rows, 128) * 128;
+  const int64_t total = plane_rows * (ld >> 4);
+  int64_t blocks = ceil_div(total, 256);
+  if (blocks > (int64_t)num_sms() * 64) blocks = (int64_t)num_sms() * 64;
+  expand_bits_pq_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x_bits, c_bits, rows, ncols, words, pq_plane,
+                                                                       plane_rows, ld);
+  BMF_LAUNCH_CHECK("bmf_expand_bits_pq");
   return 0;
 }
 

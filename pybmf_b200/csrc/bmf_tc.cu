@@ -6,6 +6,11 @@
 // epilogue without writing D to HBM:
 //   EPI_GAIN : gain[j] += sum_i relu(D[j][i])           (cover-gain scoring, Asso.py:83-95/144-188)
 //   EPI_STORE: cnt[j][i] = D[j][i]                      (association counts X^T X, Asso.py:207)
+//   EPI_GAIN2: general (non-dyadic) weights.  The data-row operand interleaves, per 128 rows, a
+//              P plane (x & ~c) and a Q plane (c), so a tile's 256 accumulator columns hold
+//              P[j][i] = |b_j & x_i & ~c_i| (columns 0..127) and Q[j][i] = |b_j & c_i| (128..255) for
+//              the same 128 rows; N = |b_j| - Q - P, the row test is the reference's literal fp64
+//              expression (metrics.py:201) and gain_p[j] += sum_use P, gain_n[j] += sum_use N.
 // Candidates sit on the MMA M axis (TMEM lanes): each epilogue thread owns one candidate and
 // reduces over its tile columns in registers -- no cross-lane traffic.
 //
@@ -30,9 +35,26 @@ constexpr int B_BYTES = BN * BK;       // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;         // 2 accumulators x 256 columns x 128 lanes x int32
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int ROWSTATE_BYTES = 2 * 128 * 16;  // EPI_GAIN2: per-row (s_old, tp_old, fp_old), double buffered
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + ROWSTATE_BYTES;
 
-enum { EPI_GAIN = 0, EPI_STORE = 1 };
+enum { EPI_GAIN = 0, EPI_STORE = 1, EPI_GAIN2 = 2 };
+
+// everything the fused epilogues need (passed by value)
+struct EpiArgs {
+  int sign;                        // EPI_GAIN
+  const int32_t* cand_pop;         // EPI_GAIN (zero-dominant bias, nullable), EPI_GAIN2 (|b_j|, required)
+  int bias_scale;                  // EPI_GAIN
+  unsigned long long* gain;        // EPI_GAIN: sum relu; EPI_GAIN2: sum_use P
+  unsigned long long* gain_n;      // EPI_GAIN2: sum_use N
+  int32_t* C;                      // EPI_STORE
+  int64_t ldc;
+  const int32_t* tp_old;           // EPI_GAIN2: per data row counts of the current cover
+  const int32_t* fp_old;
+  int64_t m_rows;                  // EPI_GAIN2: true number of data rows (the rest is padding)
+  double neg_w_fp, w_fn;           // EPI_GAIN2
+};
+struct __align__(16) RowState { double s_old; int tpo; int fpo; };
 
 // instruction descriptor (cute::UMMA::InstrDescriptor layout): dense, no saturate,
 // C = S32 (2) at [4,6), A = S8 (1) at [7,10), B = S8 (1) at [10,13), K-major both,
@@ -97,17 +119,104 @@ __device__ __forceinline__ void tile_coords(int64_t t, int mt_total, int nt_tota
   nt = (int)(r / gsize);
 }
 
+
+// two 32-column chunks in flight, one wait
+__device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// EPI_GAIN2, before the accumulator is waited for: the 128 epilogue threads of a CTA stage the state of the
+// tile's 128 data rows (et = 0..127) into buffer `acc` and meet on named barrier 1.  With two buffers one
+// barrier per tile is enough: a thread that passes the barrier of tile t+1 has finished reading tile t.
+__device__ __forceinline__ void stage_row_state(RowState* rs, int acc, int et, int nt, const EpiArgs& ea) {
+  const int64_t i = (int64_t)nt * 128 + et;
+  RowState r;
+  if (i < ea.m_rows) {
+    r.tpo = ea.tp_old[i];
+    r.fpo = ea.fp_old[i];
+    r.s_old = cover_score_f64(ea.neg_w_fp, ea.w_fn, r.fpo, r.tpo);
+  } else {                                                // padding row: never used
+    r.tpo = 0;
+    r.fpo = 0;
+    r.s_old = __longlong_as_double(0x7ff0000000000000ll);
+  }
+  rs[acc * 128 + et] = r;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+// One accumulator tile (this thread's TMEM lane = candidate `row`, BN columns) through the fused epilogue.
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile(uint32_t taddr, int64_t row, int nt, const RowState* rs, const EpiArgs& ea) {
+  if (EPI == EPI_GAIN2) {
+    const int pop = ea.cand_pop[row];
+    long long sum_p = 0, sum_n = 0;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t vp[32], vq[32];
+      tmem_ld_32x32_nowait(taddr + (uint32_t)(c * 32), vp);
+      tmem_ld_32x32_nowait(taddr + (uint32_t)(128 + c * 32), vq);
+      tmem_ld_wait();
+      int part_p = 0, part_n = 0;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const RowState r = rs[c * 32 + q];                // same address for the whole warp: broadcast
+        const int P = (int)vp[q];
+        const int N = pop - (int)vq[q] - P;
+        const bool use = cover_score_f64(ea.neg_w_fp, ea.w_fn, r.fpo + N, r.tpo + P) > r.s_old;
+        part_p += use ? P : 0;
+        part_n += use ? N : 0;
+      }
+      sum_p += part_p;
+      sum_n += part_n;
+    }
+    if (sum_p | sum_n) {
+      atomicAdd(ea.gain + row, (unsigned long long)sum_p);
+      atomicAdd(ea.gain_n + row, (unsigned long long)sum_n);
+    }
+  } else {
+    const int bias = (EPI == EPI_GAIN && ea.cand_pop != nullptr) ? ea.bias_scale * ea.cand_pop[row] : 0;
+    const int sign = ea.sign;
+    long long relu_sum = 0;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+      if (EPI == EPI_GAIN) {
+        int part = 0;                                     // 32 * 127 * K fits int32 for K < 5e5
+#pragma unroll
+        for (int q = 0; q < 32; ++q) part += max(sign * (int)v[q] - bias, 0);
+        relu_sum += part;
+      } else {
+        int4* dst = reinterpret_cast<int4*>(ea.C + row * ea.ldc + (int64_t)nt * BN + c * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          dst[q] = make_int4((int)v[4 * q], (int)v[4 * q + 1], (int)v[4 * q + 2], (int)v[4 * q + 3]);
+      }
+    }
+    if (EPI == EPI_GAIN && relu_sum != 0) atomicAdd(ea.gain + row, (unsigned long long)relu_sum);
+  }
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               int mt_total, int nt_total, int kb_total, int group_m, int sign,
-               const int32_t* __restrict__ cand_pop, int bias_scale,
-               unsigned long long* __restrict__ gain, int32_t* __restrict__ C, int64_t ldc) {
+               int mt_total, int nt_total, int kb_total, int group_m, const EpiArgs ea) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then tmem base
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  RowState* row_state = reinterpret_cast<RowState*>(smem + STAGES * STAGE_BYTES + 256);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -192,32 +301,15 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int mt, nt;
       tile_coords(t, mt_total, nt_total, group_m, mt, nt);
+      if (EPI == EPI_GAIN2) stage_row_state(row_state, acc, (int)threadIdx.x - 64, nt, ea);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       const int64_t row = (int64_t)mt * BM + quad * 32 + lane;
-      const int bias = (EPI == EPI_GAIN && cand_pop != nullptr) ? bias_scale * cand_pop[row] : 0;
-      long long relu_sum = 0;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-        if (EPI == EPI_GAIN) {
-          int part = 0;                                   // 32 * 127 * K fits int32 for K < 5e5
-#pragma unroll
-          for (int q = 0; q < 32; ++q) part += max(sign * (int)v[q] - bias, 0);
-          relu_sum += part;
-        } else {
-          int4* dst = reinterpret_cast<int4*>(C + row * ldc + (int64_t)nt * BN + c * 32);
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            dst[q] = make_int4((int)v[4 * q], (int)v[4 * q + 1], (int)v[4 * q + 2], (int)v[4 * q + 3]);
-        }
-      }
+      epilogue_tile<EPI>(taddr, row, nt, row_state + acc * 128, ea);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));        // 4 arrivals free the accumulator
-      if (EPI == EPI_GAIN && relu_sum != 0) atomicAdd(gain + row, (unsigned long long)relu_sum);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -271,15 +363,14 @@ static int make_plane_map(CUtensorMap* map, const int8_t* plane, int64_t rows, i
 }
 
 template <int EPI>
-static int launch_gemm(const int8_t* a, int64_t a_rows, const int8_t* b, int64_t b_rows, int64_t ld, int sign,
-                       const int32_t* cand_pop, int bias_scale, unsigned long long* gain, int32_t* C, int64_t ldc,
-                       cudaStream_t stream) {
+static int launch_gemm(const int8_t* a, int64_t a_rows, const int8_t* b, int64_t b_rows, int64_t ld,
+                       const EpiArgs& ea, cudaStream_t stream) {
   CUtensorMap ma, mb;
   int rc = make_plane_map(&ma, a, a_rows, ld, BM);
   if (rc) return rc;
   rc = make_plane_map(&mb, b, b_rows, ld, BN);
   if (rc) return rc;
-  static bool attr_set[2] = {false, false};
+  static bool attr_set[3] = {false, false, false};
   if (!attr_set[EPI]) {
     rc = check_cuda(cudaFuncSetAttribute(gemm_i8_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES),
                     "cudaFuncSetAttribute(gemm_i8_kernel)");
@@ -291,7 +382,7 @@ static int launch_gemm(const int8_t* a, int64_t a_rows, const int8_t* b, int64_t
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   int group_m = 16;                                       // candidate tiles per raster group (L2 reuse)
   if (const char* e = getenv("BMF_GROUP_M")) { int v = atoi(e); if (v >= 1 && v <= 64) group_m = v; }
-  gemm_i8_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, mt, nt, kb, group_m, sign, cand_pop, bias_scale, gain, C, ldc);
+  gemm_i8_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, mt, nt, kb, group_m, ea);
   return check_cuda(cudaGetLastError(), "gemm_i8_kernel launch");
 }
 
@@ -311,7 +402,7 @@ constexpr int HALF = 128;                // rows each CTA stages per operand
 constexpr int STAGES2 = 6;
 constexpr int OP_BYTES = HALF * BK;      // 16 KB
 constexpr int STAGE_BYTES2 = 2 * OP_BYTES;
-constexpr int SMEM_BYTES2 = STAGES2 * STAGE_BYTES2 + 1024 + 256;
+constexpr int SMEM_BYTES2 = STAGES2 * STAGE_BYTES2 + 1024 + 256 + ROWSTATE_BYTES;
 constexpr uint32_t IDESC_I8_2SM = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                   ((uint32_t)(BM2 >> 4) << 24);
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-pair bit of a shared::cluster address
@@ -356,13 +447,12 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t local_bar) {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_i8_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   int mt_total, int nt_total, int kb_total, int group_m, int sign,
-                   const int32_t* __restrict__ cand_pop, int bias_scale,
-                   unsigned long long* __restrict__ gain, int32_t* __restrict__ C, int64_t ldc) {
+                   int mt_total, int nt_total, int kb_total, int group_m, const EpiArgs ea) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE_BYTES2);
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES2 + 4);
+  RowState* row_state = reinterpret_cast<RowState*>(smem + STAGES2 * STAGE_BYTES2 + 256);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -451,32 +541,15 @@ gemm_i8_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     for (int64_t t = pair; t < total_tiles; t += num_pairs) {
       int mt, nt;
       tile_coords(t, mt_total, nt_total, group_m, mt, nt);
+      if (EPI == EPI_GAIN2) stage_row_state(row_state, acc, (int)threadIdx.x - 64, nt, ea);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       const int64_t row = (int64_t)mt * BM2 + (int64_t)rank * HALF + quad * 32 + lane;
-      const int bias = (EPI == EPI_GAIN && cand_pop != nullptr) ? bias_scale * cand_pop[row] : 0;
-      long long relu_sum = 0;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-        if (EPI == EPI_GAIN) {
-          int part = 0;
-#pragma unroll
-          for (int q = 0; q < 32; ++q) part += max(sign * (int)v[q] - bias, 0);
-          relu_sum += part;
-        } else {
-          int4* dst = reinterpret_cast<int4*>(C + row * ldc + (int64_t)nt * BN + c * 32);
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            dst[q] = make_int4((int)v[4 * q], (int)v[4 * q + 1], (int)v[4 * q + 2], (int)v[4 * q + 3]);
-        }
-      }
+      epilogue_tile<EPI>(taddr, row, nt, row_state + acc * 128, ea);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(tempty_bar(acc)); // 8 arrivals (4 warps x 2 CTAs) free the accumulator
-      if (EPI == EPI_GAIN && relu_sum != 0) atomicAdd(gain + row, (unsigned long long)relu_sum);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -491,15 +564,14 @@ gemm_i8_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 }
 
 template <int EPI>
-static int launch_gemm_2sm(const int8_t* a, int64_t a_rows, const int8_t* b, int64_t b_rows, int64_t ld, int sign,
-                           const int32_t* cand_pop, int bias_scale, unsigned long long* gain, int32_t* C,
-                           int64_t ldc, cudaStream_t stream) {
+static int launch_gemm_2sm(const int8_t* a, int64_t a_rows, const int8_t* b, int64_t b_rows, int64_t ld,
+                           const EpiArgs& ea, cudaStream_t stream) {
   CUtensorMap ma, mb;
   int rc = make_plane_map(&ma, a, a_rows, ld, HALF);
   if (rc) return rc;
   rc = make_plane_map(&mb, b, b_rows, ld, HALF);
   if (rc) return rc;
-  static bool attr_set[2] = {false, false};
+  static bool attr_set[3] = {false, false, false};
   if (!attr_set[EPI]) {
     rc = check_cuda(cudaFuncSetAttribute(gemm_i8_2sm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES2),
                     "cudaFuncSetAttribute(gemm_i8_2sm_kernel)");
@@ -512,7 +584,7 @@ static int launch_gemm_2sm(const int8_t* a, int64_t a_rows, const int8_t* b, int
   const int pairs = (int)(tiles < pairs_max ? tiles : pairs_max);
   int group_m = 16;                                       // 256-row candidate tiles per raster group
   if (const char* e = getenv("BMF_GROUP_M2")) { int v = atoi(e); if (v >= 1 && v <= 64) group_m = v; }
-  gemm_i8_2sm_kernel<EPI><<<2 * pairs, NUM_THREADS, SMEM_BYTES2, stream>>>(ma, mb, mt, nt, kb, group_m, sign, cand_pop, bias_scale, gain, C, ldc);
+  gemm_i8_2sm_kernel<EPI><<<2 * pairs, NUM_THREADS, SMEM_BYTES2, stream>>>(ma, mb, mt, nt, kb, group_m, ea);
   return check_cuda(cudaGetLastError(), "gemm_i8_2sm_kernel launch");
 }
 }  // namespace sm2
@@ -520,8 +592,7 @@ static int launch_gemm_2sm(const int8_t* a, int64_t a_rows, const int8_t* b, int
 // variant: 0 = auto (2-SM when the candidate rows are a multiple of 256), 1 = 1-SM, 2 = 2-SM
 template <int EPI>
 static int dispatch_gemm(int variant, const int8_t* a, int64_t a_rows, const int8_t* b, int64_t b_rows, int64_t ld,
-                         int sign, const int32_t* cand_pop, int bias_scale, unsigned long long* gain, int32_t* C,
-                         int64_t ldc, cudaStream_t stream) {
+                         const EpiArgs& ea, cudaStream_t stream) {
   if (const char* e = getenv("BMF_GEMM_VARIANT")) { int v = atoi(e); if (v == 1 || v == 2) variant = v; }
   const bool ok2 = (a_rows % sm2::BM2) == 0;
   if (variant == 2 && !ok2) {
@@ -529,8 +600,8 @@ static int dispatch_gemm(int variant, const int8_t* a, int64_t a_rows, const int
     return BMF_E_ARG;
   }
   if (variant == 2 || (variant == 0 && ok2))
-    return sm2::launch_gemm_2sm<EPI>(a, a_rows, b, b_rows, ld, sign, cand_pop, bias_scale, gain, C, ldc, stream);
-  return launch_gemm<EPI>(a, a_rows, b, b_rows, ld, sign, cand_pop, bias_scale, gain, C, ldc, stream);
+    return sm2::launch_gemm_2sm<EPI>(a, a_rows, b, b_rows, ld, ea, stream);
+  return launch_gemm<EPI>(a, a_rows, b, b_rows, ld, ea, stream);
 }
 
 }  // namespace tc
@@ -545,7 +616,10 @@ extern "C" int bmf_gemm_i8_nt(const int8_t* a_plane, int64_t a_rows_pad, const i
   BMF_REQUIRE(b_rows_pad > 0 && b_rows_pad % tc::BN == 0, "bmf_gemm_i8_nt: b rows must be a positive multiple of 256");
   BMF_REQUIRE(ld > 0 && ld % tc::BK == 0, "bmf_gemm_i8_nt: ld must be a positive multiple of 128");
   BMF_REQUIRE(ldc >= b_rows_pad && ldc % 4 == 0, "bmf_gemm_i8_nt: ldc must cover b rows and be a multiple of 4");
-  return tc::dispatch_gemm<tc::EPI_STORE>(0, a_plane, a_rows_pad, b_plane, b_rows_pad, ld, 1, nullptr, 0, nullptr, c, ldc, as_stream(stream));
+  tc::EpiArgs ea = {};
+  ea.C = c;
+  ea.ldc = ldc;
+  return tc::dispatch_gemm<tc::EPI_STORE>(0, a_plane, a_rows_pad, b_plane, b_rows_pad, ld, ea, as_stream(stream));
 }
 
 extern "C" int bmf_assoc_counts_i8(const int8_t* xt_plane, int64_t n, int64_t n_pad, int64_t ld, int32_t* cnt,
@@ -554,7 +628,10 @@ extern "C" int bmf_assoc_counts_i8(const int8_t* xt_plane, int64_t n, int64_t n_
   BMF_REQUIRE(n_pad >= n && n_pad % tc::BN == 0, "bmf_assoc_counts_i8: n_pad must be a multiple of 256 covering n");
   BMF_REQUIRE(ld > 0 && ld % tc::BK == 0, "bmf_assoc_counts_i8: ld must be a positive multiple of 128");
   BMF_REQUIRE(ldc >= n_pad && ldc % 4 == 0, "bmf_assoc_counts_i8: ldc must be >= n_pad and a multiple of 4");
-  return tc::dispatch_gemm<tc::EPI_STORE>(0, xt_plane, n_pad, xt_plane, n_pad, ld, 1, nullptr, 0, nullptr, cnt, ldc, as_stream(stream));
+  tc::EpiArgs ea = {};
+  ea.C = cnt;
+  ea.ldc = ldc;
+  return tc::dispatch_gemm<tc::EPI_STORE>(0, xt_plane, n_pad, xt_plane, n_pad, ld, ea, as_stream(stream));
 }
 
 extern "C" int bmf_cover_score_i8(const int8_t* cand_plane, int64_t cand_pad, const int8_t* rows_plane,
@@ -567,6 +644,36 @@ extern "C" int bmf_cover_score_i8(const int8_t* cand_plane, int64_t cand_pad, co
   BMF_REQUIRE(ld > 0 && ld % tc::BK == 0, "bmf_cover_score_i8: ld must be a positive multiple of 128");
   int rc = check_cuda(cudaMemsetAsync(gain, 0, sizeof(int64_t) * cand_pad, as_stream(stream)), "bmf_cover_score_i8");
   if (rc) return rc;
-  return tc::dispatch_gemm<tc::EPI_GAIN>(0, cand_plane, cand_pad, rows_plane, rows_pad, ld, sign, cand_pop, bias_scale,
-                                         reinterpret_cast<unsigned long long*>(gain), nullptr, 0, as_stream(stream));
+  tc::EpiArgs ea = {};
+  ea.sign = sign;
+  ea.cand_pop = cand_pop;
+  ea.bias_scale = bias_scale;
+  ea.gain = reinterpret_cast<unsigned long long*>(gain);
+  return tc::dispatch_gemm<tc::EPI_GAIN>(0, cand_plane, cand_pad, rows_plane, rows_pad, ld, ea, as_stream(stream));
+}
+
+extern "C" int bmf_cover_score_i8_general(const int8_t* cand_plane, int64_t cand_pad, const int8_t* pq_plane,
+                                          int64_t m, int64_t ld, const int32_t* cand_pop, const int32_t* tp_old,
+                                          const int32_t* fp_old, double w_fp, double w_fn, int64_t* gain_p,
+                                          int64_t* gain_n, bmf_stream_t stream) {
+  BMF_REQUIRE(cand_plane && pq_plane && cand_pop && tp_old && fp_old && gain_p && gain_n,
+              "bmf_cover_score_i8_general: null pointer");
+  BMF_REQUIRE(cand_pad > 0 && cand_pad % tc::BM == 0, "bmf_cover_score_i8_general: cand_pad must be a positive multiple of 128");
+  BMF_REQUIRE(m > 0, "bmf_cover_score_i8_general: no data rows");
+  BMF_REQUIRE(ld > 0 && ld % tc::BK == 0, "bmf_cover_score_i8_general: ld must be a positive multiple of 128");
+  const int64_t plane_rows = 2 * ceil_div(m, 128) * 128;   // [ceil(m/128)][P|Q][128] rows of ld bytes
+  int rc = check_cuda(cudaMemsetAsync(gain_p, 0, sizeof(int64_t) * cand_pad, as_stream(stream)), "bmf_cover_score_i8_general");
+  if (rc) return rc;
+  rc = check_cuda(cudaMemsetAsync(gain_n, 0, sizeof(int64_t) * cand_pad, as_stream(stream)), "bmf_cover_score_i8_general");
+  if (rc) return rc;
+  tc::EpiArgs ea = {};
+  ea.cand_pop = cand_pop;
+  ea.gain = reinterpret_cast<unsigned long long*>(gain_p);
+  ea.gain_n = reinterpret_cast<unsigned long long*>(gain_n);
+  ea.tp_old = tp_old;
+  ea.fp_old = fp_old;
+  ea.m_rows = m;
+  ea.neg_w_fp = -w_fp;
+  ea.w_fn = w_fn;
+  return tc::dispatch_gemm<tc::EPI_GAIN2>(0, cand_plane, cand_pad, pq_plane, plane_rows, ld, ea, as_stream(stream));
 }

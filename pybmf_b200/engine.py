@@ -83,18 +83,21 @@ class CoverEngine:
         self.wa, self.wb, self.shift = iw if iw else (0, 0, 0)
         self.integer_mode = iw is not None
         if scorer == "auto":
-            scorer = "tcgen05" if self.integer_mode else "popc"
-        if scorer == "tcgen05" and not self.integer_mode:
-            raise ValueError("the tcgen05 scorer needs weights of the form a/2^s, b/2^s with a, b <= 127; "
-                             "use scorer='popc' for w_fp=%r, w_fn=%r" % (w_fp, w_fn))
+            scorer = "tcgen05"
         assert scorer in ("tcgen05", "popc") and assoc in ("auto", "tcgen05", "popc")
         self.scorer = scorer
-        # operand encoding of the rows plane (all give D = wb*P - wa*N exactly, see include/pybmf_b200.h):
+        # operand encoding of the rows plane (see include/pybmf_b200.h):
+        #   integer mode, all give D = wb*P - wa*N exactly:
         #   "zero"  : uncovered one -> wa+wb, uncovered zero -> 0, covered -> wa, bias wa*|b_j| in the epilogue
         #   "signed": uncovered one -> +wb,   uncovered zero -> -wa, covered -> 0
+        #   general (non-dyadic) weights:
+        #   "pq"    : interleaved 0/1 planes P = x & ~c and Q = c per 128 rows; the epilogue gets P and
+        #             N = |b_j| - Q - P per element and evaluates the reference's fp64 row test literally
         enc = os.environ.get("BMF_PLANE_ENCODING", "zero")
         if enc == "zero" and self.wa + self.wb > 127:
             enc = "signed"
+        if not self.integer_mode:
+            enc = "pq"
         self.encoding = enc
         self.plane_sign = -1 if enc == "signed-" else 1
         self.cand_pop = None
@@ -152,6 +155,14 @@ class CoverEngine:
 
     def _rebuild_rows_plane(self):
         """rows_plane[i][k] = 0 if covered, +wb if x, -wa otherwise (the signed operand of D = wb*P - wa*N)."""
+        if self.encoding == "pq":
+            if self.rows_plane is None:
+                self.rows_plane = device.empty((2 * device.round_up(max(self.m_loc, 1), 128), self.ld), torch.int8)
+            if self.m_loc > 0:
+                _native.call("bmf_expand_bits_pq", self.x_bits, self.c_bits, self.m_loc, self.n, self.words,
+                             self.rows_plane, self.ld)
+            self.launches += 1
+            return
         one, zero, covered = self._plane_values()
         self.rows_plane = device.expand_bits_i8(self.x_bits, self.m_loc, self.n, one, zero, 256,
                                                 mask=self.c_bits, out=self.rows_plane, masked=covered)
@@ -184,6 +195,10 @@ class CoverEngine:
         if self.m_loc == 0:                                   # a rank without rows only joins the exchange
             self.gain_p.zero_()
             self.gain_n.zero_()
+        elif self.scorer == "tcgen05" and self.encoding == "pq":
+            _native.call("bmf_cover_score_i8_general", self.cand_plane, self.cand_pad, self.rows_plane, self.m_loc,
+                         self.ld, self.cand_pop, self.tp_old, self.fp_old, self.w_fp, self.w_fn, self.gain_p,
+                         self.gain_n)
         elif self.scorer == "tcgen05":
             _native.call("bmf_cover_score_i8", self.cand_plane, self.cand_pad, self.rows_plane,
                          self.rows_plane.shape[0], self.ld, self.plane_sign,
@@ -207,7 +222,11 @@ class CoverEngine:
                      self.n, self.wa, self.wb, base_int, scale, self.w_fp, self.w_fn, self.tp_tot, self.fp_tot,
                      float(best_score), self.record)
         u_bits = device.zeros((self.words_m,), torch.int64)
-        if self.m_loc > 0:
+        if self.m_loc > 0 and self.scorer == "tcgen05" and self.encoding == "pq":
+            _native.call("bmf_cover_apply_general", self.x_bits, self.c_bits, self.m_loc, self.n, self.words,
+                         self.basis_bits, self.alive, self.record, self.tp_old, self.fp_old, self.w_fp, self.w_fn,
+                         self.rows_plane, self.ld, u_bits, self.record[2:5])
+        elif self.m_loc > 0:
             _native.call("bmf_cover_apply", self.x_bits, self.c_bits, self.m_loc, self.n, self.words, self.basis_bits,
                          self.alive, self.record, self.tp_old, self.fp_old, self.wa, self.wb, self.w_fp, self.w_fn,
                          self.rows_plane, self.ld, self._plane_values()[2] if self.scorer == "tcgen05" else 0,

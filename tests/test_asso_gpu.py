@@ -63,15 +63,21 @@ def test_asso_matches_reference_bit_exact(M, name, scorer, assoc):
 
 
 @pytest.mark.parametrize("name", GENERAL_CASES)
-def test_asso_general_weights(M, name):
+@pytest.mark.parametrize("scorer", ["tcgen05", "popc"])
+def test_asso_general_weights(M, name, scorer):
+    """non-dyadic weights: tensor cores (interleaved P/Q operand, fp64 row test in the epilogue) and popcount"""
     c = load_golden(name)
     g = c["g"]
-    mdl = _fit(M, c)                                               # auto -> popcount scorer, fp64 row test
+    mdl = _fit(M, c, scorer=scorer)
     assert np.array_equal(_dense(mdl.U), g["U"]) and np.array_equal(_dense(mdl.V), g["V"])
     _check_logs(mdl.logs["updates"], g, exact_score=False)
-    with pytest.raises(ValueError):
-        M.Asso(tau=c["tau"], k=c["k"], w_fp=c["w_fp"], w_fn=c["w_fn"], scorer="tcgen05").fit(
-            sp.csr_matrix(c["X"]), **FIT_KW)
+
+
+def test_asso_general_weights_auto_is_tensor_core(M):
+    c = load_golden("planted_w02")
+    from pybmf_b200.engine import CoverEngine
+    eng = CoverEngine(sp.csr_matrix(c["X"]), c["w_fp"], 1 - c["w_fp"])
+    assert eng.scorer == "tcgen05" and eng.encoding == "pq" and not eng.integer_mode
 
 
 def test_known_answer_table_ex01_6(M):

@@ -206,6 +206,74 @@ def test_cover_score_i8_tcgen05(nat, m, n, w, gemm_variant):
     assert np.array_equal(got[:n], G) and got[n:].sum() == 0
 
 
+def _pq_plane(device, X, C, ld):
+    """numpy statement of the interleaved P/Q operand (include/pybmf_b200.h, bmf_expand_bits_pq)"""
+    m, n = X.shape
+    blocks = (m + 127) // 128
+    plane = np.zeros((blocks * 256, ld), np.int8)
+    for i in range(m):
+        pr = (i // 128) * 256 + i % 128
+        plane[pr, :n] = X[i] & (1 - C[i])
+        plane[pr + 128, :n] = C[i]
+    return plane
+
+
+@pytest.mark.parametrize("gemm_variant", [1, 2], indirect=True)
+@pytest.mark.parametrize("m,n,w", [(70, 50, (0.2, 0.8)), (300, 200, (0.3, 0.6)), (129, 257, (0.2, 0.8)),
+                                   (1000, 500, (0.5, 0.5)), (3000, 1100, (0.15, 0.85))])
+def test_cover_score_i8_general_tcgen05(nat, m, n, w, gemm_variant):
+    """general weights on the tensor cores: P/Q side by side in the accumulator, fp64 row test in the epilogue"""
+    _native, device = nat
+    X, C, B, alive = _cover_inputs(m * 11 + n, m, n)
+    w_fp, w_fn = w
+    words = device.words_for(n)
+    ld = device.round_up(n, 128)
+    tpo, fpo, _ = O.confusion(X, C, axis=1)
+    cand_pad = device.round_up(n, 256)
+    cand_plane = np.zeros((cand_pad, ld), np.int8)
+    cand_plane[:n, :n] = B
+    pop = np.zeros(cand_pad, np.int32)
+    pop[:n] = B.sum(axis=1)
+    pq = device.empty((2 * device.round_up(m, 128), ld), torch.int8)
+    _native.call("bmf_expand_bits_pq", _dev(device.dense_to_words(X)), _dev(device.dense_to_words(C)), m, n, words,
+                 pq, ld)
+    assert np.array_equal(pq.cpu().numpy(), _pq_plane(device, X, C, ld))
+    gp = device.zeros((cand_pad,), torch.int64) + 7                 # overwritten, not accumulated
+    gn = device.zeros((cand_pad,), torch.int64) + 7
+    _native.call("bmf_cover_score_i8_general", _dev(cand_plane), cand_pad, pq, m, ld, _dev(pop),
+                 _dev(tpo.astype(np.int32)), _dev(fpo.astype(np.int32)), w_fp, w_fn, gp, gn)
+    score, use, P, N, _, _ = O.score_candidates(X, C, B, w_fp, w_fn)
+    got_p, got_n = gp.cpu().numpy(), gn.cpu().numpy()
+    assert np.array_equal(got_p[:n], (P * use).sum(axis=0)) and np.array_equal(got_n[:n], (N * use).sum(axis=0))
+    assert got_p[n:].sum() == 0 and got_n[n:].sum() == 0
+
+
+def test_cover_apply_general_updates_pq_plane(nat):
+    _native, device = nat
+    m, n = 333, 200
+    X, C, B, alive = _cover_inputs(99, m, n)
+    alive[:] = 1
+    w_fp, w_fn = 0.2, 0.8
+    j = 37
+    words = device.words_for(n)
+    ld = device.round_up(n, 128)
+    tpo, fpo, _ = O.confusion(X, C, axis=1)
+    score, use, P, N, _, _ = O.score_candidates(X, C, B[j:j + 1], w_fp, w_fn)
+    u = use[:, 0]
+    pq = _dev(_pq_plane(device, X, C, ld))
+    c_d = _dev(device.dense_to_words(C))
+    tp_d, fp_d = _dev(tpo.astype(np.int32)), _dev(fpo.astype(np.int32))
+    ub = device.zeros((device.words_for(m),), torch.int64)
+    tot = device.zeros((3,), torch.int64)
+    _native.call("bmf_cover_apply_general", _dev(device.dense_to_words(X)), c_d, m, n, words,
+                 _dev(device.dense_to_words(B)), _dev(alive), _dev(np.array([j], np.int64)), tp_d, fp_d, w_fp, w_fn,
+                 pq, ld, ub, tot)
+    Cn = C | (u[:, None].astype(np.uint8) & B[j][None, :])
+    assert np.array_equal(device.bits_to_host(c_d, n), Cn)
+    assert np.array_equal(pq.cpu().numpy(), _pq_plane(device, X, Cn, ld))
+    assert list(tot.cpu().numpy()) == [int(u.sum()), int(P[u, 0].sum()), int(N[u, 0].sum())]
+
+
 def test_select_first_max(nat):
     _native, device = nat
     n = 3000
