@@ -250,7 +250,7 @@ def run_product_sweep(args, rank, world, local_rank, real_stdout):
                 "config": {"workload": "Boolean product + TP/FP/FN sweep, k=64 (BASELINE configs[4]); headline = largest point",
                            "m": last["m"], "n": last["n"], "l2": "bit matrices of the large points exceed L2"},
                 "roofline": {"bound": "hbm", "achieved": value / world, "peak": hbm / world, "unit": "GB/s",
-                             "frac": value / hbm, "traffic": None, "kernel": "bool_product_kernel + confusion_kernel<true>",
+                             "frac": value / hbm, "traffic": None, "kernel": "bool_product_panel_kernel + confusion_panel_kernel<false> (V^T panel in shared memory; TMA ring + Harley-Seal counting)",
                              "peak_source": peak_src},
                 "sweep": results, "library_stream_ceilings": ceilings, "gpu_launches": 2 * args.steps * len(results)}
         os.dup2(real_stdout, 1)

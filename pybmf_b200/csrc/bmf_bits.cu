@@ -542,6 +542,322 @@ confusion_kernel(const uint64_t* __restrict__ gt, const uint64_t* __restrict__ p
   }
 }
 
+// =========================================================================================
+// Column-panel variants of the Boolean product and of the confusion counts from factors.
+//
+// ncu on the row-stream kernels above at m = 1M, n = 100k, k = 64 (profiles/r01_c5_*): the V^T rows a
+// data row selects are re-fetched from L2 (2.5x the HBM bytes through L1) and the XU pipe (POPC) is
+// 68 % busy at 52 % of HBM peak, i.e. four POPCs per 64-bit word cap the kernel near 5 TB/s.
+// Here a CTA owns a panel of <= PANEL_MAX_CHUNKS x 256 bit-words (2 KB per row and chunk) of ALL k
+// rows of V^T in shared memory; its warps stream two data rows at a time through the panel, so
+//  * V^T is read from L2 once per CTA, the selected rows are ORed from shared memory (conflict free:
+//    a warp reads 512 contiguous bytes), and HBM only carries the ground truth / the product;
+//  * set bits are counted with a Harley-Seal carry-save adder tree (LOP3 on the ALU pipe): 16 words
+//    cost 15 CSAs and ONE popcount instead of 16, which takes the XU pipe out of the picture.
+// =========================================================================================
+constexpr int CH_PAIRS = 128;            // 16-byte pairs per chunk and row: 32 lanes x 4
+constexpr int PANEL_THREADS = 512;
+constexpr int PANEL_SMEM_MAX = 200 * 1024;
+
+__device__ __forceinline__ void csa64(uint64_t& h, uint64_t& l, uint64_t a, uint64_t b, uint64_t c) {
+  const uint64_t u = a ^ b;
+  h = (a & b) | (u & c);                 // majority -> one LOP3 per 32-bit half
+  l = u ^ c;                             // parity   -> one LOP3 per 32-bit half
+}
+struct HarleySeal {
+  uint64_t ones = 0, twos = 0, fours = 0, eights = 0;
+  long long sixteens = 0;                // popcounts of the "sixteens" words
+  __device__ __forceinline__ void add16(const uint64_t (&w)[16]) {
+    uint64_t t2a, t2b, t4a, t4b, t8a, t8b, t16;
+    csa64(t2a, ones, ones, w[0], w[1]);
+    csa64(t2b, ones, ones, w[2], w[3]);
+    csa64(t4a, twos, twos, t2a, t2b);
+    csa64(t2a, ones, ones, w[4], w[5]);
+    csa64(t2b, ones, ones, w[6], w[7]);
+    csa64(t4b, twos, twos, t2a, t2b);
+    csa64(t8a, fours, fours, t4a, t4b);
+    csa64(t2a, ones, ones, w[8], w[9]);
+    csa64(t2b, ones, ones, w[10], w[11]);
+    csa64(t4a, twos, twos, t2a, t2b);
+    csa64(t2a, ones, ones, w[12], w[13]);
+    csa64(t2b, ones, ones, w[14], w[15]);
+    csa64(t4b, twos, twos, t2a, t2b);
+    csa64(t8b, fours, fours, t4a, t4b);
+    csa64(t16, eights, eights, t8a, t8b);
+    sixteens += __popcll(t16);
+  }
+  __device__ __forceinline__ long long total() const {
+    return 16 * sixteens + 8 * (long long)__popcll(eights) + 4 * (long long)__popcll(fours) +
+           2 * (long long)__popcll(twos) + (long long)__popcll(ones);
+  }
+};
+
+// V^T panel -> shared memory: Vs[l][p] (pairs), zero beyond the matrix
+__device__ __forceinline__ void load_vt_panel(ulonglong2* Vs, const uint64_t* __restrict__ vt, int64_t k,
+                                              int64_t words, int64_t pair0, int panel_pairs) {
+  const int64_t pairs = words >> 1;
+  const int total = (int)k * panel_pairs;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int l = e / panel_pairs, p = e - l * panel_pairs;
+    const int64_t gp = pair0 + p;
+    Vs[e] = gp < pairs ? ld_words2(vt + (int64_t)l * words + 2 * gp) : make_ulonglong2(0ull, 0ull);
+  }
+  __syncthreads();
+}
+
+// OR of the V^T rows selected by ONE usage word (k <= 64) at the lane's four pair slots
+__device__ __forceinline__ void panel_or1(const ulonglong2* Vs, int panel_pairs, uint64_t sel, int slot0,
+                                          ulonglong2 (&d)[4]) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) d[u] = make_ulonglong2(0ull, 0ull);
+  while (sel) {
+    const int l = __ffsll((long long)sel) - 1;
+    sel &= sel - 1;
+    const ulonglong2* vr = Vs + l * panel_pairs + slot0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const ulonglong2 v = vr[32 * u];
+      d[u].x |= v.x;
+      d[u].y |= v.y;
+    }
+  }
+}
+
+// Confusion counts from factors, k <= 64.  CTA (panel, split), 16 warps.  Every warp streams ITS rows (blocks of
+// 32 consecutive rows, usage words fetched with one coalesced load per block and broadcast by shuffle) through a
+// PRIVATE ring of RING_DEPTH (3 at k = 64, up to 8) shared-memory slots filled by 1-D bulk copies (TMA engine, mbarrier complete_tx):
+// lane 0 re-issues the copy for row idx + RING_DEPTH as soon as row idx has been consumed, so 16 x RING_DEPTH row
+// segments (2 KB each) are in flight per SM at no register cost -- what it takes to cover HBM latency at 6-7 TB/s.
+// Producer and consumer of a slot are the same warp, so one "full" barrier per slot is the whole protocol.
+constexpr int RING_DEPTH_MAX = 8;       // slots per warp: as many as shared memory allows next to the V^T panel
+constexpr int PANEL_WARPS = PANEL_THREADS / 32;
+
+// half a Harley-Seal block: 8 words -> one "eights" carry; two of them make a "sixteens" word
+struct HarleySeal8 {
+  uint64_t ones = 0, twos = 0, fours = 0, eights = 0, pend = 0;
+  long long sixteens = 0;
+  __device__ __forceinline__ uint64_t fold8(const uint64_t (&w)[8]) {
+    uint64_t t2a, t2b, t4a, t4b, t8;
+    csa64(t2a, ones, ones, w[0], w[1]);
+    csa64(t2b, ones, ones, w[2], w[3]);
+    csa64(t4a, twos, twos, t2a, t2b);
+    csa64(t2a, ones, ones, w[4], w[5]);
+    csa64(t2b, ones, ones, w[6], w[7]);
+    csa64(t4b, twos, twos, t2a, t2b);
+    csa64(t8, fours, fours, t4a, t4b);
+    return t8;
+  }
+  __device__ __forceinline__ void add8_first(const uint64_t (&w)[8]) { pend = fold8(w); }
+  __device__ __forceinline__ void add8_second(const uint64_t (&w)[8]) {
+    uint64_t t16;
+    const uint64_t t8 = fold8(w);
+    csa64(t16, eights, eights, pend, t8);
+    pend = 0;
+    sixteens += __popcll(t16);
+  }
+  __device__ __forceinline__ long long total() const {
+    return 16 * sixteens + 8 * (long long)(__popcll(eights) + __popcll(pend)) + 4 * (long long)__popcll(fours) +
+           2 * (long long)__popcll(twos) + (long long)__popcll(ones);
+  }
+};
+
+// d = OR of the V^T rows selected by `sel` (warp-uniform) at the lane's four pair slots; the common cases of one and
+// two selected rows are straight-line code (sel comes from a shuffle, so the branch never diverges)
+__device__ __forceinline__ void panel_or_fast(const ulonglong2* Vs, int panel_pairs, uint64_t sel, int slot0,
+                                              ulonglong2 (&d)[4]) {
+  if (sel == 0) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) d[u] = make_ulonglong2(0ull, 0ull);
+    return;
+  }
+  const int l0 = __ffsll((long long)sel) - 1;
+  sel &= sel - 1;
+  const ulonglong2* v0 = Vs + l0 * panel_pairs + slot0;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) d[u] = v0[32 * u];
+  while (sel) {
+    const int l = __ffsll((long long)sel) - 1;
+    sel &= sel - 1;
+    const ulonglong2* vr = Vs + l * panel_pairs + slot0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const ulonglong2 v = vr[32 * u];
+      d[u].x |= v.x;
+      d[u].y |= v.y;
+    }
+  }
+}
+
+template <bool COUNT_GT>
+__global__ void __launch_bounds__(PANEL_THREADS, 1)
+confusion_panel_kernel(const uint64_t* __restrict__ gt, int64_t m, int64_t words,
+                       const uint64_t* __restrict__ u_words, const uint64_t* __restrict__ vt, int64_t k,
+                       int panel_chunks, int RING_DEPTH, unsigned long long* __restrict__ counts) {
+  extern __shared__ __align__(128) uint8_t panel_smem[];
+  const int panel_pairs = panel_chunks * CH_PAIRS;
+  const int row_bytes = panel_pairs * 16;
+  ulonglong2* Vs = reinterpret_cast<ulonglong2*>(panel_smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* ring = panel_smem + (size_t)k * row_bytes + (size_t)warp * RING_DEPTH * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(panel_smem + (size_t)(k + PANEL_WARPS * RING_DEPTH) * row_bytes);
+  const uint32_t bar0 = smem_u32(bars + warp * RING_DEPTH);
+  const uint32_t ring0 = smem_u32(ring);
+
+  const int64_t pairs = words >> 1;
+  const int64_t pair0 = (int64_t)blockIdx.x * panel_pairs;
+  const int valid_pairs = (int)((pairs - pair0) < panel_pairs ? (pairs - pair0) : panel_pairs);
+  const uint32_t seg_bytes = (uint32_t)valid_pairs * 16u;
+  const int nch = (valid_pairs + CH_PAIRS - 1) / CH_PAIRS;  // chunks this panel really has
+  if (lane == 0) {
+    for (int s = 0; s < RING_DEPTH; ++s) mbar_init(bar0 + 8u * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // the bulk copies only ever write seg_bytes per slot: zero the slots once and their tails stay zero, so the
+  // consumer needs no column predicates
+  for (int e = lane; e < RING_DEPTH * panel_pairs; e += 32)
+    reinterpret_cast<ulonglong2*>(ring)[e] = make_ulonglong2(0ull, 0ull);
+  fence_proxy_async();
+  load_vt_panel(Vs, vt, k, words, pair0, panel_pairs);     // ends with __syncthreads()
+
+  // this warp's rows: 32-row blocks gw, gw + nwarps, ...
+  const int64_t gw = (int64_t)blockIdx.y * PANEL_WARPS + warp;
+  const int64_t nwarps = (int64_t)gridDim.y * PANEL_WARPS;
+  const int64_t blocks_total = (m + 31) >> 5;
+  int my_blocks = 0, last_rows = 0;
+  if (gw < blocks_total) {
+    my_blocks = (int)((blocks_total - 1 - gw) / nwarps) + 1;
+    const int64_t last_block = gw + (int64_t)(my_blocks - 1) * nwarps;
+    last_rows = (int)((m - last_block * 32) < 32 ? (m - last_block * 32) : 32);
+  }
+  int to_issue = my_blocks > 0 ? (my_blocks - 1) * 32 + last_rows : 0;    // rows not yet requested
+  // issue side (meaningful in lane 0): next row segment to request, as an incrementally updated pointer
+  const uint64_t* iss_ptr = gt + 2 * pair0 + gw * 32 * words;
+  const int64_t step_block = (nwarps * 32 - 31) * words;
+  int iss_r = 0, iss_slot = 0;
+  auto issue = [&]() {
+    mbar_expect_tx(bar0 + 8u * iss_slot, seg_bytes);
+    bulk_load(ring0 + (uint32_t)(iss_slot * row_bytes), iss_ptr, seg_bytes, bar0 + 8u * iss_slot);
+    iss_slot = iss_slot == RING_DEPTH - 1 ? 0 : iss_slot + 1;
+    if (++iss_r == 32) { iss_r = 0; iss_ptr += step_block; } else { iss_ptr += words; }
+    --to_issue;
+  };
+  if (lane == 0)
+    for (int d = 0; d < RING_DEPTH && to_issue > 0; ++d) issue();
+
+  HarleySeal8 hs_tp, hs_pd, hs_gt;
+  int slot = 0;
+  uint32_t phase = 0;
+  bool second = false;
+  const uint64_t* u_ptr = u_words + gw * 32 + lane;
+  uint64_t u_next = (my_blocks > 0 && gw * 32 + lane < m) ? __ldg(u_ptr) : 0ull;
+  for (int blk = 0; blk < my_blocks; ++blk) {
+    const uint64_t u_cur = u_next;
+    u_ptr += nwarps * 32;
+    u_next = (blk + 1 < my_blocks && (gw + (int64_t)(blk + 1) * nwarps) * 32 + lane < m) ? __ldg(u_ptr) : 0ull;
+    const int nrows = blk + 1 < my_blocks ? 32 : last_rows;
+    for (int r = 0; r < nrows; ++r) {
+      const uint64_t sel = __shfl_sync(0xffffffffu, u_cur, r);
+      const ulonglong2* seg = reinterpret_cast<const ulonglong2*>(ring + (size_t)slot * row_bytes);
+      mbar_wait(bar0 + 8u * slot, phase);
+      for (int c = 0; c < nch; ++c) {
+        const int slot0 = c * CH_PAIRS + lane;
+        ulonglong2 g[4], d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) g[u] = seg[slot0 + 32 * u];
+        panel_or_fast(Vs, panel_pairs, sel, slot0, d);
+        uint64_t w[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { w[2 * u] = g[u].x & d[u].x; w[2 * u + 1] = g[u].y & d[u].y; }
+        if (!second) hs_tp.add8_first(w); else hs_tp.add8_second(w);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { w[2 * u] = d[u].x; w[2 * u + 1] = d[u].y; }
+        if (!second) hs_pd.add8_first(w); else hs_pd.add8_second(w);
+        if (COUNT_GT) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { w[2 * u] = g[u].x; w[2 * u + 1] = g[u].y; }
+          if (!second) hs_gt.add8_first(w); else hs_gt.add8_second(w);
+        }
+        second = !second;
+      }
+      __syncwarp();                                         // every lane has consumed the slot
+      if (lane == 0 && to_issue > 0) issue();               // refill it with the row RING_DEPTH ahead
+      if (++slot == RING_DEPTH) { slot = 0; phase ^= 1u; }
+    }
+  }
+  const long long t_tp = warp_sum_ll(hs_tp.total());
+  const long long t_pd = warp_sum_ll(hs_pd.total());
+  const long long t_gt = COUNT_GT ? warp_sum_ll(hs_gt.total()) : 0;
+  if (lane == 0 && (t_pd | t_gt)) {
+    atomicAdd(counts + 0, (unsigned long long)t_tp);
+    atomicAdd(counts + 1, (unsigned long long)t_pd);
+    if (COUNT_GT) atomicAdd(counts + 2, (unsigned long long)t_gt);
+  }
+}
+
+// Boolean product, k <= 64: a warp owns 32 consecutive rows per pass, fetches their usage words with ONE
+// coalesced load (the next block's is prefetched) and broadcasts them by shuffle, so no global load sits on the
+// critical path of a row; 1024 threads keep enough 128-bit streaming stores in flight.
+constexpr int PRODUCT_THREADS = 1024;
+__global__ void __launch_bounds__(PRODUCT_THREADS, 1)
+bool_product_panel_kernel(const uint64_t* __restrict__ u_words, int64_t m, const uint64_t* __restrict__ vt,
+                          int64_t k, int64_t words, int panel_chunks, uint64_t* __restrict__ pd) {
+  extern __shared__ __align__(128) uint8_t panel_smem[];
+  ulonglong2* Vs = reinterpret_cast<ulonglong2*>(panel_smem);
+  const int panel_pairs = panel_chunks * CH_PAIRS;
+  const int64_t pairs = words >> 1;
+  const int64_t pair0 = (int64_t)blockIdx.x * panel_pairs;
+  load_vt_panel(Vs, vt, k, words, pair0, panel_pairs);
+
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.y * (blockDim.x >> 5);
+  uint64_t mine = warp0 * 32 + lane < m ? __ldg(u_words + warp0 * 32 + lane) : 0ull;
+  for (int64_t base = warp0 * 32; base < m; base += nwarps * 32) {
+    const uint64_t cur = mine;
+    const int64_t nb = base + nwarps * 32 + lane;
+    mine = nb < m ? __ldg(u_words + nb) : 0ull;
+    const int nrows = (int)((m - base) < 32 ? (m - base) : 32);
+    for (int r = 0; r < nrows; ++r) {
+      const uint64_t sel = __shfl_sync(0xffffffffu, cur, r);
+      uint64_t* out = pd + (base + r) * words;
+      for (int c = 0; c < panel_chunks; ++c) {
+        const int slot0 = c * CH_PAIRS + lane;
+        if (pair0 + c * CH_PAIRS >= pairs) break;
+        ulonglong2 d[4];
+        panel_or1(Vs, panel_pairs, sel, slot0, d);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t gp = pair0 + slot0 + 32 * u;
+          if (gp < pairs) __stcs(reinterpret_cast<ulonglong2*>(out) + gp, d[u]);
+        }
+      }
+    }
+  }
+}
+
+// panel geometry for k <= 64 rows of V^T: chunks (of 256 words) per panel; 0 = use the row-stream kernels
+constexpr int PANEL_SMEM_BUDGET = 224 * 1024;
+static inline int panel_chunks_for(int64_t k, int64_t kw, int64_t words) {
+  if (k <= 0 || k > 64 || kw != 1) return 0;
+  const int64_t need = ceil_div(words >> 1, CH_PAIRS);
+  // two chunks only when that makes ONE balanced panel and still leaves two ring slots per warp
+  if (need == 2 && (k + 2 * PANEL_WARPS) * 2 * CH_PAIRS * 16 <= PANEL_SMEM_BUDGET) return 2;
+  return 1;
+}
+static inline int confusion_ring_depth(int64_t k, int chunks) {
+  const int64_t row_bytes = (int64_t)chunks * CH_PAIRS * 16;
+  int64_t depth = (PANEL_SMEM_BUDGET - k * row_bytes) / (PANEL_WARPS * row_bytes);
+  if (depth > RING_DEPTH_MAX) depth = RING_DEPTH_MAX;
+  return (int)depth;
+}
+static inline size_t confusion_panel_smem(int64_t k, int chunks, int depth) {
+  return (size_t)(k + PANEL_WARPS * depth) * chunks * CH_PAIRS * 16 + PANEL_WARPS * RING_DEPTH_MAX * 8;
+}
+static inline bool panel_disabled() {
+  const char* e = getenv("BMF_NO_PANEL");
+  return e != nullptr && e[0] == '1';
+}
+
 // counts = (TP, |pd|, |gt| or unused) -> (TP, FP, FN)
 __global__ void confusion_finalize_kernel(long long* __restrict__ counts, long long gt_ones) {
   const long long tp = counts[0], pd = counts[1], g = gt_ones >= 0 ? gt_ones : counts[2];
@@ -803,6 +1119,24 @@ extern "C" int bmf_bool_product(const uint64_t* u_words, int64_t m, int64_t kw, 
                                 int64_t k, int64_t words, uint64_t* pd_bits, bmf_stream_t stream) {
   BMF_REQUIRE(u_words && pd_bits && m > 0 && kw > 0 && k >= 0 && k <= kw * 64, "bmf_bool_product: bad arguments");
   BMF_REQUIRE(words > 0 && words % 2 == 0 && (k == 0 || vt_bits), "bmf_bool_product: bad words / vt_bits");
+  const int chunks = panel_disabled() ? 0 : panel_chunks_for(k, kw, words);
+  if (chunks > 0) {
+    const int panel_pairs = chunks * CH_PAIRS;
+    const size_t smem = (size_t)k * panel_pairs * 16;
+    const int64_t panels = ceil_div(words >> 1, panel_pairs);
+    int64_t splits = (int64_t)num_sms() / panels;              // one CTA per SM, ONE wave
+    const int64_t max_splits = ceil_div(m, 32 * (PRODUCT_THREADS / 32));
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    if (splits > 65535) splits = 65535;
+    int rc = check_cuda(cudaFuncSetAttribute(bool_product_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem), "bmf_bool_product");
+    if (rc) return rc;
+    dim3 grid((unsigned)panels, (unsigned)splits);
+    bool_product_panel_kernel<<<grid, PRODUCT_THREADS, smem, as_stream(stream)>>>(u_words, m, vt_bits, k, words, chunks, pd_bits);
+    BMF_LAUNCH_CHECK("bmf_bool_product");
+    return 0;
+  }
   int64_t blocks = ceil_div(m, 8);
   if (blocks > row_stream_grid()) blocks = row_stream_grid();
   bool_product_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(u_words, m, kw, vt_bits, words, pd_bits);
@@ -812,11 +1146,41 @@ extern "C" int bmf_bool_product(const uint64_t* u_words, int64_t m, int64_t kw, 
 
 template <bool FROM_FACTORS>
 static int launch_confusion(const uint64_t* gt_bits, const uint64_t* pd_bits, int64_t m, int64_t words,
-                            const uint64_t* u_words, int64_t kw, const uint64_t* vt_bits, int64_t gt_ones,
+                            const uint64_t* u_words, int64_t kw, const uint64_t* vt_bits, int64_t k, int64_t gt_ones,
                             int64_t* counts, int32_t* row_tp, int32_t* row_fp, cudaStream_t st, const char* who) {
   int rc = check_cuda(cudaMemsetAsync(counts, 0, 3 * sizeof(int64_t), st), who);
   if (rc) return rc;
   unsigned long long* c = reinterpret_cast<unsigned long long*>(counts);
+  if (FROM_FACTORS && row_tp == nullptr && row_fp == nullptr && !panel_disabled()) {
+    const int chunks = panel_chunks_for(k, kw, words);
+    if (chunks > 0) {
+      const int panel_pairs = chunks * CH_PAIRS;
+      const int depth = confusion_ring_depth(k, chunks);
+      const size_t smem = confusion_panel_smem(k, chunks, depth);
+      const int64_t panels = ceil_div(words >> 1, panel_pairs);
+      int64_t splits = (int64_t)num_sms() / panels;              // one CTA per SM, ONE wave
+      const int64_t max_splits = ceil_div(ceil_div(m, 32), PANEL_WARPS);
+      if (splits > max_splits) splits = max_splits;
+      if (splits < 1) splits = 1;
+      if (splits > 65535) splits = 65535;
+      dim3 grid((unsigned)panels, (unsigned)splits);
+      if (gt_ones >= 0) {
+        rc = check_cuda(cudaFuncSetAttribute(confusion_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem), who);
+        if (rc) return rc;
+        confusion_panel_kernel<false><<<grid, PANEL_THREADS, smem, st>>>(gt_bits, m, words, u_words, vt_bits, k, chunks, depth, c);
+      } else {
+        rc = check_cuda(cudaFuncSetAttribute(confusion_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem), who);
+        if (rc) return rc;
+        confusion_panel_kernel<true><<<grid, PANEL_THREADS, smem, st>>>(gt_bits, m, words, u_words, vt_bits, k, chunks, depth, c);
+      }
+      rc = check_cuda(cudaGetLastError(), who);
+      if (rc) return rc;
+      confusion_finalize_kernel<<<1, 1, 0, st>>>(reinterpret_cast<long long*>(counts), (long long)gt_ones);
+      return check_cuda(cudaGetLastError(), who);
+    }
+  }
   int64_t blocks = ceil_div(m, 8);
   if (blocks > row_stream_grid()) blocks = row_stream_grid();
   if (gt_ones >= 0)
@@ -836,7 +1200,7 @@ extern "C" int bmf_confusion_factors(const uint64_t* gt_bits, int64_t m, int64_t
                                      int64_t* counts, int32_t* row_tp, int32_t* row_fp, bmf_stream_t stream) {
   BMF_REQUIRE(gt_bits && u_words && counts && m > 0 && kw > 0 && k <= kw * 64, "bmf_confusion_factors: bad arguments");
   BMF_REQUIRE(words > 0 && words % 2 == 0 && (k == 0 || vt_bits), "bmf_confusion_factors: bad words / vt_bits");
-  return launch_confusion<true>(gt_bits, nullptr, m, words, u_words, kw, vt_bits, gt_ones, counts, row_tp, row_fp,
+  return launch_confusion<true>(gt_bits, nullptr, m, words, u_words, kw, vt_bits, k, gt_ones, counts, row_tp, row_fp,
                                 as_stream(stream), "bmf_confusion_factors");
 }
 
@@ -844,7 +1208,7 @@ extern "C" int bmf_confusion_bits(const uint64_t* gt_bits, const uint64_t* pd_bi
                                   int64_t gt_ones, int64_t* counts, int32_t* row_tp, int32_t* row_fp,
                                   bmf_stream_t stream) {
   BMF_REQUIRE(gt_bits && pd_bits && counts && m > 0 && words > 0 && words % 2 == 0, "bmf_confusion_bits: bad arguments");
-  return launch_confusion<false>(gt_bits, pd_bits, m, words, nullptr, 0, nullptr, gt_ones, counts, row_tp, row_fp,
+  return launch_confusion<false>(gt_bits, pd_bits, m, words, nullptr, 0, nullptr, 0, gt_ones, counts, row_tp, row_fp,
                                  as_stream(stream), "bmf_confusion_bits");
 }
 

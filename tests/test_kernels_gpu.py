@@ -372,6 +372,49 @@ def test_bool_product_and_confusion(nat, m, n, k):
             _native.call("bmf_confusion_bits", _dev(device.dense_to_words(X)), pd, m, words, ones, counts, row_tp, row_fp)
         assert list(counts.cpu().numpy()) == [int(tp), int(fp), int(fn)]
         assert np.array_equal(row_tp.cpu().numpy(), rtp) and np.array_equal(row_fp.cpu().numpy(), rfp)
+        if mode == "factors":                                       # totals only -> column-panel kernel (Harley-Seal)
+            counts = device.zeros((3,), torch.int64) + 999
+            _native.call("bmf_confusion_factors", _dev(device.dense_to_words(X)), m, words, _dev(uw), kw, _dev(vt), k,
+                         ones, counts, None, None)
+            assert list(counts.cpu().numpy()) == [int(tp), int(fp), int(fn)]
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 64, 1), (33, 16500, 64), (2500, 33000, 17), (10001, 4097, 100), (777, 1000, 128),
+                                   (150001, 130, 5)])
+def test_panel_kernels_match_row_stream_kernels(nat, m, n, k, monkeypatch):
+    """column-panel product / confusion (V^T in shared memory, Harley-Seal counting) vs the row-stream
+    kernels (BMF_NO_PANEL=1) and numpy; k > 100 does not fit shared memory and must fall back silently"""
+    _native, device = nat
+    rng = np.random.RandomState(m + n + k)
+    kw = (k + 63) // 64
+    U = _rand01(rng, m, k, 2.0 / max(k, 4))
+    V = _rand01(rng, n, k, 0.05)
+    uw = _dev(np.ascontiguousarray(device.dense_to_words(U, words=kw)))
+    vt = _dev(device.dense_to_words(V.T))
+    words = device.words_for(n)
+    gt = torch.randint(-2 ** 63, 2 ** 63 - 1, (m, words), dtype=torch.int64, device="cuda")
+    gt &= torch.randint(-2 ** 63, 2 ** 63 - 1, (m, words), dtype=torch.int64, device="cuda")
+    if n % 64:
+        gt[:, n // 64] &= (1 << (n % 64)) - 1
+    gt[:, (n + 63) // 64:] = 0
+    out = {}
+    for tag, env in (("panel", "0"), ("rows", "1")):
+        monkeypatch.setenv("BMF_NO_PANEL", env)
+        pd = device.zeros((m, words), torch.int64) - 1
+        _native.call("bmf_bool_product", uw, m, kw, vt, k, words, pd)
+        c_known = device.zeros((3,), torch.int64)
+        c_count = device.zeros((3,), torch.int64)
+        _native.call("bmf_confusion_factors", gt, m, words, uw, kw, vt, k, -1, c_count, None, None)
+        _native.call("bmf_confusion_factors", gt, m, words, uw, kw, vt, k, int(c_count[0] + c_count[2]), c_known, None, None)
+        out[tag] = (pd, c_count.cpu().numpy(), c_known.cpu().numpy())
+    assert torch.equal(out["panel"][0], out["rows"][0])
+    assert np.array_equal(out["panel"][1], out["rows"][1]) and np.array_equal(out["panel"][2], out["rows"][2])
+    assert np.array_equal(out["panel"][1], out["panel"][2])
+    want = O.bool_product(U, V)
+    assert np.array_equal(device.bits_to_host(out["panel"][0], n), want)
+    G = device.bits_to_host(gt, n)
+    tp, fp, fn = O.confusion(G, want)
+    assert list(out["panel"][1]) == [int(tp), int(fp), int(fn)]
 
 
 def test_confusion_triplets(nat):
