@@ -67,6 +67,30 @@ def to_csr_pattern(X) -> sp.csr_matrix:
     return X
 
 
+def csr_rows_view(X, r0: int, r1: int) -> sp.csr_matrix:
+    """Rows [r0, r1) of a csr matrix WITHOUT copying indices / data (scipy's X[r0:r1] copies both: 0.4 s for half
+    of a 1e8-nnz matrix); only the (r1 - r0 + 1) row pointers are rebased."""
+    X = X if sp.isspmatrix_csr(X) else sp.csr_matrix(X)
+    if r0 == 0 and r1 == X.shape[0]:
+        return X
+    a, b = int(X.indptr[r0]), int(X.indptr[r1])
+    indptr = (X.indptr[r0:r1 + 1] - X.indptr[r0]).astype(np.int64, copy=False)
+    out = sp.csr_matrix((r1 - r0, X.shape[1]), dtype=X.dtype)
+    out.indptr, out.indices, out.data = indptr, X.indices[a:b], X.data[a:b]
+    return out
+
+
+def has_stored_zeros(X: sp.csr_matrix) -> bool:
+    """O(nnz) host scan of the value array (the pattern kernels treat every STORED entry as a one)."""
+    return bool(X.nnz) and X.data.dtype != np.bool_ and np.count_nonzero(X.data) != X.nnz
+
+
+def drop_stored_zeros(X: sp.csr_matrix) -> sp.csr_matrix:
+    X = X.copy()
+    X.eliminate_zeros()
+    return X
+
+
 # ---- device packing --------------------------------------------------------------------------
 def upload_csr(X: sp.csr_matrix):
     """H2D copy of the pattern arrays (indptr int64, indices int32); values are never read."""

@@ -9,6 +9,8 @@ totals and takes the identical lowest-index strict argmax
 from __future__ import annotations
 
 import os
+import sys
+import time
 
 import numpy as np
 import scipy.sparse as sp
@@ -62,22 +64,50 @@ def all_reduce_sum(t):
     return t
 
 
+class _Trace:
+    """BMF_FIT_TRACE=1: wall-clock phases of a fit (with a device sync at every mark), printed by rank 0."""
+
+    def __init__(self):
+        self.on = os.environ.get("BMF_FIT_TRACE", "0") == "1"
+        self.t = time.perf_counter()
+        self.rows = []
+
+    def mark(self, name):
+        if not self.on:
+            return
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        self.rows.append((name, now - self.t))
+        self.t = now
+
+    def dump(self, rank):
+        if self.on and rank == 0:
+            agg = {}
+            for name, dt in self.rows:
+                agg[name] = agg.get(name, 0.0) + dt
+            print("[fit trace] " + "  ".join("%s=%.1fms" % (k, 1e3 * v) for k, v in agg.items()), file=sys.stderr)
+
+
 class CoverEngine:
     """All device buffers and kernel launches behind Asso.init_model / Asso._fit."""
 
     def __init__(self, X: sp.csr_matrix, w_fp: float, w_fn: float, scorer: str = "auto", assoc: str = "auto"):
         _native.require_gpu()
+        self.trace = _Trace()
         self.rank, self.world = dist_ctx()
         self.m, self.n = X.shape
         self.plan = ShardPlan(self.m, self.world)
         r0, r1 = self.plan.rows(self.rank)
         self.r0, self.r1 = r0, r1
         self.m_loc = r1 - r0
-        # each rank canonicalises only ITS rows; the total number of ones is one scalar all-reduce
-        Xl = device.to_csr_pattern(X[r0:r1] if self.world > 1 else X)
-        nnz = torch.tensor([int(Xl.nnz)], dtype=torch.int64, device=device.dev())
-        all_reduce_sum(nnz)
-        self.sum_x = int(nnz.item())
+        # Each rank takes only ITS rows (a view, no copy).  The packer ORs bits, so unsorted or duplicate column
+        # indices need no host-side canonicalisation; explicitly stored zeros do matter, but scanning 1e8 values
+        # takes the host ~0.1 s, so the scan runs in build_basis() WHILE the GPU packs and computes X^T X, and only
+        # a matrix that really stores zeros (rare) is cleaned and rebuilt.  |X| is counted on the device.
+        self._ctor_args = (w_fp, w_fn, scorer, assoc)
+        Xl = device.csr_rows_view(X, r0, r1)
+        self._host_rows = Xl
+        self.trace.mark("host_csr")
         self.w_fp, self.w_fn = float(w_fp), float(w_fn)
         iw = integer_weights(self.w_fp, self.w_fn)
         self.wa, self.wb, self.shift = iw if iw else (0, 0, 0)
@@ -109,6 +139,13 @@ class CoverEngine:
         m_alloc = max(self.m_loc, 1)
         self._ip, self._ix = device.upload_csr(Xl)
         self.x_bits = device.pack_csr(self._ip, self._ix, self.m_loc, self.n)
+        ones = device.zeros((3,), torch.int64)
+        if self.m_loc > 0:                                      # |X| of this rank's rows: TP of X against itself
+            _native.call("bmf_confusion_bits", self.x_bits, self.x_bits, self.m_loc, self.words, -1, ones, None, None)
+        all_reduce_sum(ones)
+        self._ones = ones                                       # read (one sync) at the end of build_basis()
+        self.sum_x = None
+        self.trace.mark("h2d_pack")
         self.c_bits = device.zeros((m_alloc, self.words), torch.int64)
         self.tp_old = device.zeros((m_alloc,), torch.int32)
         self.fp_old = device.zeros((m_alloc,), torch.int32)
@@ -128,6 +165,30 @@ class CoverEngine:
 
     # ---- association + basis (Asso.py:191-235) -------------------------------------------------
     def build_basis(self, tau: float):
+        self._build_basis(tau)                                 # enqueued, not waited for
+        Xl, self._host_rows = self._host_rows, None
+        dirty = torch.tensor([1 if (Xl is not None and device.has_stored_zeros(Xl)) else 0], dtype=torch.int64,
+                             device=device.dev())
+        self.trace.mark("host_zero_scan")
+        all_reduce_sum(dirty)                                  # every rank must take the same branch
+        if int(dirty.item()):
+            launches = self.launches
+            clean = device.drop_stored_zeros(Xl)
+            full = sp.csr_matrix((self.m, self.n), dtype=clean.dtype)      # this rank's rows in place, others empty
+            ip = np.zeros(self.m + 1, dtype=np.int64)
+            ip[self.r0 + 1:self.r1 + 1] = clean.indptr[1:]
+            ip[self.r1 + 1:] = clean.indptr[-1]
+            full.indptr, full.indices, full.data = ip, clean.indices, clean.data
+            self.__init__(full, *self._ctor_args)
+            self._host_rows = None
+            self.launches += launches
+            self._build_basis(tau)
+        nb = int(self.alive.sum().item())
+        self.sum_x = int(self._ones[0].item())
+        self.trace.mark("basis_wait")
+        return nb
+
+    def _build_basis(self, tau: float):
         n, m_loc = self.n, self.m_loc
         n_pad = device.round_up(n, 256)
         cnt = device.zeros((n_pad, n_pad), torch.int32)
@@ -141,7 +202,9 @@ class CoverEngine:
                 _native.call("bmf_assoc_counts_popc", xt_bits, n, xt_bits.shape[1], cnt, n_pad)
             self.launches += 3
             del xt_bits
+        self.trace.mark("assoc_counts")
         all_reduce_sum(cnt)
+        self.trace.mark("assoc_allreduce")
         self.cnt = cnt
         if self.scorer == "tcgen05":
             self.cand_plane = device.zeros((self.cand_pad, self.ld), torch.int8)
@@ -151,7 +214,7 @@ class CoverEngine:
         self.launches += 1
         if self.scorer == "tcgen05":
             self._rebuild_rows_plane()
-        return int(self.alive.sum().item())
+        self.trace.mark("basis_planes")
 
     def _rebuild_rows_plane(self):
         """rows_plane[i][k] = 0 if covered, +wb if x, -wa otherwise (the signed operand of D = wb*P - wa*N)."""

@@ -346,6 +346,9 @@ class Asso(BaseModel):
             self._fit()
         finally:
             self._materialize_factors(final=True)
+            if "_dev" in self.__dict__:
+                self._dev.trace.mark("factors_to_host")
+                self._dev.trace.dump(self._dev.rank)
             self._release_device()
         self.__dict__.pop("X_pd", None)                        # recomputed lazily from the final U, V (Asso.py:44)
         self.finish(show_logs=self.show_logs, save_model=self.save_model, show_result=self.show_result)
@@ -444,6 +447,7 @@ class Asso(BaseModel):
         best_score = 0
         n_basis = self._dev_nb
         need_reset = False
+        prescored = False
         while is_improving:
             best_score = 0 if k == 0 else best_score
             if n_basis == 0:
@@ -452,8 +456,12 @@ class Asso(BaseModel):
             if need_reset:                                   # factors were truncated (D1): cover = current U o V^T
                 dev.reset_cover([(e["ui"], e["j"]) for e in self._dev_kept if e is not None])
                 need_reset = False
-            dev.score_all()
+                prescored = False
+            if not prescored:
+                dev.score_all()
+            prescored = False
             winner, score, used, sum_p, sum_n = dev.select_and_apply(best_score)
+            dev.trace.mark("greedy_steps")
             if winner < 0:
                 is_improving = self.early_stop(msg="No pattern found.", k=k)
                 break
@@ -465,6 +473,14 @@ class Asso(BaseModel):
 
             tp, fp = dev.tp_tot, dev.fp_tot
             fn = dev.sum_x - tp
+            # The next step's scoring pass depends only on device state, so it is enqueued BEFORE this step's log row
+            # is built on the host (pandas, ~2 ms) -- unless the early-stop rules below are about to end the loop or to
+            # truncate the factors (D1), both of which are decided by these integer counters alone.
+            will_stop = (hasattr(self, "tol") and U_.rates(tp, fp, fn, size)["ERR"] <= self.tol) or \
+                        (self.k is not None and k + 1 >= self.k) or n_basis == 0
+            if not will_stop and not dev.trace.on:
+                dev.score_all()
+                prescored = True
             tp_a, fp_a, fn_a = (np.array(v, dtype=np.int64) for v in (tp, fp, fn))
             score_05 = -0.5 * fp_a + 0.5 * tp_a                                     # Asso.py:119
             u_sum = np.float64(sum(e["used"] for e in self._dev_kept if e is not None))

@@ -80,6 +80,32 @@ def test_asso_general_weights_auto_is_tensor_core(M):
     assert eng.scorer == "tcgen05" and eng.encoding == "pq" and not eng.integer_mode
 
 
+def test_non_canonical_csr_input(M):
+    """stored zeros, duplicate and unsorted column indices in the csr input give the same fit as the clean matrix
+    (the packer ORs bits; stored zeros are detected by a host scan that overlaps the association GEMM)"""
+    c = load_golden("c1_noisy")
+    g = c["g"]
+    X = sp.csr_matrix(c["X"]).astype(np.int64)
+    coo = X.tocoo()
+    rng = np.random.RandomState(3)
+    zr, zc = rng.randint(0, X.shape[0], 500), rng.randint(0, X.shape[1], 500)
+    keep = np.asarray(X[zr, zc]).ravel() == 0                        # explicit zeros only where X is zero
+    dup = rng.choice(len(coo.row), 300, replace=False)              # duplicates of existing ones (values add up to 2)
+    rows = np.concatenate([coo.row, zr[keep], coo.row[dup]])
+    cols = np.concatenate([coo.col, zc[keep], coo.col[dup]])
+    vals = np.concatenate([coo.data, np.zeros(keep.sum(), np.int64), coo.data[dup]])
+    perm = rng.permutation(len(rows))
+    order = np.argsort(rows[perm], kind="stable")                   # rows grouped, columns in random order
+    r, cc, v = rows[perm][order], cols[perm][order], vals[perm][order]
+    indptr = np.concatenate([[0], np.cumsum(np.bincount(r, minlength=X.shape[0]))])
+    messy = sp.csr_matrix((v, cc, indptr), shape=X.shape)
+    assert not messy.has_sorted_indices and (messy.data == 0).any()
+    mdl = M.Asso(tau=c["tau"], k=c["k"], w_fp=c["w_fp"], w_fn=c["w_fn"])
+    mdl.fit(messy, **FIT_KW)
+    assert np.array_equal(_dense(mdl.U), g["U"]) and np.array_equal(_dense(mdl.V), g["V"])
+    _check_logs(mdl.logs["updates"], g)
+
+
 def test_known_answer_table_ex01_6(M):
     """numbers typed from /root/reference/examples/ex01_6_logs.ipynb:253-361"""
     c = load_golden("ex01_6")
