@@ -60,15 +60,19 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
 
-    def mark(self):
-        """Samples taken from now on belong to the timed region."""
+    def mark(self, wait_s=4.0):
+        """Samples taken from now on belong to the timed region.  nvidia-smi needs a moment to come up (longer when
+        eight ranks start one each): wait, outside the timed region, until it has delivered its first sample."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < wait_s:
+            time.sleep(0.02)
         self.first = len(self.rows)
 
     def start(self):
         self.first = 0
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -104,7 +108,7 @@ def cpu_sample_setup(X, workload, tau):
     The candidates are association rows of the sampled columns computed from the row sample."""
     from oracle import asso_oracle as O
     m, n = X.shape
-    rows, cands = {"c4": (2048, 1024), "c2": (2048, 1024), "c1": (1000, 500)}[workload]
+    rows, cands = {"c4": (4096, 2048), "c2": (4096, 2048), "c1": (1000, 500)}[workload]
     rows, cands = min(rows, m), min(cands, n)
     Xs = O.as_dense01(X[:rows])
     A = O.build_assoc(Xs[:, :])[:cands]
@@ -381,8 +385,8 @@ def main():
     for _ in range(args.warmup):
         greedy_step(False)
     launches0 = eng.launches
+    sampler.mark()                                              # may wait for nvidia-smi's first sample: before the barrier
     barrier()
-    sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):

@@ -53,6 +53,7 @@ struct EpiArgs {
   const int32_t* fp_old;
   int64_t m_rows;                  // EPI_GAIN2: true number of data rows (the rest is padding)
   double neg_w_fp, w_fn;           // EPI_GAIN2
+  uint64_t policy_a, policy_b;     // L2 eviction policy of the candidate (A) and data-row (B) TMA loads
 };
 struct __align__(16) RowState { double s_old; int tpo; int fpo; };
 
@@ -62,10 +63,18 @@ struct __align__(16) RowState { double s_old; int tpo; int fpo; };
 constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                               ((uint32_t)(BM >> 4) << 24);
 
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+// L2 eviction policies for the operand streams (createpolicy encodings, as in cute::TMA::CacheHintSm90),
+// selectable with BMF_L2_HINT for experiments; see dispatch_gemm for what was measured.
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -258,8 +267,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), STAGE_BYTES);
           const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
-          tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * BK, mt * BM);
-          tma_load_2d(a_dst + A_BYTES, &tmap_b, full_bar(stage), kb * BK, nt * BN);
+          tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * BK, mt * BM, ea.policy_a);
+          tma_load_2d(a_dst + A_BYTES, &tmap_b, full_bar(stage), kb * BK, nt * BN, ea.policy_b);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -416,10 +425,12 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1,
+                                                uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void tcgen05_commit_2sm(uint32_t bar) {
@@ -498,8 +509,8 @@ gemm_i8_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           const uint32_t leader_full = full_bar(stage) & PEER_MASK;
           if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES2);     // bytes of both CTAs
           const uint32_t a_dst = smem_base + stage * STAGE_BYTES2;
-          tma_load_2d_2sm(a_dst, &tmap_a, leader_full, kb * BK, mt * BM2 + (int)rank * HALF);
-          tma_load_2d_2sm(a_dst + OP_BYTES, &tmap_b, leader_full, kb * BK, nt * BN + (int)rank * HALF);
+          tma_load_2d_2sm(a_dst, &tmap_a, leader_full, kb * BK, mt * BM2 + (int)rank * HALF, ea.policy_a);
+          tma_load_2d_2sm(a_dst + OP_BYTES, &tmap_b, leader_full, kb * BK, nt * BN + (int)rank * HALF, ea.policy_b);
           if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
         }
       }
@@ -592,8 +603,16 @@ static int launch_gemm_2sm(const int8_t* a, int64_t a_rows, const int8_t* b, int
 // variant: 0 = auto (2-SM when the candidate rows are a multiple of 256), 1 = 1-SM, 2 = 2-SM
 template <int EPI>
 static int dispatch_gemm(int variant, const int8_t* a, int64_t a_rows, const int8_t* b, int64_t b_rows, int64_t ld,
-                         const EpiArgs& ea, cudaStream_t stream) {
+                         const EpiArgs& ea_in, cudaStream_t stream) {
   if (const char* e = getenv("BMF_GEMM_VARIANT")) { int v = atoi(e); if (v == 1 || v == 2) variant = v; }
+  EpiArgs ea = ea_in;
+  // measured at c4 (profiles/r01b_l2_hint_sweep.md): the data-row tiles ARE re-read inside a wave (16 pairs share one), so
+  // evict_first on them raises DRAM traffic 295 -> 450 GB per launch; evict_last on the candidate panel changes nothing
+  // measurable.  Default: no hint.  0 none, 1 A evict_last + B evict_first, 2 B only, 3 A only
+  int hint = 0;
+  if (const char* e = getenv("BMF_L2_HINT")) { int v = atoi(e); if (v >= 0 && v <= 3) hint = v; }
+  ea.policy_a = (hint == 1 || hint == 3) ? L2_EVICT_LAST : L2_EVICT_NORMAL;
+  ea.policy_b = (hint == 1 || hint == 2) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
   const bool ok2 = (a_rows % sm2::BM2) == 0;
   if (variant == 2 && !ok2) {
     set_error("2-SM int8 kernel needs the candidate rows padded to a multiple of 256 (got %lld)", (long long)a_rows);

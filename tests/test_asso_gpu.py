@@ -343,6 +343,35 @@ def test_c4_full_size_properties(M):
     assert torch.equal(gp[: eng.n][live], eng.gain_p[: eng.n][live])
 
 
+def test_c4_slice_general_weights_tensor_cores_equal_popcount(M):
+    """non-dyadic weights at Netflix width (17770 columns, 120k rows of configs[3]): the P/Q tensor-core scorer and the
+    popcount scorer give identical sum_use P / sum_use N for every live candidate, before and after a greedy step
+    (which exercises the in-place update of the interleaved P/Q operand plane)."""
+    from pybmf_b200 import _native, device, synth
+    from pybmf_b200.engine import CoverEngine
+    X = synth.config_c4(rows=(0, 120000))
+    eng = CoverEngine(X, 0.2, 0.8, scorer="tcgen05")
+    assert eng.encoding == "pq"
+    nb = eng.build_basis(0.5)
+    assert nb > 15000
+    best = 0.0
+    for _step in range(2):
+        eng.score_all()
+        gp = device.zeros((eng.cand_pad,), torch.int64)
+        gn = device.zeros((eng.cand_pad,), torch.int64)
+        _native.call("bmf_cover_score_popc", eng.x_bits, eng.c_bits, eng.m_loc, eng.n, eng.words, eng.basis_bits,
+                     eng.alive, eng.tp_old, eng.fp_old, 0, 0, 0.2, 0.8, gp, gn)
+        live = eng.alive.bool()
+        assert torch.equal(gp[: eng.n][live], eng.gain_p[: eng.n][live])
+        assert torch.equal(gn[: eng.n][live], eng.gain_n[: eng.n][live])
+        winner, best, used, sp_, sn_ = eng.select_and_apply(best)
+        assert winner >= 0 and used > 0
+    # the plane kept current by bmf_cover_apply_general equals a fresh expansion of (X, C)
+    fresh = device.empty(tuple(eng.rows_plane.shape), torch.int8)
+    _native.call("bmf_expand_bits_pq", eng.x_bits, eng.c_bits, eng.m_loc, eng.n, eng.words, fresh, eng.ld)
+    assert torch.equal(fresh, eng.rows_plane)
+
+
 def test_model_is_picklable_and_lazy_attrs(M, tmp_path):
     import pickle
     c = load_golden("planted_w025")
