@@ -39,6 +39,10 @@ extern "C" {
 #define BMF_I8_CAND_TILE 128  /* rows of the "candidate" operand (MMA M)                  */
 #define BMF_I8_ROW_TILE 256   /* rows of the "data row" operand (MMA N)                   */
 #define BMF_I8_K_TILE 128     /* bytes of K per pipeline stage (= one 128B swizzle row)   */
+/* FP4 (tcgen05 kind::mxf4) kernels: candidate rows padded to 256, data rows to 240, K to 256 elements */
+#define BMF_F4_CAND_TILE 256
+#define BMF_F4_ROW_TILE 240
+#define BMF_F4_K_TILE 256     /* elements of K per stage = 128 bytes of packed E2M1         */
 
 typedef void* bmf_stream_t;
 
@@ -121,6 +125,31 @@ int bmf_expand_bits_pq(const uint64_t* x_bits, const uint64_t* c_bits, int64_t r
 int bmf_cover_score_i8_general(const int8_t* cand_plane, int64_t cand_pad, const int8_t* pq_plane, int64_t m,
                                int64_t ld, const int32_t* cand_pop, const int32_t* tp_old, const int32_t* fp_old,
                                double w_fp, double w_fn, int64_t* gain_p, int64_t* gain_n, bmf_stream_t stream);
+
+/* ---- FP4 tensor-core variants (tcgen05 kind::mxf4, packed E2M1 operands, unit block scales, FP32 accumulate) ----
+ * Twice the kind::i8 rate at half the operand bytes, and still EXACT for this path: the operand values are
+ * non-negative integers that E2M1 represents exactly (0, 1, 2, 3, 4, 6) and every partial sum is an integer
+ * below 2^24.  An f4 plane is row-major with `ld_bytes` bytes per row (a multiple of 128 covering ceil(ncols/2)),
+ * two 4-bit E2M1 codes per byte, element k in byte k/2, low nibble for even k; padding is code 0.
+ * bmf_expand_bits_f4: value codes `one`/`zero`/`masked` are E2M1 bit patterns (0 -> 0.0, 2 -> 1.0, 4 -> 2.0,
+ * 5 -> 3.0, 6 -> 4.0, 7 -> 6.0), otherwise as bmf_expand_bits_i8.  bmf_e2m1_code maps an integer value to its
+ * code or returns -1 when E2M1 cannot represent it (the caller then stays on the int8 kernels).
+ * bmf_gemm_f4_nt: c[i][j] = sum_k a[i][k]*b[j][k] as int32 (a rows multiple of 256, b rows multiple of 240).
+ * bmf_cover_score_f4: the zero-dominant encoding of bmf_cover_score_i8 (sign = +1) on f4 planes. */
+int bmf_e2m1_code(int32_t value);
+int bmf_expand_bits_f4(const uint64_t* bits, const uint64_t* mask_bits, int64_t rows, int64_t ncols, int64_t words,
+                       int32_t one, int32_t zero, int32_t masked, uint8_t* plane, int64_t rows_pad, int64_t ld_bytes,
+                       bmf_stream_t stream);
+int bmf_gemm_f4_nt(const uint8_t* a_plane, int64_t a_rows_pad, const uint8_t* b_plane, int64_t b_rows_pad,
+                   int64_t ld_bytes, int32_t* c, int64_t ldc, bmf_stream_t stream);
+int bmf_cover_score_f4(const uint8_t* cand_plane, int64_t cand_pad, const uint8_t* rows_plane, int64_t rows_pad,
+                       int64_t ld_bytes, const int32_t* cand_pop, int32_t bias_scale, int64_t* gain,
+                       bmf_stream_t stream);
+/* bmf_cover_apply on an f4 rows plane: newly covered entries of the used rows get the E2M1 code `covered_code` */
+int bmf_cover_apply_f4(const uint64_t* x_bits, uint64_t* c_bits, int64_t m, int64_t n, int64_t words,
+                       const uint64_t* basis_bits, uint8_t* alive, const int64_t* winner, int32_t* tp_old,
+                       int32_t* fp_old, int32_t wa, int32_t wb, uint8_t* rows_plane, int64_t ld_bytes,
+                       int32_t covered_code, uint64_t* u_bits, int64_t* totals, bmf_stream_t stream);
 
 /* argmax of Asso.py:94: first j (lowest index) among alive candidates whose score is
  * strictly greater than `best_score` and than every earlier score.

@@ -55,6 +55,33 @@ __global__ void expand_bits_i8_kernel(const uint64_t* __restrict__ bits, const u
   }
 }
 
+// 32 bits -> 32 E2M1 codes (16 bytes) per thread, one 128-bit store; element k of a row lives in byte k/2,
+// low nibble for even k
+__global__ void expand_bits_f4_kernel(const uint64_t* __restrict__ bits, const uint64_t* __restrict__ mask,
+                                      int64_t rows, int64_t ncols, int64_t words, uint32_t one, uint32_t zero,
+                                      uint32_t masked, uint8_t* __restrict__ plane, int64_t rows_pad, int64_t ld_bytes) {
+  const int64_t chunks = ld_bytes >> 4;
+  const int64_t total = rows_pad * chunks;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / chunks, ch = t - r * chunks;
+    const int64_t c0 = ch << 5;
+    uint32_t out[4] = {0, 0, 0, 0};
+    if (r < rows && c0 < ncols) {
+      const int64_t w = c0 >> 6;
+      const uint32_t b32 = (w < words) ? (uint32_t)(bits[r * words + w] >> (c0 & 63)) : 0u;
+      const uint32_t k32 = (mask != nullptr && w < words) ? (uint32_t)(mask[r * words + w] >> (c0 & 63)) : 0u;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        uint32_t v = 0;
+        if (c0 + i < ncols) v = ((k32 >> i) & 1u) ? masked : (((b32 >> i) & 1u) ? one : zero);
+        out[i >> 3] |= v << ((i & 7) * 4);
+      }
+    }
+    *reinterpret_cast<uint4*>(plane + r * ld_bytes + (ch << 4)) = make_uint4(out[0], out[1], out[2], out[3]);
+  }
+}
+
 // x bits + covered mask -> the interleaved P/Q operand of the general-weights tensor-core scorer:
 // per block of 128 data rows, 128 rows of P_i = x_i & ~c_i followed by 128 rows of Q_i = c_i (0/1 bytes);
 // plane row of data row i: (i / 128) * 256 + (i % 128) for P, + 128 for Q.  Padding rows / columns are 0.
@@ -367,6 +394,19 @@ cover_apply_kernel(const uint64_t* __restrict__ xb, uint64_t* __restrict__ cb, i
           int8_t* rowp = rows_plane + i * ld + p * 128;
           while (s0) { const int k = __ffsll((long long)s0) - 1; s0 &= s0 - 1; rowp[k] = (int8_t)covered_value; }
           while (s1) { const int k = __ffsll((long long)s1) - 1; s1 &= s1 - 1; rowp[64 + k] = (int8_t)covered_value; }
+        } else if (pq_layout == 2) {                                     // packed E2M1 plane: rewrite the nibble
+          uint8_t* rowp = reinterpret_cast<uint8_t*>(rows_plane) + i * ld + p * 64;
+          const uint32_t code = (uint32_t)covered_value & 0xFu;
+          while (s0) {
+            const int k = __ffsll((long long)s0) - 1; s0 &= s0 - 1;
+            uint8_t* bp = rowp + (k >> 1);
+            *bp = (k & 1) ? (uint8_t)((*bp & 0x0Fu) | (code << 4)) : (uint8_t)((*bp & 0xF0u) | code);
+          }
+          while (s1) {
+            const int k = __ffsll((long long)s1) - 1; s1 &= s1 - 1;
+            uint8_t* bp = rowp + 32 + (k >> 1);
+            *bp = (k & 1) ? (uint8_t)((*bp & 0x0Fu) | (code << 4)) : (uint8_t)((*bp & 0xF0u) | code);
+          }
         } else {                                                         // P plane: no longer uncovered; Q plane: covered
           int8_t* rowp = rows_plane + ((i >> 7) * 256 + (i & 127)) * ld + p * 128;
           int8_t* rowq = rowp + 128 * ld;
@@ -1072,7 +1112,8 @@ static int launch_cover_apply(const uint64_t* x_bits, uint64_t* c_bits, int64_t 
   BMF_REQUIRE(x_bits && c_bits && basis_bits && alive && winner && tp_old && fp_old && u_bits && totals,
               "bmf_cover_apply: null pointer");
   BMF_REQUIRE(m > 0 && n > 0 && words % 2 == 0 && words * 64 >= n, "bmf_cover_apply: bad shape");
-  BMF_REQUIRE(rows_plane == nullptr || (ld % 128 == 0 && ld >= words * 64), "bmf_cover_apply: ld must cover words*64");
+  BMF_REQUIRE(rows_plane == nullptr || (ld % 128 == 0 && ld * (pq_layout == 2 ? 2 : 1) >= words * 64),
+              "bmf_cover_apply: ld must cover words*64");
   int64_t blocks = ceil_div(m, 8);
   if (blocks > row_stream_grid()) blocks = row_stream_grid();
   cover_apply_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
@@ -1099,6 +1140,45 @@ extern "C" int bmf_cover_apply_general(const uint64_t* x_bits, uint64_t* c_bits,
   BMF_REQUIRE(pq_plane != nullptr, "bmf_cover_apply_general: null pq_plane");
   return launch_cover_apply(x_bits, c_bits, m, n, words, basis_bits, alive, winner, tp_old, fp_old, 0, 0, w_fp,
                             w_fn, pq_plane, ld, 0, 1, u_bits, totals, stream);
+}
+
+extern "C" int bmf_cover_apply_f4(const uint64_t* x_bits, uint64_t* c_bits, int64_t m, int64_t n, int64_t words,
+                                  const uint64_t* basis_bits, uint8_t* alive, const int64_t* winner, int32_t* tp_old,
+                                  int32_t* fp_old, int32_t wa, int32_t wb, uint8_t* rows_plane, int64_t ld_bytes,
+                                  int32_t covered_code, uint64_t* u_bits, int64_t* totals, bmf_stream_t stream) {
+  BMF_REQUIRE(rows_plane != nullptr && covered_code >= 0 && covered_code <= 7, "bmf_cover_apply_f4: bad plane / code");
+  BMF_REQUIRE((wa | wb) != 0, "bmf_cover_apply_f4: integer weights only");
+  return launch_cover_apply(x_bits, c_bits, m, n, words, basis_bits, alive, winner, tp_old, fp_old, wa, wb, 0.0, 0.0,
+                            reinterpret_cast<int8_t*>(rows_plane), ld_bytes, covered_code, 2, u_bits, totals, stream);
+}
+
+extern "C" int bmf_e2m1_code(int32_t value) {
+  switch (value) {
+    case 0: return 0;
+    case 1: return 2;
+    case 2: return 4;
+    case 3: return 5;
+    case 4: return 6;
+    case 6: return 7;
+    default: return -1;
+  }
+}
+
+extern "C" int bmf_expand_bits_f4(const uint64_t* bits, const uint64_t* mask_bits, int64_t rows, int64_t ncols,
+                                  int64_t words, int32_t one, int32_t zero, int32_t masked, uint8_t* plane,
+                                  int64_t rows_pad, int64_t ld_bytes, bmf_stream_t stream) {
+  BMF_REQUIRE(bits && plane, "bmf_expand_bits_f4: null pointer");
+  BMF_REQUIRE(ld_bytes % 128 == 0 && ld_bytes * 2 >= ncols && rows_pad >= rows && rows >= 0, "bmf_expand_bits_f4: bad ld / rows_pad");
+  BMF_REQUIRE(((one | zero | masked) & ~7) == 0, "bmf_expand_bits_f4: codes must be non-negative E2M1 bit patterns (0..7)");
+  if (rows_pad == 0) return 0;
+  const int64_t total = rows_pad * (ld_bytes >> 4);
+  int64_t blocks = ceil_div(total, 256);
+  if (blocks > (int64_t)num_sms() * 64) blocks = (int64_t)num_sms() * 64;
+  expand_bits_f4_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(bits, mask_bits, rows, ncols, words, (uint32_t)one,
+                                                                       (uint32_t)zero, (uint32_t)masked, plane, rows_pad,
+                                                                       ld_bytes);
+  BMF_LAUNCH_CHECK("bmf_expand_bits_f4");
+  return 0;
 }
 
 extern "C" int bmf_expand_bits_pq(const uint64_t* x_bits, const uint64_t* c_bits, int64_t rows, int64_t ncols,

@@ -600,6 +600,241 @@ static int launch_gemm_2sm(const int8_t* a, int64_t a_rows, const int8_t* b, int
 }
 }  // namespace sm2
 
+
+// =================================================================================================
+// FP4 variant of the pair kernel: tcgen05.mma kind::mxf4 (packed E2M1 operands, block-32 UE8M0 scale factors,
+// FP32 accumulators) runs at TWICE the kind::i8 rate and moves half the operand bytes.  The operands of this path
+// are tiny non-negative integers -- candidate rows {0,1}, data rows {0, wa, wa+wb} -- which E2M1 represents exactly
+// ({0, .5, 1, 1.5, 2, 3, 4, 6}); every product is an integer <= 6 and every partial sum an integer < 2^24, so the
+// FP32 accumulation is EXACT and the epilogue converts back to the same int32 the kind::i8 kernel produces
+// (tests compare the two bit for bit, also at the full Netflix-shaped size).  All scale factors are 1.0: the 32 TMEM
+// columns behind the accumulators are filled once with the UE8M0 byte 0x7F, so any scale-factor layout reads 1.0.
+// Tile: 256 candidates x 240 data rows (two 240-column FP32 accumulators + 32 scale columns = 512 TMEM columns),
+// K = 256 elements (128 bytes) per stage, four K=64 MMAs per stage.
+// =================================================================================================
+namespace f4 {
+using sm2::cluster_ctarank;
+using sm2::cluster_sync_all;
+using sm2::tma_load_2d_2sm;
+using sm2::tcgen05_commit_2sm;
+using sm2::mbar_arrive_leader;
+using sm2::PEER_MASK;
+constexpr int BM4 = 256, HALFM = 128;    // candidates per pair tile / per CTA
+constexpr int BN4 = BMF_F4_ROW_TILE;     // 240 data rows per pair tile
+constexpr int HALFN = BN4 / 2;           // 120 per CTA
+constexpr int STAGES4 = 6;
+constexpr int A_OP = HALFM * BK;         // 16 KB
+constexpr int B_OP = HALFN * BK;         // 15 KB
+constexpr int STAGE_BYTES4 = A_OP + B_OP;   // 31 KB, a multiple of 1024 (swizzle atom alignment)
+constexpr int SMEM_BYTES4 = STAGES4 * STAGE_BYTES4 + 1024 + 256 + ROWSTATE_BYTES;
+constexpr int SF_COL = 2 * BN4;          // scale-factor columns [480, 512)
+constexpr uint32_t SF_ONE = 0x7F7F7F7Fu; // UE8M0 1.0 in every byte
+// cute::UMMA::InstrDescriptorBlockScaled: a/b format E2M1 (MXF4Format 1) at [7,10)/[10,13), K-major both,
+// N>>3 at [17,23), scale format UE8M0 (1) at bit 23, M>>4 at [24,29), K = 64 (bit 31 = 0), scale-factor ids 0
+constexpr uint32_t IDESC_F4 = (1u << 7) | (1u << 10) | ((uint32_t)(BN4 >> 3) << 17) | (1u << 23) |
+                              ((uint32_t)(BM4 >> 4) << 24);
+
+__device__ __forceinline__ void tcgen05_mma_f4_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                   uint32_t accumulate, uint32_t sfa, uint32_t sfb) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(sfa), "r"(sfb)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32_x8(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(v)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32_x8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ int f32_bits_to_int(uint32_t bits) { return __float2int_rn(__uint_as_float(bits)); }
+
+// One FP32 accumulator tile (this thread's TMEM lane = candidate `row`, 240 columns) through the fused epilogue.
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile_f4(uint32_t taddr, int64_t row, int nt, const EpiArgs& ea) {
+  const int bias = (EPI == EPI_GAIN && ea.cand_pop != nullptr) ? ea.bias_scale * ea.cand_pop[row] : 0;
+  long long relu_sum = 0;
+#pragma unroll 1
+  for (int c = 0; c < BN4 / 16; ++c) {
+    uint32_t lo[8], hi[8];
+    tmem_ld_32x32_x8(taddr + (uint32_t)(c * 16), lo);
+    tmem_ld_32x32_x8(taddr + (uint32_t)(c * 16 + 8), hi);
+    tmem_ld_wait();
+    if (EPI == EPI_GAIN) {
+      int part = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) part += max(f32_bits_to_int(lo[q]) - bias, 0) + max(f32_bits_to_int(hi[q]) - bias, 0);
+      relu_sum += part;
+    } else {
+      int4* dst = reinterpret_cast<int4*>(ea.C + row * ea.ldc + (int64_t)nt * BN4 + c * 16);
+      dst[0] = make_int4(f32_bits_to_int(lo[0]), f32_bits_to_int(lo[1]), f32_bits_to_int(lo[2]), f32_bits_to_int(lo[3]));
+      dst[1] = make_int4(f32_bits_to_int(lo[4]), f32_bits_to_int(lo[5]), f32_bits_to_int(lo[6]), f32_bits_to_int(lo[7]));
+      dst[2] = make_int4(f32_bits_to_int(hi[0]), f32_bits_to_int(hi[1]), f32_bits_to_int(hi[2]), f32_bits_to_int(hi[3]));
+      dst[3] = make_int4(f32_bits_to_int(hi[4]), f32_bits_to_int(hi[5]), f32_bits_to_int(hi[6]), f32_bits_to_int(hi[7]));
+    }
+  }
+  if (EPI == EPI_GAIN && relu_sum != 0) atomicAdd(ea.gain + row, (unsigned long long)relu_sum);
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_f4_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   int mt_total, int nt_total, int kb_total, int group_m, const EpiArgs ea) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES4 * STAGE_BYTES4);
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES4 + 4);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES4 + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES4 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES4 + 2 + a); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int64_t pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int64_t total_tiles = (int64_t)mt_total * nt_total;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES4; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_base_slot);
+  if (warp >= 2) {                                        // unit scale factors: all 128 lanes x columns [480, 512)
+    const uint32_t sf_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)SF_COL;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmem_st_32x32_x8(sf_addr + (uint32_t)(c * 8), SF_ONE);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();                                     // scale factors of BOTH CTAs are in place before any MMA
+  tcgen05_fence_after();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = pair; t < total_tiles; t += num_pairs) {
+        int mt, nt;
+        tile_coords(t, mt_total, nt_total, group_m, mt, nt);
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t leader_full = full_bar(stage) & PEER_MASK;
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES4);
+          const uint32_t a_dst = smem_base + stage * STAGE_BYTES4;
+          tma_load_2d_2sm(a_dst, &tmap_a, leader_full, kb * BK, mt * BM4 + (int)rank * HALFM, ea.policy_a);
+          tma_load_2d_2sm(a_dst + A_OP, &tmap_b, leader_full, kb * BK, nt * BN4 + (int)rank * HALFN, ea.policy_b);
+          if (++stage == STAGES4) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint32_t sfa = tmem_base + (uint32_t)SF_COL, sfb = tmem_base + (uint32_t)SF_COL + 8u;
+      for (int64_t t = pair; t < total_tiles; t += num_pairs) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN4);
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_base + stage * STAGE_BYTES4;
+          const uint64_t da = make_smem_desc(a_addr), db = make_smem_desc(a_addr + A_OP);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)                     // K = 64 elements = 32 bytes per MMA
+            tcgen05_mma_f4_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC_F4,
+                               (uint32_t)((kb | k) != 0), sfa, sfb);
+          tcgen05_commit_2sm(empty_bar(stage));
+          if (++stage == STAGES4) { stage = 0; phase ^= 1u; }
+        }
+        tcgen05_commit_2sm(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t t = pair; t < total_tiles; t += num_pairs) {
+      int mt, nt;
+      tile_coords(t, mt_total, nt_total, group_m, mt, nt);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN4);
+      const int64_t row = (int64_t)mt * BM4 + (int64_t)rank * HALFM + quad * 32 + lane;
+      epilogue_tile_f4<EPI>(taddr, row, nt, ea);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+template <int EPI>
+static int launch_gemm_f4(const uint8_t* a, int64_t a_rows, const uint8_t* b, int64_t b_rows, int64_t ld_bytes,
+                          const EpiArgs& ea_in, cudaStream_t stream) {
+  CUtensorMap ma, mb;
+  int rc = make_plane_map(&ma, reinterpret_cast<const int8_t*>(a), a_rows, ld_bytes, HALFM);
+  if (rc) return rc;
+  rc = make_plane_map(&mb, reinterpret_cast<const int8_t*>(b), b_rows, ld_bytes, HALFN);
+  if (rc) return rc;
+  static bool attr_set[3] = {false, false, false};
+  if (!attr_set[EPI]) {
+    rc = check_cuda(cudaFuncSetAttribute(gemm_f4_2sm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES4),
+                    "cudaFuncSetAttribute(gemm_f4_2sm_kernel)");
+    if (rc) return rc;
+    attr_set[EPI] = true;
+  }
+  EpiArgs ea = ea_in;
+  ea.policy_a = L2_EVICT_NORMAL;
+  ea.policy_b = L2_EVICT_NORMAL;
+  const int mt = (int)(a_rows / BM4), nt = (int)(b_rows / BN4), kb = (int)(ld_bytes / BK);
+  const int64_t tiles = (int64_t)mt * nt;
+  const int pairs_max = num_sms() / 2;
+  const int pairs = (int)(tiles < pairs_max ? tiles : pairs_max);
+  int group_m = 16;
+  if (const char* e = getenv("BMF_GROUP_M2")) { int v = atoi(e); if (v >= 1 && v <= 64) group_m = v; }
+  gemm_f4_2sm_kernel<EPI><<<2 * pairs, NUM_THREADS, SMEM_BYTES4, stream>>>(ma, mb, mt, nt, kb, group_m, ea);
+  return check_cuda(cudaGetLastError(), "gemm_f4_2sm_kernel launch");
+}
+}  // namespace f4
+
 // variant: 0 = auto (2-SM when the candidate rows are a multiple of 256), 1 = 1-SM, 2 = 2-SM
 template <int EPI>
 static int dispatch_gemm(int variant, const int8_t* a, int64_t a_rows, const int8_t* b, int64_t b_rows, int64_t ld,
@@ -695,4 +930,36 @@ extern "C" int bmf_cover_score_i8_general(const int8_t* cand_plane, int64_t cand
   ea.neg_w_fp = -w_fp;
   ea.w_fn = w_fn;
   return tc::dispatch_gemm<tc::EPI_GAIN2>(0, cand_plane, cand_pad, pq_plane, plane_rows, ld, ea, as_stream(stream));
+}
+
+// ---- FP4 (kind::mxf4) entry points -------------------------------------------------------------------
+extern "C" int bmf_gemm_f4_nt(const uint8_t* a_plane, int64_t a_rows_pad, const uint8_t* b_plane, int64_t b_rows_pad,
+                              int64_t ld_bytes, int32_t* c, int64_t ldc, bmf_stream_t stream) {
+  BMF_REQUIRE(a_plane && b_plane && c, "bmf_gemm_f4_nt: null pointer");
+  BMF_REQUIRE(a_rows_pad > 0 && a_rows_pad % tc::f4::BM4 == 0, "bmf_gemm_f4_nt: a rows must be a positive multiple of 256");
+  BMF_REQUIRE(b_rows_pad > 0 && b_rows_pad % tc::f4::BN4 == 0, "bmf_gemm_f4_nt: b rows must be a positive multiple of 240");
+  BMF_REQUIRE(ld_bytes > 0 && ld_bytes % tc::BK == 0, "bmf_gemm_f4_nt: ld_bytes must be a positive multiple of 128");
+  BMF_REQUIRE(ldc >= b_rows_pad && ldc % 4 == 0, "bmf_gemm_f4_nt: ldc must cover b rows and be a multiple of 4");
+  tc::EpiArgs ea = {};
+  ea.C = c;
+  ea.ldc = ldc;
+  return tc::f4::launch_gemm_f4<tc::EPI_STORE>(a_plane, a_rows_pad, b_plane, b_rows_pad, ld_bytes, ea, as_stream(stream));
+}
+
+extern "C" int bmf_cover_score_f4(const uint8_t* cand_plane, int64_t cand_pad, const uint8_t* rows_plane,
+                                  int64_t rows_pad, int64_t ld_bytes, const int32_t* cand_pop, int32_t bias_scale,
+                                  int64_t* gain, bmf_stream_t stream) {
+  BMF_REQUIRE(cand_plane && rows_plane && gain, "bmf_cover_score_f4: null pointer");
+  BMF_REQUIRE(cand_pad > 0 && cand_pad % tc::f4::BM4 == 0, "bmf_cover_score_f4: cand_pad must be a positive multiple of 256");
+  BMF_REQUIRE(rows_pad > 0 && rows_pad % tc::f4::BN4 == 0, "bmf_cover_score_f4: rows_pad must be a positive multiple of 240");
+  BMF_REQUIRE(ld_bytes > 0 && ld_bytes % tc::BK == 0, "bmf_cover_score_f4: ld_bytes must be a positive multiple of 128");
+  BMF_REQUIRE(cand_pop != nullptr || bias_scale == 0, "bmf_cover_score_f4: a bias needs cand_pop");
+  int rc = check_cuda(cudaMemsetAsync(gain, 0, sizeof(int64_t) * cand_pad, as_stream(stream)), "bmf_cover_score_f4");
+  if (rc) return rc;
+  tc::EpiArgs ea = {};
+  ea.sign = 1;
+  ea.cand_pop = cand_pop;
+  ea.bias_scale = bias_scale;
+  ea.gain = reinterpret_cast<unsigned long long*>(gain);
+  return tc::f4::launch_gemm_f4<tc::EPI_GAIN>(cand_plane, cand_pad, rows_plane, rows_pad, ld_bytes, ea, as_stream(stream));
 }

@@ -112,9 +112,15 @@ class CoverEngine:
         iw = integer_weights(self.w_fp, self.w_fn)
         self.wa, self.wb, self.shift = iw if iw else (0, 0, 0)
         self.integer_mode = iw is not None
+        # scorer: 'auto' / 'tcgen05' pick the fastest exact tensor-core path (FP4 when the operand values are E2M1
+        # numbers, else int8); 'tcgen05_i8' / 'tcgen05_f4' force one; 'popc' is the bit-packed AND+POPC variant
+        operand = os.environ.get("BMF_OPERAND", "auto")
+        if scorer in ("tcgen05_i8", "tcgen05_f4"):
+            operand, scorer = scorer[-2:], "tcgen05"
         if scorer == "auto":
             scorer = "tcgen05"
-        assert scorer in ("tcgen05", "popc") and assoc in ("auto", "tcgen05", "popc")
+        assert scorer in ("tcgen05", "popc") and assoc in ("auto", "tcgen05", "tcgen05_i8", "tcgen05_f4", "popc")
+        assert operand in ("auto", "i8", "f4")
         self.scorer = scorer
         # operand encoding of the rows plane (see include/pybmf_b200.h):
         #   integer mode, all give D = wb*P - wa*N exactly:
@@ -131,11 +137,25 @@ class CoverEngine:
         self.encoding = enc
         self.plane_sign = -1 if enc == "signed-" else 1
         self.cand_pop = None
+        # FP4 (tcgen05 kind::mxf4, twice the int8 rate): exact when the plane values 0 / wa / wa+wb are E2M1 numbers
+        lib = _native.load()
+        f4_ok = self.integer_mode and enc == "zero" and lib.bmf_e2m1_code(self.wa) >= 0 and lib.bmf_e2m1_code(self.wa + self.wb) >= 0
+        if operand == "f4" and scorer == "tcgen05" and not f4_ok:
+            raise ValueError("the FP4 scorer needs integer weights whose values wa=%d and wa+wb=%d are E2M1 numbers "
+                             "(0, 1, 2, 3, 4, 6)" % (self.wa, self.wa + self.wb))
+        self.operand = "f4" if (scorer == "tcgen05" and f4_ok and operand in ("auto", "f4")) else "i8"
+        if assoc in ("tcgen05_i8", "tcgen05_f4"):
+            self.assoc_operand, assoc = assoc[-2:], "tcgen05"
+        else:
+            self.assoc_operand = "i8" if operand == "i8" else "f4"
+        if max(self.r1 - self.r0, 1) >= (1 << 24):             # co-occurrence counts must stay below 2^24 for FP32
+            self.assoc_operand = "i8"
         self.assoc_kind = "tcgen05" if assoc == "auto" else assoc
 
         self.words = device.words_for(self.n)
         self.words_m = device.words_for(max(self.m_loc, 1))
-        self.ld = device.round_up(self.n, 128)                  # K extent of the cover planes
+        self.ld = device.round_up(self.n, 128)                  # K extent of the int8 cover planes (bytes)
+        self.ld4 = device.round_up(self.n, 256) // 2            # ... of the packed FP4 planes (bytes)
         m_alloc = max(self.m_loc, 1)
         self._ip, self._ix = device.upload_csr(Xl)
         self.x_bits = device.pack_csr(self._ip, self._ix, self.m_loc, self.n)
@@ -191,27 +211,41 @@ class CoverEngine:
     def _build_basis(self, tau: float):
         n, m_loc = self.n, self.m_loc
         n_pad = device.round_up(n, 256)
-        cnt = device.zeros((n_pad, n_pad), torch.int32)
+        ldc = max(n_pad, device.round_up(n, 240))              # the FP4 kernel's data-row tiles are 240 wide
+        cnt = device.zeros((n_pad, ldc), torch.int32)
         if m_loc > 0:
             xt_bits = device.pack_csr(self._ip, self._ix, m_loc, n, transposed=True)
-            if self.assoc_kind == "tcgen05":
+            if self.assoc_kind == "tcgen05" and self.assoc_operand == "f4":
+                # X^T as packed E2M1 0/1; A operand = rows padded to 256, B operand = the same plane padded to 240
+                ldk = device.round_up(m_loc, 256) // 2
+                xt_plane = device.empty((max(n_pad, ldc), ldk), torch.uint8)
+                _native.call("bmf_expand_bits_f4", xt_bits, None, n, m_loc, xt_bits.shape[1], 2, 0, 0, xt_plane,
+                             xt_plane.shape[0], ldk)
+                _native.call("bmf_gemm_f4_nt", xt_plane, n_pad, xt_plane, device.round_up(n, 240), ldk, cnt, ldc)
+                del xt_plane
+            elif self.assoc_kind == "tcgen05":
                 xt_plane = device.expand_bits_i8(xt_bits, n, m_loc, 1, 0, 256)
-                _native.call("bmf_assoc_counts_i8", xt_plane, n, n_pad, xt_plane.shape[1], cnt, n_pad)
+                _native.call("bmf_assoc_counts_i8", xt_plane, n, n_pad, xt_plane.shape[1], cnt, ldc)
                 del xt_plane
             else:
-                _native.call("bmf_assoc_counts_popc", xt_bits, n, xt_bits.shape[1], cnt, n_pad)
+                _native.call("bmf_assoc_counts_popc", xt_bits, n, xt_bits.shape[1], cnt, ldc)
             self.launches += 3
             del xt_bits
         self.trace.mark("assoc_counts")
         all_reduce_sum(cnt)
         self.trace.mark("assoc_allreduce")
         self.cnt = cnt
-        if self.scorer == "tcgen05":
+        if self.scorer == "tcgen05" and self.operand == "i8":
             self.cand_plane = device.zeros((self.cand_pad, self.ld), torch.int8)
         self.cand_pop = device.zeros((self.cand_pad,), torch.int32)
-        _native.call("bmf_basis_threshold", cnt, n_pad, n, float(tau), self.basis_bits, self.words,
+        _native.call("bmf_basis_threshold", cnt, ldc, n, float(tau), self.basis_bits, self.words,
                      self.cand_plane, self.ld, self.alive, self.cand_pop)
         self.launches += 1
+        if self.scorer == "tcgen05" and self.operand == "f4":   # candidate rows as packed E2M1 0/1
+            self.cand_plane = device.empty((self.cand_pad, self.ld4), torch.uint8)
+            _native.call("bmf_expand_bits_f4", self.basis_bits, None, n, n, self.words, 2, 0, 0, self.cand_plane,
+                         self.cand_pad, self.ld4)
+            self.launches += 1
         if self.scorer == "tcgen05":
             self._rebuild_rows_plane()
         self.trace.mark("basis_planes")
@@ -227,6 +261,15 @@ class CoverEngine:
             self.launches += 1
             return
         one, zero, covered = self._plane_values()
+        if self.operand == "f4":
+            lib = _native.load()
+            rows_pad = device.round_up(max(self.m_loc, 1), 240)
+            if self.rows_plane is None:
+                self.rows_plane = device.empty((rows_pad, self.ld4), torch.uint8)
+            _native.call("bmf_expand_bits_f4", self.x_bits, self.c_bits, self.m_loc, self.n, self.words,
+                         lib.bmf_e2m1_code(one), 0, lib.bmf_e2m1_code(covered), self.rows_plane, rows_pad, self.ld4)
+            self.launches += 1
+            return
         self.rows_plane = device.expand_bits_i8(self.x_bits, self.m_loc, self.n, one, zero, 256,
                                                 mask=self.c_bits, out=self.rows_plane, masked=covered)
         self.launches += 1
@@ -262,6 +305,9 @@ class CoverEngine:
             _native.call("bmf_cover_score_i8_general", self.cand_plane, self.cand_pad, self.rows_plane, self.m_loc,
                          self.ld, self.cand_pop, self.tp_old, self.fp_old, self.w_fp, self.w_fn, self.gain_p,
                          self.gain_n)
+        elif self.scorer == "tcgen05" and self.operand == "f4":
+            _native.call("bmf_cover_score_f4", self.cand_plane, self.cand_pad, self.rows_plane,
+                         self.rows_plane.shape[0], self.ld4, self.cand_pop, self.wa, self.gain_p)
         elif self.scorer == "tcgen05":
             _native.call("bmf_cover_score_i8", self.cand_plane, self.cand_pad, self.rows_plane,
                          self.rows_plane.shape[0], self.ld, self.plane_sign,
@@ -289,6 +335,10 @@ class CoverEngine:
             _native.call("bmf_cover_apply_general", self.x_bits, self.c_bits, self.m_loc, self.n, self.words,
                          self.basis_bits, self.alive, self.record, self.tp_old, self.fp_old, self.w_fp, self.w_fn,
                          self.rows_plane, self.ld, u_bits, self.record[2:5])
+        elif self.m_loc > 0 and self.scorer == "tcgen05" and self.operand == "f4":
+            _native.call("bmf_cover_apply_f4", self.x_bits, self.c_bits, self.m_loc, self.n, self.words,
+                         self.basis_bits, self.alive, self.record, self.tp_old, self.fp_old, self.wa, self.wb,
+                         self.rows_plane, self.ld4, _native.load().bmf_e2m1_code(self.wa), u_bits, self.record[2:5])
         elif self.m_loc > 0:
             _native.call("bmf_cover_apply", self.x_bits, self.c_bits, self.m_loc, self.n, self.words, self.basis_bits,
                          self.alive, self.record, self.tp_old, self.fp_old, self.wa, self.wb, self.w_fp, self.w_fn,

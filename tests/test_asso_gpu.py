@@ -48,7 +48,8 @@ def _check_logs(df, g, exact_score=True):
 
 
 @pytest.mark.parametrize("name", EXACT_CASES)
-@pytest.mark.parametrize("scorer,assoc", [("tcgen05", "tcgen05"), ("popc", "popc")])
+@pytest.mark.parametrize("scorer,assoc", [("tcgen05", "tcgen05"), ("tcgen05_f4", "tcgen05_f4"), ("tcgen05_i8", "tcgen05_i8"),
+                                          ("popc", "popc")])
 def test_asso_matches_reference_bit_exact(M, name, scorer, assoc):
     c = load_golden(name)
     g = c["g"]
@@ -293,11 +294,25 @@ def test_c4_full_size_properties(M):
     from pybmf_b200 import _native, device, synth
     from pybmf_b200.engine import CoverEngine
     X = synth.config_c4()
-    eng = CoverEngine(X, 0.5, 0.5, scorer="tcgen05")
+    # FP4 (kind::mxf4) engine first: association counts, basis and first-step gains must equal the int8 engine's
+    eng4 = CoverEngine(X, 0.5, 0.5, scorer="tcgen05_f4", assoc="tcgen05_f4")
+    assert eng4.operand == "f4" and eng4.assoc_operand == "f4"
+    nb4 = eng4.build_basis(0.5)
+    eng4.score_all()
+    g_f4, cnt_f4, basis_f4 = eng4.gain_p.clone(), eng4.cnt[: eng4.n, : eng4.n].clone(), eng4.basis_bits.clone()
+    w4, s4, used4, sp4, sn4 = eng4.select_and_apply(0.0)
+    eng4.score_all()
+    g_f4_step2 = eng4.gain_p.clone()
+    del eng4
+    torch.cuda.empty_cache()
+    eng = CoverEngine(X, 0.5, 0.5, scorer="tcgen05_i8", assoc="tcgen05_i8")
+    assert eng.operand == "i8" and eng.assoc_operand == "i8"
     nb = eng.build_basis(0.5)
-    assert nb == int(eng.alive.sum().item()) and nb > 17000
+    assert nb == int(eng.alive.sum().item()) and nb > 17000 and nb == nb4
+    assert torch.equal(cnt_f4, eng.cnt[: eng.n, : eng.n]) and torch.equal(basis_f4, eng.basis_bits)
     eng.score_all()
     g_pair = eng.gain_p.clone()
+    assert torch.equal(g_f4, g_pair)                                # kind::mxf4 == kind::i8, bit for bit
     os.environ["BMF_GEMM_VARIANT"] = "1"
     try:
         eng.score_all()
@@ -321,6 +336,7 @@ def test_c4_full_size_properties(M):
     # (b) apply and cross-check the state with independent kernels
     winner, score, used, sp_, sn_ = eng.select_and_apply(0.0)
     assert winner >= 0 and used > 0 and score == 0.5 * int(g_pair[winner].item())
+    assert (winner, score, used, sp_, sn_) == (w4, s4, used4, sp4, sn4)
     counts = device.zeros((3,), torch.int64)
     rtp = device.zeros((m,), torch.int32)
     rfp = device.zeros((m,), torch.int32)
@@ -341,6 +357,7 @@ def test_c4_full_size_properties(M):
                  eng.tp_old, eng.fp_old, 1, 1, 0.5, 0.5, gp, None)
     live = eng.alive.bool()
     assert torch.equal(gp[: eng.n][live], eng.gain_p[: eng.n][live])
+    assert torch.equal(g_f4_step2[: eng.n][live], eng.gain_p[: eng.n][live])   # FP4 plane updated in place == int8
 
 
 def test_c4_slice_general_weights_tensor_cores_equal_popcount(M):

@@ -274,6 +274,92 @@ def test_cover_apply_general_updates_pq_plane(nat):
     assert list(tot.cpu().numpy()) == [int(u.sum()), int(P[u, 0].sum()), int(N[u, 0].sum())]
 
 
+E2M1_CODE = {0: 0, 1: 2, 2: 4, 3: 5, 4: 6, 6: 7}
+
+
+def _pack_f4(values, ld_bytes):
+    """integer matrix -> packed E2M1 plane [rows, ld_bytes]: element k in byte k/2, low nibble for even k"""
+    rows, cols = values.shape
+    codes = np.zeros((rows, ld_bytes * 2), np.uint8)
+    lut = np.zeros(8, np.uint8)
+    for v, c in E2M1_CODE.items():
+        lut[v] = c
+    codes[:, :cols] = lut[values]
+    return (codes[:, 0::2] | (codes[:, 1::2] << 4)).astype(np.uint8)
+
+
+@pytest.mark.parametrize("ma,nb,k", [(256, 240, 256), (256, 480, 1024), (512, 240, 2304), (768, 720, 17920)])
+def test_gemm_f4_tcgen05_exact(nat, ma, nb, k):
+    """tcgen05 kind::mxf4 with unit block scales on small-integer operands is EXACT (FP32 accumulate of integers)"""
+    _native, device = nat
+    rng = np.random.RandomState(ma + nb + k)
+    A = (rng.rand(ma, k) < 0.4).astype(np.int64)                      # candidate-like operand {0,1}
+    vals = np.array([0, 1, 2, 3, 4, 6])
+    B = vals[rng.randint(0, 6, size=(nb, k))]
+    B[: nb // 4] = 6                                                  # dense rows: sums up to 6*0.4*k
+    assert _native.load().bmf_e2m1_code(5) == -1 and _native.load().bmf_e2m1_code(6) == 7
+    ld_bytes = k // 2
+    c = device.zeros((ma, nb), torch.int32) - 1
+    _native.call("bmf_gemm_f4_nt", _dev(_pack_f4(A, ld_bytes)), ma, _dev(_pack_f4(B, ld_bytes)), nb, ld_bytes, c, nb)
+    want = A @ B.T
+    assert want.max() > 4000 or k < 2000
+    assert np.array_equal(c.cpu().numpy().astype(np.int64), want)
+
+
+@pytest.mark.parametrize("rows,ncols", [(5, 70), (300, 500), (241, 257)])
+def test_expand_bits_f4(nat, rows, ncols):
+    _native, device = nat
+    rng = np.random.RandomState(rows + ncols)
+    A = _rand01(rng, rows, ncols, 0.4)
+    K = _rand01(rng, rows, ncols, 0.3)
+    ld_bytes = device.round_up(ncols, 256) // 2
+    rows_pad = device.round_up(rows, 240)
+    plane = device.empty((rows_pad, ld_bytes), torch.uint8)
+    _native.call("bmf_expand_bits_f4", _dev(device.dense_to_words(A)), _dev(device.dense_to_words(K)), rows, ncols,
+                 device.words_for(ncols), 4, 0, 2, plane, rows_pad, ld_bytes)
+    vals = np.zeros((rows_pad, ncols), np.int64)
+    vals[:rows] = np.where(K == 1, 1, np.where(A == 1, 2, 0))
+    assert np.array_equal(plane.cpu().numpy(), _pack_f4(vals, ld_bytes))
+
+
+@pytest.mark.parametrize("m,n,w", [(70, 50, (0.5, 0.5)), (300, 200, (0.25, 0.75)), (1000, 500, (0.75, 0.25)),
+                                   (5000, 2100, (0.5, 0.5))])
+def test_cover_score_f4_tcgen05(nat, m, n, w):
+    """FP4 scorer == integer gains, and the plane kept current by bmf_cover_apply_f4 == a fresh expansion"""
+    _native, device = nat
+    X, C, B, alive = _cover_inputs(m * 7 + n, m, n)
+    alive[:] = 1
+    wa, wb, _ = O.integer_weights(*w)
+    lib = _native.load()
+    c_one, c_cov = lib.bmf_e2m1_code(wa + wb), lib.bmf_e2m1_code(wa)
+    assert c_one >= 0 and c_cov >= 0
+    words = device.words_for(n)
+    ld_bytes = device.round_up(n, 256) // 2
+    rows_pad, cand_pad = device.round_up(m, 240), device.round_up(n, 256)
+    x_d, c_d, b_d = _dev(device.dense_to_words(X)), _dev(device.dense_to_words(C)), _dev(device.dense_to_words(B))
+    rows_plane = device.empty((rows_pad, ld_bytes), torch.uint8)
+    cand_plane = device.empty((cand_pad, ld_bytes), torch.uint8)
+    _native.call("bmf_expand_bits_f4", x_d, c_d, m, n, words, c_one, 0, c_cov, rows_plane, rows_pad, ld_bytes)
+    _native.call("bmf_expand_bits_f4", b_d, None, n, n, words, 2, 0, 0, cand_plane, cand_pad, ld_bytes)
+    pop = np.zeros(cand_pad, np.int32)
+    pop[:n] = B.sum(axis=1)
+    gain = device.zeros((cand_pad,), torch.int64) + 5
+    _native.call("bmf_cover_score_f4", cand_plane, cand_pad, rows_plane, rows_pad, ld_bytes, _dev(pop), wa, gain)
+    G = O.integer_gains(X, C, B, wa, wb)
+    got = gain.cpu().numpy()
+    assert np.array_equal(got[:n], G) and got[n:].sum() == 0
+    # apply the best candidate and compare the updated plane with a fresh expansion
+    j = int(np.argmax(G))
+    tpo, fpo, _ = O.confusion(X, C, axis=1)
+    ub = device.zeros((device.words_for(m),), torch.int64)
+    tot = device.zeros((3,), torch.int64)
+    _native.call("bmf_cover_apply_f4", x_d, c_d, m, n, words, b_d, _dev(alive), _dev(np.array([j], np.int64)),
+                 _dev(tpo.astype(np.int32)), _dev(fpo.astype(np.int32)), wa, wb, rows_plane, ld_bytes, c_cov, ub, tot)
+    fresh = device.empty((rows_pad, ld_bytes), torch.uint8)
+    _native.call("bmf_expand_bits_f4", x_d, c_d, m, n, words, c_one, 0, c_cov, fresh, rows_pad, ld_bytes)
+    assert torch.equal(fresh, rows_plane)
+
+
 def test_select_first_max(nat):
     _native, device = nat
     n = 3000
