@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbmf_b200.so")
 SOURCES = ["bmf_core.cu", "bmf_bits.cu", "bmf_tc.cu"]
 HEADERS = [os.path.join(CSRC, "bmf_common.cuh"), os.path.join(HERE, "..", "include", "pybmf_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+NVCC_FLAGS = os.environ.get("BMF_EXTRA_NVCC", "").split() + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
 

@@ -620,14 +620,21 @@ using sm2::tcgen05_commit_2sm;
 using sm2::mbar_arrive_leader;
 using sm2::PEER_MASK;
 constexpr int BM4 = 256, HALFM = 128;    // candidates per pair tile / per CTA
+#ifdef BMF_F4_PROBE_BN                   /* timing experiment only (accumulator 1 overlaps the scale columns) */
+constexpr int BN4 = BMF_F4_PROBE_BN;
+#else
 constexpr int BN4 = BMF_F4_ROW_TILE;     // 240 data rows per pair tile
+#endif
 constexpr int HALFN = BN4 / 2;           // 120 per CTA
-constexpr int STAGES4 = 6;
+#ifndef BMF_F4_STAGES
+#define BMF_F4_STAGES 7
+#endif
+constexpr int STAGES4 = BMF_F4_STAGES;
 constexpr int A_OP = HALFM * BK;         // 16 KB
 constexpr int B_OP = HALFN * BK;         // 15 KB
 constexpr int STAGE_BYTES4 = A_OP + B_OP;   // 31 KB, a multiple of 1024 (swizzle atom alignment)
-constexpr int SMEM_BYTES4 = STAGES4 * STAGE_BYTES4 + 1024 + 256 + ROWSTATE_BYTES;
-constexpr int SF_COL = 2 * BN4;          // scale-factor columns [480, 512)
+constexpr int SMEM_BYTES4 = STAGES4 * STAGE_BYTES4 + 1024 + 256;
+constexpr int SF_COL = 480;              // scale-factor columns [480, 512)
 constexpr uint32_t SF_ONE = 0x7F7F7F7Fu; // UE8M0 1.0 in every byte
 // cute::UMMA::InstrDescriptorBlockScaled: a/b format E2M1 (MXF4Format 1) at [7,10)/[10,13), K-major both,
 // N>>3 at [17,23), scale format UE8M0 (1) at bit 23, M>>4 at [24,29), K = 64 (bit 31 = 0), scale-factor ids 0
@@ -741,8 +748,16 @@ gemm_f4_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t leader_full = full_bar(stage) & PEER_MASK;
+#if defined(BMF_F4_TIMING_PROBE) && BMF_F4_TIMING_PROBE == 2   /* no operand traffic at all: MMA issue + pipe only */
+          if (leader) mbar_arrive(full_bar(stage));
+          if (++stage == STAGES4) { stage = 0; phase ^= 1u; }
+          continue;
+#endif
           if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES4);
           const uint32_t a_dst = smem_base + stage * STAGE_BYTES4;
+#ifdef BMF_F4_TIMING_PROBE   /* timing experiment only: every tile re-reads tile (0, 0) -> operands always hit L2 */
+          mt = 0; nt = 0;
+#endif
           tma_load_2d_2sm(a_dst, &tmap_a, leader_full, kb * BK, mt * BM4 + (int)rank * HALFM, ea.policy_a);
           tma_load_2d_2sm(a_dst + A_OP, &tmap_b, leader_full, kb * BK, nt * BN4 + (int)rank * HALFN, ea.policy_b);
           if (++stage == STAGES4) { stage = 0; phase ^= 1u; }
