@@ -440,6 +440,11 @@ def main():
     e2e = None
     if not args.no_e2e:
         k_e2e = min(max(args.steps, 1), k_fit)
+        try:                                                    # warm-up: first-use costs of the host side (pandas, scipy)
+            models.Asso(tau=tau, k=1, w_fp=w_fp, scorer=args.scorer).fit(
+                X, task="reconstruction", save_model=False, show_logs=False, show_result=False)
+        except TypeError:
+            pass
         barrier()
         t0 = time.perf_counter()
         mdl = models.Asso(tau=tau, k=k_e2e, w_fp=w_fp, scorer=args.scorer)

@@ -145,6 +145,18 @@ int bmf_gemm_f4_nt(const uint8_t* a_plane, int64_t a_rows_pad, const uint8_t* b_
 int bmf_cover_score_f4(const uint8_t* cand_plane, int64_t cand_pad, const uint8_t* rows_plane, int64_t rows_pad,
                        int64_t ld_bytes, const int32_t* cand_pop, int32_t bias_scale, int64_t* gain,
                        bmf_stream_t stream);
+/* general (non-dyadic) weights on the FP4 pipe: the interleaved P/Q operand of bmf_cover_score_i8_general as packed
+ * E2M1 0/1, in blocks of 120 data rows (plane row of data row i = (i/120)*240 + i%120 for P, +120 for Q;
+ * 2*ceil(m/120)*120 rows of ld_bytes), same outputs as bmf_cover_score_i8_general. */
+int bmf_expand_bits_pq_f4(const uint64_t* x_bits, const uint64_t* c_bits, int64_t rows, int64_t ncols, int64_t words,
+                          uint8_t* pq_plane, int64_t ld_bytes, bmf_stream_t stream);
+int bmf_cover_score_f4_general(const uint8_t* cand_plane, int64_t cand_pad, const uint8_t* pq_plane, int64_t m,
+                               int64_t ld_bytes, const int32_t* cand_pop, const int32_t* tp_old, const int32_t* fp_old,
+                               double w_fp, double w_fn, int64_t* gain_p, int64_t* gain_n, bmf_stream_t stream);
+int bmf_cover_apply_f4_general(const uint64_t* x_bits, uint64_t* c_bits, int64_t m, int64_t n, int64_t words,
+                               const uint64_t* basis_bits, uint8_t* alive, const int64_t* winner, int32_t* tp_old,
+                               int32_t* fp_old, double w_fp, double w_fn, uint8_t* pq_plane, int64_t ld_bytes,
+                               uint64_t* u_bits, int64_t* totals, bmf_stream_t stream);
 /* bmf_cover_apply on an f4 rows plane: newly covered entries of the used rows get the E2M1 code `covered_code` */
 int bmf_cover_apply_f4(const uint64_t* x_bits, uint64_t* c_bits, int64_t m, int64_t n, int64_t words,
                        const uint64_t* basis_bits, uint8_t* alive, const int64_t* winner, int32_t* tp_old,

@@ -38,6 +38,9 @@ SIGNATURES = {
     "bmf_gemm_f4_nt": [_p, _i64, _p, _i64, _i64, _p, _i64, _p],
     "bmf_cover_score_f4": [_p, _i64, _p, _i64, _i64, _p, _i32, _p, _p],
     "bmf_cover_apply_f4": [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i32, _i32, _p, _i64, _i32, _p, _p, _p],
+    "bmf_expand_bits_pq_f4": [_p, _p, _i64, _i64, _i64, _p, _i64, _p],
+    "bmf_cover_score_f4_general": [_p, _i64, _p, _i64, _i64, _p, _p, _p, _f64, _f64, _p, _p, _p],
+    "bmf_cover_apply_f4_general": [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _f64, _f64, _p, _i64, _p, _p, _p],
     "bmf_select_first_max": [_p, _p, _p, _i64, _i32, _i32, _i64, _f64, _f64, _f64, _i64, _i64, _f64, _p, _p],
     "bmf_cover_apply": [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i32, _i32, _f64, _f64, _p, _i64, _i8, _p, _p, _p],
     "bmf_bool_product": [_p, _i64, _i64, _p, _i64, _i64, _p, _p],

@@ -110,6 +110,33 @@ __global__ void expand_bits_pq_kernel(const uint64_t* __restrict__ xb, const uin
   }
 }
 
+// the same P/Q operand as packed E2M1 0/1 for the FP4 kernel: blocks of 120 data rows (its tile holds 120 P + 120 Q)
+__global__ void expand_bits_pq_f4_kernel(const uint64_t* __restrict__ xb, const uint64_t* __restrict__ cb,
+                                         int64_t rows, int64_t ncols, int64_t words, uint8_t* __restrict__ plane,
+                                         int64_t plane_rows, int64_t ld_bytes) {
+  const int64_t chunks = ld_bytes >> 4;
+  const int64_t total = plane_rows * chunks;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pr = t / chunks, ch = t - pr * chunks;
+    const int64_t c0 = ch << 5;
+    const int64_t blk = pr / 240, within = pr - blk * 240;
+    const bool is_q = within >= 120;
+    const int64_t r = blk * 120 + (is_q ? within - 120 : within);
+    uint32_t out[4] = {0, 0, 0, 0};
+    const int64_t w = c0 >> 6;
+    if (r < rows && c0 < ncols && w < words) {
+      const uint32_t x32 = (uint32_t)(xb[r * words + w] >> (c0 & 63));
+      const uint32_t c32 = (uint32_t)(cb[r * words + w] >> (c0 & 63));
+      const uint32_t b32 = is_q ? c32 : (x32 & ~c32);
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c0 + i < ncols) out[i >> 3] |= (((b32 >> i) & 1u) * 2u) << ((i & 7) * 4);     // E2M1 code 2 = 1.0
+    }
+    *reinterpret_cast<uint4*>(plane + pr * ld_bytes + (ch << 4)) = make_uint4(out[0], out[1], out[2], out[3]);
+  }
+}
+
 // =========================================================================================
 // popcount contraction tiles.  Block = 256 threads computes a 64 x 64 tile of
 // (row i of A) x (row j of B); thread (ty, tx) owns rows ty*4+r and columns c*16+tx so that
@@ -406,6 +433,21 @@ cover_apply_kernel(const uint64_t* __restrict__ xb, uint64_t* __restrict__ cb, i
             const int k = __ffsll((long long)s1) - 1; s1 &= s1 - 1;
             uint8_t* bp = rowp + 32 + (k >> 1);
             *bp = (k & 1) ? (uint8_t)((*bp & 0x0Fu) | (code << 4)) : (uint8_t)((*bp & 0xF0u) | code);
+          }
+        } else if (pq_layout == 3) {                                     // packed E2M1 P/Q planes, blocks of 120 rows
+          uint8_t* rowp = reinterpret_cast<uint8_t*>(rows_plane) + ((i / 120) * 240 + (i % 120)) * ld + p * 64;
+          uint8_t* rowq = rowp + 120 * ld;
+          while (s0) {
+            const int k = __ffsll((long long)s0) - 1; s0 &= s0 - 1;
+            const int b = k >> 1;
+            if (k & 1) { rowp[b] &= 0x0Fu; rowq[b] = (uint8_t)((rowq[b] & 0x0Fu) | 0x20u); }
+            else       { rowp[b] &= 0xF0u; rowq[b] = (uint8_t)((rowq[b] & 0xF0u) | 0x02u); }
+          }
+          while (s1) {
+            const int k = __ffsll((long long)s1) - 1; s1 &= s1 - 1;
+            const int b = 32 + (k >> 1);
+            if (k & 1) { rowp[b] &= 0x0Fu; rowq[b] = (uint8_t)((rowq[b] & 0x0Fu) | 0x20u); }
+            else       { rowp[b] &= 0xF0u; rowq[b] = (uint8_t)((rowq[b] & 0xF0u) | 0x02u); }
           }
         } else {                                                         // P plane: no longer uncovered; Q plane: covered
           int8_t* rowp = rows_plane + ((i >> 7) * 256 + (i & 127)) * ld + p * 128;
@@ -1112,7 +1154,7 @@ static int launch_cover_apply(const uint64_t* x_bits, uint64_t* c_bits, int64_t 
   BMF_REQUIRE(x_bits && c_bits && basis_bits && alive && winner && tp_old && fp_old && u_bits && totals,
               "bmf_cover_apply: null pointer");
   BMF_REQUIRE(m > 0 && n > 0 && words % 2 == 0 && words * 64 >= n, "bmf_cover_apply: bad shape");
-  BMF_REQUIRE(rows_plane == nullptr || (ld % 128 == 0 && ld * (pq_layout == 2 ? 2 : 1) >= words * 64),
+  BMF_REQUIRE(rows_plane == nullptr || (ld % 128 == 0 && ld * (pq_layout >= 2 ? 2 : 1) >= words * 64),
               "bmf_cover_apply: ld must cover words*64");
   int64_t blocks = ceil_div(m, 8);
   if (blocks > row_stream_grid()) blocks = row_stream_grid();
@@ -1150,6 +1192,29 @@ extern "C" int bmf_cover_apply_f4(const uint64_t* x_bits, uint64_t* c_bits, int6
   BMF_REQUIRE((wa | wb) != 0, "bmf_cover_apply_f4: integer weights only");
   return launch_cover_apply(x_bits, c_bits, m, n, words, basis_bits, alive, winner, tp_old, fp_old, wa, wb, 0.0, 0.0,
                             reinterpret_cast<int8_t*>(rows_plane), ld_bytes, covered_code, 2, u_bits, totals, stream);
+}
+
+extern "C" int bmf_cover_apply_f4_general(const uint64_t* x_bits, uint64_t* c_bits, int64_t m, int64_t n, int64_t words,
+                                          const uint64_t* basis_bits, uint8_t* alive, const int64_t* winner,
+                                          int32_t* tp_old, int32_t* fp_old, double w_fp, double w_fn, uint8_t* pq_plane,
+                                          int64_t ld_bytes, uint64_t* u_bits, int64_t* totals, bmf_stream_t stream) {
+  BMF_REQUIRE(pq_plane != nullptr, "bmf_cover_apply_f4_general: null pq_plane");
+  return launch_cover_apply(x_bits, c_bits, m, n, words, basis_bits, alive, winner, tp_old, fp_old, 0, 0, w_fp, w_fn,
+                            reinterpret_cast<int8_t*>(pq_plane), ld_bytes, 0, 3, u_bits, totals, stream);
+}
+
+extern "C" int bmf_expand_bits_pq_f4(const uint64_t* x_bits, const uint64_t* c_bits, int64_t rows, int64_t ncols,
+                                     int64_t words, uint8_t* pq_plane, int64_t ld_bytes, bmf_stream_t stream) {
+  BMF_REQUIRE(x_bits && c_bits && pq_plane, "bmf_expand_bits_pq_f4: null pointer");
+  BMF_REQUIRE(rows > 0 && ld_bytes % 128 == 0 && ld_bytes * 2 >= ncols && words * 64 >= ncols, "bmf_expand_bits_pq_f4: bad shape / ld");
+  const int64_t plane_rows = 2 * ceil_div(rows, 120) * 120;
+  const int64_t total = plane_rows * (ld_bytes >> 4);
+  int64_t blocks = ceil_div(total, 256);
+  if (blocks > (int64_t)num_sms() * 64) blocks = (int64_t)num_sms() * 64;
+  expand_bits_pq_f4_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x_bits, c_bits, rows, ncols, words, pq_plane,
+                                                                          plane_rows, ld_bytes);
+  BMF_LAUNCH_CHECK("bmf_expand_bits_pq_f4");
+  return 0;
 }
 
 extern "C" int bmf_e2m1_code(int32_t value) {

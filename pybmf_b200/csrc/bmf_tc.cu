@@ -633,7 +633,7 @@ constexpr int STAGES4 = BMF_F4_STAGES;
 constexpr int A_OP = HALFM * BK;         // 16 KB
 constexpr int B_OP = HALFN * BK;         // 15 KB
 constexpr int STAGE_BYTES4 = A_OP + B_OP;   // 31 KB, a multiple of 1024 (swizzle atom alignment)
-constexpr int SMEM_BYTES4 = STAGES4 * STAGE_BYTES4 + 1024 + 256;
+constexpr int SMEM_BYTES4 = STAGES4 * STAGE_BYTES4 + 1024 + 256 + ROWSTATE_BYTES;
 constexpr int SF_COL = 480;              // scale-factor columns [480, 512)
 constexpr uint32_t SF_ONE = 0x7F7F7F7Fu; // UE8M0 1.0 in every byte
 // cute::UMMA::InstrDescriptorBlockScaled: a/b format E2M1 (MXF4Format 1) at [7,10)/[10,13), K-major both,
@@ -663,8 +663,55 @@ __device__ __forceinline__ void tmem_ld_32x32_x8(uint32_t taddr, uint32_t (&v)[8
 __device__ __forceinline__ int f32_bits_to_int(uint32_t bits) { return __float2int_rn(__uint_as_float(bits)); }
 
 // One FP32 accumulator tile (this thread's TMEM lane = candidate `row`, 240 columns) through the fused epilogue.
+// EPI_GAIN2 on FP4 tiles: 120 data rows per tile, P in columns [0, 120), Q in [120, 240)
+__device__ __forceinline__ void stage_row_state_f4(RowState* rs, int acc, int et, int nt, const EpiArgs& ea) {
+  if (et < HALFN) {
+    const int64_t i = (int64_t)nt * HALFN + et;
+    RowState r;
+    if (i < ea.m_rows) {
+      r.tpo = ea.tp_old[i];
+      r.fpo = ea.fp_old[i];
+      r.s_old = cover_score_f64(ea.neg_w_fp, ea.w_fn, r.fpo, r.tpo);
+    } else {
+      r.tpo = 0;
+      r.fpo = 0;
+      r.s_old = __longlong_as_double(0x7ff0000000000000ll);
+    }
+    rs[acc * 128 + et] = r;
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
 template <int EPI>
-__device__ __forceinline__ void epilogue_tile_f4(uint32_t taddr, int64_t row, int nt, const EpiArgs& ea) {
+__device__ __forceinline__ void epilogue_tile_f4(uint32_t taddr, int64_t row, int nt, const RowState* rs, const EpiArgs& ea) {
+  if (EPI == EPI_GAIN2) {
+    const int pop = ea.cand_pop[row];
+    long long sum_p = 0, sum_n = 0;
+#pragma unroll 1
+    for (int c = 0; c < HALFN / 8; ++c) {
+      uint32_t vp[8], vq[8];
+      tmem_ld_32x32_x8(taddr + (uint32_t)(c * 8), vp);
+      tmem_ld_32x32_x8(taddr + (uint32_t)(HALFN + c * 8), vq);
+      tmem_ld_wait();
+      int part_p = 0, part_n = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const RowState r = rs[c * 8 + q];
+        const int P = f32_bits_to_int(vp[q]);
+        const int N = pop - f32_bits_to_int(vq[q]) - P;
+        const bool use = cover_score_f64(ea.neg_w_fp, ea.w_fn, r.fpo + N, r.tpo + P) > r.s_old;
+        part_p += use ? P : 0;
+        part_n += use ? N : 0;
+      }
+      sum_p += part_p;
+      sum_n += part_n;
+    }
+    if (sum_p | sum_n) {
+      atomicAdd(ea.gain + row, (unsigned long long)sum_p);
+      atomicAdd(ea.gain_n + row, (unsigned long long)sum_n);
+    }
+    return;
+  }
   const int bias = (EPI == EPI_GAIN && ea.cand_pop != nullptr) ? ea.bias_scale * ea.cand_pop[row] : 0;
   long long relu_sum = 0;
 #pragma unroll 1
@@ -697,6 +744,7 @@ gemm_f4_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES4 * STAGE_BYTES4);
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES4 + 4);
+  RowState* row_state = reinterpret_cast<RowState*>(smem + STAGES4 * STAGE_BYTES4 + 256);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -800,11 +848,12 @@ gemm_f4_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     for (int64_t t = pair; t < total_tiles; t += num_pairs) {
       int mt, nt;
       tile_coords(t, mt_total, nt_total, group_m, mt, nt);
+      if (EPI == EPI_GAIN2) stage_row_state_f4(row_state, acc, (int)threadIdx.x - 64, nt, ea);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN4);
       const int64_t row = (int64_t)mt * BM4 + (int64_t)rank * HALFM + quad * 32 + lane;
-      epilogue_tile_f4<EPI>(taddr, row, nt, ea);
+      epilogue_tile_f4<EPI>(taddr, row, nt, row_state + acc * 128, ea);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
@@ -977,4 +1026,30 @@ extern "C" int bmf_cover_score_f4(const uint8_t* cand_plane, int64_t cand_pad, c
   ea.bias_scale = bias_scale;
   ea.gain = reinterpret_cast<unsigned long long*>(gain);
   return tc::f4::launch_gemm_f4<tc::EPI_GAIN>(cand_plane, cand_pad, rows_plane, rows_pad, ld_bytes, ea, as_stream(stream));
+}
+
+extern "C" int bmf_cover_score_f4_general(const uint8_t* cand_plane, int64_t cand_pad, const uint8_t* pq_plane, int64_t m,
+                                          int64_t ld_bytes, const int32_t* cand_pop, const int32_t* tp_old,
+                                          const int32_t* fp_old, double w_fp, double w_fn, int64_t* gain_p,
+                                          int64_t* gain_n, bmf_stream_t stream) {
+  BMF_REQUIRE(cand_plane && pq_plane && cand_pop && tp_old && fp_old && gain_p && gain_n,
+              "bmf_cover_score_f4_general: null pointer");
+  BMF_REQUIRE(cand_pad > 0 && cand_pad % tc::f4::BM4 == 0, "bmf_cover_score_f4_general: cand_pad must be a positive multiple of 256");
+  BMF_REQUIRE(m > 0, "bmf_cover_score_f4_general: no data rows");
+  BMF_REQUIRE(ld_bytes > 0 && ld_bytes % tc::BK == 0, "bmf_cover_score_f4_general: ld_bytes must be a positive multiple of 128");
+  const int64_t plane_rows = 2 * ceil_div(m, tc::f4::HALFN) * tc::f4::HALFN;   // [ceil(m/120)][P|Q][120] rows
+  int rc = check_cuda(cudaMemsetAsync(gain_p, 0, sizeof(int64_t) * cand_pad, as_stream(stream)), "bmf_cover_score_f4_general");
+  if (rc) return rc;
+  rc = check_cuda(cudaMemsetAsync(gain_n, 0, sizeof(int64_t) * cand_pad, as_stream(stream)), "bmf_cover_score_f4_general");
+  if (rc) return rc;
+  tc::EpiArgs ea = {};
+  ea.cand_pop = cand_pop;
+  ea.gain = reinterpret_cast<unsigned long long*>(gain_p);
+  ea.gain_n = reinterpret_cast<unsigned long long*>(gain_n);
+  ea.tp_old = tp_old;
+  ea.fp_old = fp_old;
+  ea.m_rows = m;
+  ea.neg_w_fp = -w_fp;
+  ea.w_fn = w_fn;
+  return tc::f4::launch_gemm_f4<tc::EPI_GAIN2>(cand_plane, cand_pad, pq_plane, plane_rows, ld_bytes, ea, as_stream(stream));
 }

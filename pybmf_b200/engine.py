@@ -137,9 +137,11 @@ class CoverEngine:
         self.encoding = enc
         self.plane_sign = -1 if enc == "signed-" else 1
         self.cand_pop = None
+        self._cand_pop_host = None
         # FP4 (tcgen05 kind::mxf4, twice the int8 rate): exact when the plane values 0 / wa / wa+wb are E2M1 numbers
         lib = _native.load()
-        f4_ok = self.integer_mode and enc == "zero" and lib.bmf_e2m1_code(self.wa) >= 0 and lib.bmf_e2m1_code(self.wa + self.wb) >= 0
+        f4_ok = (enc == "pq") or (self.integer_mode and enc == "zero" and lib.bmf_e2m1_code(self.wa) >= 0
+                                  and lib.bmf_e2m1_code(self.wa + self.wb) >= 0)       # the P/Q planes are 0/1: always fine
         if operand == "f4" and scorer == "tcgen05" and not f4_ok:
             raise ValueError("the FP4 scorer needs integer weights whose values wa=%d and wa+wb=%d are E2M1 numbers "
                              "(0, 1, 2, 3, 4, 6)" % (self.wa, self.wa + self.wb))
@@ -252,6 +254,14 @@ class CoverEngine:
 
     def _rebuild_rows_plane(self):
         """rows_plane[i][k] = 0 if covered, +wb if x, -wa otherwise (the signed operand of D = wb*P - wa*N)."""
+        if self.encoding == "pq" and self.operand == "f4":
+            if self.rows_plane is None:
+                self.rows_plane = device.empty((2 * device.round_up(max(self.m_loc, 1), 120), self.ld4), torch.uint8)
+            if self.m_loc > 0:
+                _native.call("bmf_expand_bits_pq_f4", self.x_bits, self.c_bits, self.m_loc, self.n, self.words,
+                             self.rows_plane, self.ld4)
+            self.launches += 1
+            return
         if self.encoding == "pq":
             if self.rows_plane is None:
                 self.rows_plane = device.empty((2 * device.round_up(max(self.m_loc, 1), 128), self.ld), torch.int8)
@@ -301,6 +311,10 @@ class CoverEngine:
         if self.m_loc == 0:                                   # a rank without rows only joins the exchange
             self.gain_p.zero_()
             self.gain_n.zero_()
+        elif self.scorer == "tcgen05" and self.encoding == "pq" and self.operand == "f4":
+            _native.call("bmf_cover_score_f4_general", self.cand_plane, self.cand_pad, self.rows_plane, self.m_loc,
+                         self.ld4, self.cand_pop, self.tp_old, self.fp_old, self.w_fp, self.w_fn, self.gain_p,
+                         self.gain_n)
         elif self.scorer == "tcgen05" and self.encoding == "pq":
             _native.call("bmf_cover_score_i8_general", self.cand_plane, self.cand_pad, self.rows_plane, self.m_loc,
                          self.ld, self.cand_pop, self.tp_old, self.fp_old, self.w_fp, self.w_fn, self.gain_p,
@@ -331,7 +345,11 @@ class CoverEngine:
                      self.n, self.wa, self.wb, base_int, scale, self.w_fp, self.w_fn, self.tp_tot, self.fp_tot,
                      float(best_score), self.record)
         u_bits = device.zeros((self.words_m,), torch.int64)
-        if self.m_loc > 0 and self.scorer == "tcgen05" and self.encoding == "pq":
+        if self.m_loc > 0 and self.scorer == "tcgen05" and self.encoding == "pq" and self.operand == "f4":
+            _native.call("bmf_cover_apply_f4_general", self.x_bits, self.c_bits, self.m_loc, self.n, self.words,
+                         self.basis_bits, self.alive, self.record, self.tp_old, self.fp_old, self.w_fp, self.w_fn,
+                         self.rows_plane, self.ld4, u_bits, self.record[2:5])
+        elif self.m_loc > 0 and self.scorer == "tcgen05" and self.encoding == "pq":
             _native.call("bmf_cover_apply_general", self.x_bits, self.c_bits, self.m_loc, self.n, self.words,
                          self.basis_bits, self.alive, self.record, self.tp_old, self.fp_old, self.w_fp, self.w_fn,
                          self.rows_plane, self.ld, u_bits, self.record[2:5])
@@ -362,6 +380,16 @@ class CoverEngine:
 
     def basis_row_host(self, j: int) -> np.ndarray:
         return device.words_to_dense(self.basis_bits[j:j + 1].cpu().numpy(), self.n)[0]
+
+    def basis_rows_host(self, js) -> np.ndarray:
+        idx = torch.as_tensor(list(js), dtype=torch.int64, device=device.dev())
+        return device.words_to_dense(self.basis_bits[idx].cpu().numpy(), self.n)
+
+    def cand_pop_host(self, j: int) -> int:
+        """|b_j| from a host copy of the per-candidate popcounts (one D2H per fit instead of one per greedy step)."""
+        if self._cand_pop_host is None:
+            self._cand_pop_host = self.cand_pop[: self.n].cpu().numpy()
+        return int(self._cand_pop_host[j])
 
     def gather_used_columns(self, ids) -> np.ndarray:
         """Columns `ids` of U over ALL ranks' rows as uint8 [m, len(ids)] (one device all-gather)."""

@@ -386,10 +386,12 @@ class Asso(BaseModel):
         ncols = len(kept)
         if live and dev is not None:
             cols = dev.gather_used_columns([e["ui"] for _p, e in live])            # [m, len(live)] uint8
-            r, c = np.nonzero(cols)
             pos = np.array([p for p, _e in live], dtype=np.int64)
-            Uc = csr_matrix((np.ones(len(r)), (r, pos[c])), shape=(self.m, ncols))
-            vr = [np.flatnonzero(e["row"]) for _p, e in live]
+            _r, c = np.nonzero(cols)                                               # row-major order = csr order
+            indptr = np.concatenate([[0], np.cumsum(cols.sum(axis=1, dtype=np.int64))])
+            Uc = csr_matrix((np.ones(len(c)), pos[c], indptr), shape=(self.m, ncols))
+            rows = dev.basis_rows_host([e["j"] for _p, e in live])                 # one D2H for all chosen basis rows
+            vr = [np.flatnonzero(row) for row in rows]
             Vc = csr_matrix((np.ones(sum(len(v) for v in vr)),
                              (np.concatenate(vr), np.repeat(pos, [len(v) for v in vr]))), shape=(self.n, ncols))
         else:
@@ -466,9 +468,8 @@ class Asso(BaseModel):
                 is_improving = self.early_stop(msg="No pattern found.", k=k)
                 break
             best_score = score
-            row = dev.basis_row_host(winner)
-            rowsum = int(row.sum())
-            self._place_factor(k, {"ui": len(dev.u_cols) - 1, "j": winner, "used": used, "rowsum": rowsum, "row": row})
+            rowsum = dev.cand_pop_host(winner)                # |b_winner|; the row itself is fetched once, at the end
+            self._place_factor(k, {"ui": len(dev.u_cols) - 1, "j": winner, "used": used, "rowsum": rowsum})
             n_basis -= 1
 
             tp, fp = dev.tp_tot, dev.fp_tot

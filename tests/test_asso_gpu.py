@@ -64,7 +64,7 @@ def test_asso_matches_reference_bit_exact(M, name, scorer, assoc):
 
 
 @pytest.mark.parametrize("name", GENERAL_CASES)
-@pytest.mark.parametrize("scorer", ["tcgen05", "popc"])
+@pytest.mark.parametrize("scorer", ["tcgen05", "tcgen05_f4", "tcgen05_i8", "popc"])
 def test_asso_general_weights(M, name, scorer):
     """non-dyadic weights: tensor cores (interleaved P/Q operand, fp64 row test in the epilogue) and popcount"""
     c = load_golden(name)
@@ -78,7 +78,7 @@ def test_asso_general_weights_auto_is_tensor_core(M):
     c = load_golden("planted_w02")
     from pybmf_b200.engine import CoverEngine
     eng = CoverEngine(sp.csr_matrix(c["X"]), c["w_fp"], 1 - c["w_fp"])
-    assert eng.scorer == "tcgen05" and eng.encoding == "pq" and not eng.integer_mode
+    assert eng.scorer == "tcgen05" and eng.encoding == "pq" and eng.operand == "f4" and not eng.integer_mode
 
 
 def test_non_canonical_csr_input(M):
@@ -360,15 +360,16 @@ def test_c4_full_size_properties(M):
     assert torch.equal(g_f4_step2[: eng.n][live], eng.gain_p[: eng.n][live])   # FP4 plane updated in place == int8
 
 
-def test_c4_slice_general_weights_tensor_cores_equal_popcount(M):
-    """non-dyadic weights at Netflix width (17770 columns, 120k rows of configs[3]): the P/Q tensor-core scorer and the
-    popcount scorer give identical sum_use P / sum_use N for every live candidate, before and after a greedy step
-    (which exercises the in-place update of the interleaved P/Q operand plane)."""
+@pytest.mark.parametrize("scorer", ["tcgen05_f4", "tcgen05_i8"])
+def test_c4_slice_general_weights_tensor_cores_equal_popcount(M, scorer):
+    """non-dyadic weights at Netflix width (17770 columns, 120k rows of configs[3]): the P/Q tensor-core scorers (FP4 and
+    int8) and the popcount scorer give identical sum_use P / sum_use N for every live candidate, before and after a
+    greedy step (which exercises the in-place update of the interleaved P/Q operand plane)."""
     from pybmf_b200 import _native, device, synth
     from pybmf_b200.engine import CoverEngine
     X = synth.config_c4(rows=(0, 120000))
-    eng = CoverEngine(X, 0.2, 0.8, scorer="tcgen05")
-    assert eng.encoding == "pq"
+    eng = CoverEngine(X, 0.2, 0.8, scorer=scorer)
+    assert eng.encoding == "pq" and eng.operand == scorer[-2:]
     nb = eng.build_basis(0.5)
     assert nb > 15000
     best = 0.0
@@ -383,9 +384,12 @@ def test_c4_slice_general_weights_tensor_cores_equal_popcount(M):
         assert torch.equal(gn[: eng.n][live], eng.gain_n[: eng.n][live])
         winner, best, used, sp_, sn_ = eng.select_and_apply(best)
         assert winner >= 0 and used > 0
-    # the plane kept current by bmf_cover_apply_general equals a fresh expansion of (X, C)
-    fresh = device.empty(tuple(eng.rows_plane.shape), torch.int8)
-    _native.call("bmf_expand_bits_pq", eng.x_bits, eng.c_bits, eng.m_loc, eng.n, eng.words, fresh, eng.ld)
+    # the plane kept current by bmf_cover_apply_*general equals a fresh expansion of (X, C)
+    fresh = torch.empty_like(eng.rows_plane)
+    if eng.operand == "f4":
+        _native.call("bmf_expand_bits_pq_f4", eng.x_bits, eng.c_bits, eng.m_loc, eng.n, eng.words, fresh, eng.ld4)
+    else:
+        _native.call("bmf_expand_bits_pq", eng.x_bits, eng.c_bits, eng.m_loc, eng.n, eng.words, fresh, eng.ld)
     assert torch.equal(fresh, eng.rows_plane)
 
 

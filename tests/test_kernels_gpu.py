@@ -248,6 +248,53 @@ def test_cover_score_i8_general_tcgen05(nat, m, n, w, gemm_variant):
     assert got_p[n:].sum() == 0 and got_n[n:].sum() == 0
 
 
+@pytest.mark.parametrize("m,n,w", [(70, 50, (0.2, 0.8)), (300, 200, (0.3, 0.6)), (121, 257, (0.2, 0.8)),
+                                   (3000, 1100, (0.15, 0.85))])
+def test_cover_score_f4_general_tcgen05(nat, m, n, w):
+    """general weights on the FP4 pipe: packed E2M1 P/Q planes in blocks of 120 rows, fp64 row test in the epilogue;
+    the plane kept current by bmf_cover_apply_f4_general equals a fresh expansion"""
+    _native, device = nat
+    X, C, B, alive = _cover_inputs(m * 13 + n, m, n)
+    alive[:] = 1
+    w_fp, w_fn = w
+    words = device.words_for(n)
+    ld_bytes = device.round_up(n, 256) // 2
+    cand_pad = device.round_up(n, 256)
+    tpo, fpo, _ = O.confusion(X, C, axis=1)
+    x_d, c_d, b_d = _dev(device.dense_to_words(X)), _dev(device.dense_to_words(C)), _dev(device.dense_to_words(B))
+    cand_plane = device.empty((cand_pad, ld_bytes), torch.uint8)
+    _native.call("bmf_expand_bits_f4", b_d, None, n, n, words, 2, 0, 0, cand_plane, cand_pad, ld_bytes)
+    pop = np.zeros(cand_pad, np.int32)
+    pop[:n] = B.sum(axis=1)
+    pq = device.empty((2 * device.round_up(m, 120), ld_bytes), torch.uint8)
+    _native.call("bmf_expand_bits_pq_f4", x_d, c_d, m, n, words, pq, ld_bytes)
+    vals = np.zeros((pq.shape[0], n), np.int64)                      # numpy statement of the layout
+    for i in range(m):
+        pr = (i // 120) * 240 + i % 120
+        vals[pr] = X[i] & (1 - C[i])
+        vals[pr + 120] = C[i]
+    assert np.array_equal(pq.cpu().numpy(), _pack_f4(vals, ld_bytes))
+    gp = device.zeros((cand_pad,), torch.int64) + 7
+    gn = device.zeros((cand_pad,), torch.int64) + 7
+    tp_d, fp_d = _dev(tpo.astype(np.int32)), _dev(fpo.astype(np.int32))
+    _native.call("bmf_cover_score_f4_general", cand_plane, cand_pad, pq, m, ld_bytes, _dev(pop), tp_d, fp_d, w_fp, w_fn,
+                 gp, gn)
+    score, use, P, N, _, _ = O.score_candidates(X, C, B, w_fp, w_fn)
+    got_p, got_n = gp.cpu().numpy(), gn.cpu().numpy()
+    assert np.array_equal(got_p[:n], (P * use).sum(axis=0)) and np.array_equal(got_n[:n], (N * use).sum(axis=0))
+    assert got_p[n:].sum() == 0 and got_n[n:].sum() == 0
+    j = int(np.argmax(score))
+    ub = device.zeros((device.words_for(m),), torch.int64)
+    tot = device.zeros((3,), torch.int64)
+    _native.call("bmf_cover_apply_f4_general", x_d, c_d, m, n, words, b_d, _dev(alive), _dev(np.array([j], np.int64)),
+                 tp_d, fp_d, w_fp, w_fn, pq, ld_bytes, ub, tot)
+    u = use[:, j]
+    assert list(tot.cpu().numpy()) == [int(u.sum()), int(P[u, j].sum()), int(N[u, j].sum())]
+    fresh = torch.empty_like(pq)
+    _native.call("bmf_expand_bits_pq_f4", x_d, c_d, m, n, words, fresh, ld_bytes)
+    assert torch.equal(fresh, pq)
+
+
 def test_cover_apply_general_updates_pq_plane(nat):
     _native, device = nat
     m, n = 333, 200
