@@ -429,6 +429,18 @@ def main():
                 "algorithmic_ops_per_launch": ops_launch,
                 "spec_tops_of_pipe": 9000.0 if pipe == "fp4" else 4500.0,
                 "frac_of_pipe_spec": achieved / (9000.0 if pipe == "fp4" else 4500.0)}
+    variant = ("pq-" if eng.encoding == "pq" else "") + operand if args.scorer != "popc" else "popc"
+    try:                                                        # per-launch DRAM bytes from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            hit = json.load(fh).get("%s:%s:%d" % (args.workload, variant, world))
+        if hit:
+            roofline["traffic"] = hit["bytes"]
+            roofline["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)"
+            roofline["traffic_source"] = hit["source"]
+            roofline["algorithmic_bytes_per_launch"] = ((m / world) + nb) * (n / 2.0 if operand == "f4" else float(n)) \
+                * (2 if variant.startswith("pq") else 1)
+    except (OSError, ValueError):
+        pass
     del eng
     torch.cuda.empty_cache()
     if rank == 0:

@@ -42,6 +42,7 @@ extern "C" {
 /* FP4 (tcgen05 kind::mxf4) kernels: candidate rows padded to 256, data rows to 240, K to 256 elements */
 #define BMF_F4_CAND_TILE 256
 #define BMF_F4_ROW_TILE 240
+#define BMF_F4_SUPER_ROWS 496 /* data rows padded to 496 select the super-tile kernel (256 + 240 sub-tiles)  */
 #define BMF_F4_K_TILE 256     /* elements of K per stage = 128 bytes of packed E2M1         */
 
 typedef void* bmf_stream_t;
@@ -134,7 +135,8 @@ int bmf_cover_score_i8_general(const int8_t* cand_plane, int64_t cand_pad, const
  * bmf_expand_bits_f4: value codes `one`/`zero`/`masked` are E2M1 bit patterns (0 -> 0.0, 2 -> 1.0, 4 -> 2.0,
  * 5 -> 3.0, 6 -> 4.0, 7 -> 6.0), otherwise as bmf_expand_bits_i8.  bmf_e2m1_code maps an integer value to its
  * code or returns -1 when E2M1 cannot represent it (the caller then stays on the int8 kernels).
- * bmf_gemm_f4_nt: c[i][j] = sum_k a[i][k]*b[j][k] as int32 (a rows multiple of 256, b rows multiple of 240).
+ * bmf_gemm_f4_nt: c[i][j] = sum_k a[i][k]*b[j][k] as int32 (a rows multiple of 256, b rows multiple of 240, or
+ * of 496 = BMF_F4_SUPER_ROWS, which selects the faster super-tile kernel; likewise rows_pad of bmf_cover_score_f4).
  * bmf_cover_score_f4: the zero-dominant encoding of bmf_cover_score_i8 (sign = +1) on f4 planes. */
 int bmf_e2m1_code(int32_t value);
 int bmf_expand_bits_f4(const uint64_t* bits, const uint64_t* mask_bits, int64_t rows, int64_t ncols, int64_t words,

@@ -55,6 +55,15 @@ __global__ void expand_bits_i8_kernel(const uint64_t* __restrict__ bits, const u
   }
 }
 
+// 8 bits -> 8 nibbles (bit i lands on the least significant bit of nibble i); multiplying the result by a 4-bit
+// code then writes that code into every selected nibble (codes <= 7: no carries between nibbles)
+__device__ __forceinline__ uint32_t spread8(uint32_t x) {
+  x = (x | (x << 12)) & 0x000F000Fu;
+  x = (x | (x << 6)) & 0x03030303u;
+  x = (x | (x << 3)) & 0x11111111u;
+  return x;
+}
+
 // 32 bits -> 32 E2M1 codes (16 bytes) per thread, one 128-bit store; element k of a row lives in byte k/2,
 // low nibble for even k
 __global__ void expand_bits_f4_kernel(const uint64_t* __restrict__ bits, const uint64_t* __restrict__ mask,
@@ -71,12 +80,13 @@ __global__ void expand_bits_f4_kernel(const uint64_t* __restrict__ bits, const u
       const int64_t w = c0 >> 6;
       const uint32_t b32 = (w < words) ? (uint32_t)(bits[r * words + w] >> (c0 & 63)) : 0u;
       const uint32_t k32 = (mask != nullptr && w < words) ? (uint32_t)(mask[r * words + w] >> (c0 & 63)) : 0u;
+      const int64_t left = ncols - c0;                              // valid columns in this chunk
+      const uint32_t valid = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
+      const uint32_t s_one = b32 & ~k32 & valid, s_zero = ~b32 & ~k32 & valid, s_mask = k32 & valid;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        uint32_t v = 0;
-        if (c0 + i < ncols) v = ((k32 >> i) & 1u) ? masked : (((b32 >> i) & 1u) ? one : zero);
-        out[i >> 3] |= v << ((i & 7) * 4);
-      }
+      for (int q = 0; q < 4; ++q)
+        out[q] = spread8((s_one >> (8 * q)) & 0xFFu) * one + spread8((s_zero >> (8 * q)) & 0xFFu) * zero +
+                 spread8((s_mask >> (8 * q)) & 0xFFu) * masked;
     }
     *reinterpret_cast<uint4*>(plane + r * ld_bytes + (ch << 4)) = make_uint4(out[0], out[1], out[2], out[3]);
   }
@@ -128,10 +138,11 @@ __global__ void expand_bits_pq_f4_kernel(const uint64_t* __restrict__ xb, const 
     if (r < rows && c0 < ncols && w < words) {
       const uint32_t x32 = (uint32_t)(xb[r * words + w] >> (c0 & 63));
       const uint32_t c32 = (uint32_t)(cb[r * words + w] >> (c0 & 63));
-      const uint32_t b32 = is_q ? c32 : (x32 & ~c32);
+      const int64_t left = ncols - c0;
+      const uint32_t valid = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
+      const uint32_t b32 = (is_q ? c32 : (x32 & ~c32)) & valid;
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (c0 + i < ncols) out[i >> 3] |= (((b32 >> i) & 1u) * 2u) << ((i & 7) * 4);     // E2M1 code 2 = 1.0
+      for (int q = 0; q < 4; ++q) out[q] = spread8((b32 >> (8 * q)) & 0xFFu) * 2u;        // E2M1 code 2 = 1.0
     }
     *reinterpret_cast<uint4*>(plane + pr * ld_bytes + (ch << 4)) = make_uint4(out[0], out[1], out[2], out[3]);
   }

@@ -897,6 +897,224 @@ static int launch_gemm_f4(const uint8_t* a, int64_t a_rows, const uint8_t* b, in
   gemm_f4_2sm_kernel<EPI><<<2 * pairs, NUM_THREADS, SMEM_BYTES4, stream>>>(ma, mb, mt, nt, kb, group_m, ea);
   return check_cuda(cudaGetLastError(), "gemm_f4_2sm_kernel launch");
 }
+
+// -------------------------------------------------------------------------------------------------
+// Super-tile variant (EPI_GAIN / EPI_STORE): a kind::mxf4 instruction costs ~150 cycles whatever N is, so wider is
+// better, but two 256-column accumulators leave no TMEM for the scale factors.  Here a CTA pair walks SUPER tiles of
+// 256 candidates x 496 data rows as two back-to-back sub-tiles: N = 256 into accumulator 0 (columns [0, 256)) and
+// N = 240 into accumulator 1 (columns [256, 496)); scale factors sit in columns [496, 512).  Average N = 248
+// instead of 240 (+3 %), the A tile is re-used by both sub-tiles out of L2, and the accumulator index equals the
+// sub-tile index, so the double-buffering protocol is unchanged.
+// -------------------------------------------------------------------------------------------------
+constexpr int SUPER_ROWS = BMF_F4_SUPER_ROWS;   // 496
+static inline bool super_tiles_disabled() {
+  const char* e = getenv("BMF_F4_NO_SUPER");
+  return e != nullptr && e[0] == '1';
+}
+constexpr int SUB0 = 256, SUB1 = SUPER_ROWS - SUB0;          // sub-tile widths
+constexpr int STAGES_S = 6;
+constexpr int STAGE_BYTES_S = A_OP + (SUB0 / 2) * BK;        // 32 KB (sub-tile 1 uses 31 KB of it)
+constexpr int SMEM_BYTES_S = STAGES_S * STAGE_BYTES_S + 1024 + 256;
+constexpr int SF_COL_S = SUPER_ROWS;                          // scale-factor columns [496, 512)
+constexpr uint32_t idesc_f4(int n) {
+  return (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | (1u << 23) | ((uint32_t)(BM4 >> 4) << 24);
+}
+
+template <int EPI, int NCOLS>
+__device__ __forceinline__ void epilogue_cols_f4(uint32_t taddr, int64_t row, int64_t col0, const EpiArgs& ea) {
+  const int bias = (EPI == EPI_GAIN && ea.cand_pop != nullptr) ? ea.bias_scale * ea.cand_pop[row] : 0;
+  long long relu_sum = 0;
+#pragma unroll 1
+  for (int c = 0; c < NCOLS / 16; ++c) {
+    uint32_t lo[8], hi[8];
+    tmem_ld_32x32_x8(taddr + (uint32_t)(c * 16), lo);
+    tmem_ld_32x32_x8(taddr + (uint32_t)(c * 16 + 8), hi);
+    tmem_ld_wait();
+    if (EPI == EPI_GAIN) {
+      int part = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) part += max(f32_bits_to_int(lo[q]) - bias, 0) + max(f32_bits_to_int(hi[q]) - bias, 0);
+      relu_sum += part;
+    } else {
+      int4* dst = reinterpret_cast<int4*>(ea.C + row * ea.ldc + col0 + c * 16);
+      dst[0] = make_int4(f32_bits_to_int(lo[0]), f32_bits_to_int(lo[1]), f32_bits_to_int(lo[2]), f32_bits_to_int(lo[3]));
+      dst[1] = make_int4(f32_bits_to_int(lo[4]), f32_bits_to_int(lo[5]), f32_bits_to_int(lo[6]), f32_bits_to_int(lo[7]));
+      dst[2] = make_int4(f32_bits_to_int(hi[0]), f32_bits_to_int(hi[1]), f32_bits_to_int(hi[2]), f32_bits_to_int(hi[3]));
+      dst[3] = make_int4(f32_bits_to_int(hi[4]), f32_bits_to_int(hi[5]), f32_bits_to_int(hi[6]), f32_bits_to_int(hi[7]));
+    }
+  }
+  if (EPI == EPI_GAIN && relu_sum != 0) atomicAdd(ea.gain + row, (unsigned long long)relu_sum);
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_f4s_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b0,
+                    const __grid_constant__ CUtensorMap tmap_b1, int mt_total, int st_total, int kb_total, int group_m,
+                    const EpiArgs ea) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES_S * STAGE_BYTES_S);
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES_S + 4);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES_S + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES_S + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES_S + 2 + a); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int64_t pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int64_t total_tiles = (int64_t)mt_total * st_total;   // super tiles
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES_S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b0)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b1)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_base_slot);
+  if (warp >= 2) {                                        // unit scale factors: all 128 lanes x columns [496, 512)
+    const uint32_t sf_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)SF_COL_S;
+    tmem_st_32x32_x8(sf_addr, SF_ONE);
+    tmem_st_32x32_x8(sf_addr + 8u, SF_ONE);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = pair; t < total_tiles; t += num_pairs) {
+        int mt, st;
+        tile_coords(t, mt_total, st_total, group_m, mt, st);
+#pragma unroll 1
+        for (int sub = 0; sub < 2; ++sub) {
+          const int half = sub ? SUB1 / 2 : SUB0 / 2;                       // data rows this CTA stages
+          const int row0 = st * SUPER_ROWS + (sub ? SUB0 : 0) + (int)rank * half;
+          const CUtensorMap* mb = sub ? &tmap_b1 : &tmap_b0;
+          const uint32_t tx = 2u * (uint32_t)(A_OP + half * BK);
+          for (int kb = 0; kb < kb_total; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t leader_full = full_bar(stage) & PEER_MASK;
+            if (leader) mbar_expect_tx(full_bar(stage), tx);
+            const uint32_t a_dst = smem_base + stage * STAGE_BYTES_S;
+            tma_load_2d_2sm(a_dst, &tmap_a, leader_full, kb * BK, mt * BM4 + (int)rank * HALFM, ea.policy_a);
+            tma_load_2d_2sm(a_dst + A_OP, mb, leader_full, kb * BK, row0, ea.policy_b);
+            if (++stage == STAGES_S) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const uint32_t sfa = tmem_base + (uint32_t)SF_COL_S, sfb = tmem_base + (uint32_t)SF_COL_S + 8u;
+      for (int64_t t = pair; t < total_tiles; t += num_pairs) {
+#pragma unroll 1
+        for (int sub = 0; sub < 2; ++sub) {
+          mbar_wait(tempty_bar(sub), acc_phase ^ 1u);
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(sub ? SUB0 : 0);
+          const uint32_t idesc = sub ? idesc_f4(SUB1) : idesc_f4(SUB0);
+          for (int kb = 0; kb < kb_total; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tcgen05_fence_after();
+            const uint32_t a_addr = smem_base + stage * STAGE_BYTES_S;
+            const uint64_t da = make_smem_desc(a_addr), db = make_smem_desc(a_addr + A_OP);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tcgen05_mma_f4_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                 (uint32_t)((kb | k) != 0), sfa, sfb);
+            tcgen05_commit_2sm(empty_bar(stage));
+            if (++stage == STAGES_S) { stage = 0; phase ^= 1u; }
+          }
+          tcgen05_commit_2sm(tfull_bar(sub));
+        }
+        acc_phase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;
+    uint32_t acc_phase = 0;
+    for (int64_t t = pair; t < total_tiles; t += num_pairs) {
+      int mt, st;
+      tile_coords(t, mt_total, st_total, group_m, mt, st);
+      const int64_t row = (int64_t)mt * BM4 + (int64_t)rank * HALFM + quad * 32 + lane;
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+      mbar_wait(tfull_bar(0), acc_phase);
+      tcgen05_fence_after();
+      epilogue_cols_f4<EPI, SUB0>(lane_base, row, (int64_t)st * SUPER_ROWS, ea);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tempty_bar(0));
+      mbar_wait(tfull_bar(1), acc_phase);
+      tcgen05_fence_after();
+      epilogue_cols_f4<EPI, SUB1>(lane_base + (uint32_t)SUB0, row, (int64_t)st * SUPER_ROWS + SUB0, ea);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tempty_bar(1));
+      acc_phase ^= 1u;
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+template <int EPI>
+static int launch_gemm_f4s(const uint8_t* a, int64_t a_rows, const uint8_t* b, int64_t b_rows, int64_t ld_bytes,
+                           const EpiArgs& ea_in, cudaStream_t stream) {
+  CUtensorMap ma, mb0, mb1;
+  int rc = make_plane_map(&ma, reinterpret_cast<const int8_t*>(a), a_rows, ld_bytes, HALFM);
+  if (rc) return rc;
+  rc = make_plane_map(&mb0, reinterpret_cast<const int8_t*>(b), b_rows, ld_bytes, SUB0 / 2);
+  if (rc) return rc;
+  rc = make_plane_map(&mb1, reinterpret_cast<const int8_t*>(b), b_rows, ld_bytes, SUB1 / 2);
+  if (rc) return rc;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[EPI]) {
+    rc = check_cuda(cudaFuncSetAttribute(gemm_f4s_2sm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_S),
+                    "cudaFuncSetAttribute(gemm_f4s_2sm_kernel)");
+    if (rc) return rc;
+    attr_set[EPI] = true;
+  }
+  EpiArgs ea = ea_in;
+  ea.policy_a = L2_EVICT_NORMAL;
+  ea.policy_b = L2_EVICT_NORMAL;
+  const int mt = (int)(a_rows / BM4), st = (int)(b_rows / SUPER_ROWS), kb = (int)(ld_bytes / BK);
+  const int64_t tiles = (int64_t)mt * st;
+  const int pairs_max = num_sms() / 2;
+  const int pairs = (int)(tiles < pairs_max ? tiles : pairs_max);
+  int group_m = 16;
+  if (const char* e = getenv("BMF_GROUP_M2")) { int v = atoi(e); if (v >= 1 && v <= 64) group_m = v; }
+  gemm_f4s_2sm_kernel<EPI><<<2 * pairs, NUM_THREADS, SMEM_BYTES_S, stream>>>(ma, mb0, mb1, mt, st, kb, group_m, ea);
+  return check_cuda(cudaGetLastError(), "gemm_f4s_2sm_kernel launch");
+}
 }  // namespace f4
 
 // variant: 0 = auto (2-SM when the candidate rows are a multiple of 256), 1 = 1-SM, 2 = 2-SM
@@ -1001,12 +1219,16 @@ extern "C" int bmf_gemm_f4_nt(const uint8_t* a_plane, int64_t a_rows_pad, const 
                               int64_t ld_bytes, int32_t* c, int64_t ldc, bmf_stream_t stream) {
   BMF_REQUIRE(a_plane && b_plane && c, "bmf_gemm_f4_nt: null pointer");
   BMF_REQUIRE(a_rows_pad > 0 && a_rows_pad % tc::f4::BM4 == 0, "bmf_gemm_f4_nt: a rows must be a positive multiple of 256");
-  BMF_REQUIRE(b_rows_pad > 0 && b_rows_pad % tc::f4::BN4 == 0, "bmf_gemm_f4_nt: b rows must be a positive multiple of 240");
+  BMF_REQUIRE(b_rows_pad > 0 && (b_rows_pad % tc::f4::BN4 == 0 || b_rows_pad % tc::f4::SUPER_ROWS == 0),
+              "bmf_gemm_f4_nt: b rows must be a positive multiple of 240 or of 496");
   BMF_REQUIRE(ld_bytes > 0 && ld_bytes % tc::BK == 0, "bmf_gemm_f4_nt: ld_bytes must be a positive multiple of 128");
   BMF_REQUIRE(ldc >= b_rows_pad && ldc % 4 == 0, "bmf_gemm_f4_nt: ldc must cover b rows and be a multiple of 4");
   tc::EpiArgs ea = {};
   ea.C = c;
   ea.ldc = ldc;
+  if (b_rows_pad % tc::f4::SUPER_ROWS == 0 && !tc::f4::super_tiles_disabled())
+    return tc::f4::launch_gemm_f4s<tc::EPI_STORE>(a_plane, a_rows_pad, b_plane, b_rows_pad, ld_bytes, ea, as_stream(stream));
+  BMF_REQUIRE(b_rows_pad % tc::f4::BN4 == 0, "bmf_gemm_f4_nt: b rows must be a multiple of 240 for the plain-tile kernel");
   return tc::f4::launch_gemm_f4<tc::EPI_STORE>(a_plane, a_rows_pad, b_plane, b_rows_pad, ld_bytes, ea, as_stream(stream));
 }
 
@@ -1015,7 +1237,8 @@ extern "C" int bmf_cover_score_f4(const uint8_t* cand_plane, int64_t cand_pad, c
                                   int64_t* gain, bmf_stream_t stream) {
   BMF_REQUIRE(cand_plane && rows_plane && gain, "bmf_cover_score_f4: null pointer");
   BMF_REQUIRE(cand_pad > 0 && cand_pad % tc::f4::BM4 == 0, "bmf_cover_score_f4: cand_pad must be a positive multiple of 256");
-  BMF_REQUIRE(rows_pad > 0 && rows_pad % tc::f4::BN4 == 0, "bmf_cover_score_f4: rows_pad must be a positive multiple of 240");
+  BMF_REQUIRE(rows_pad > 0 && (rows_pad % tc::f4::BN4 == 0 || rows_pad % tc::f4::SUPER_ROWS == 0),
+              "bmf_cover_score_f4: rows_pad must be a positive multiple of 240 or of 496");
   BMF_REQUIRE(ld_bytes > 0 && ld_bytes % tc::BK == 0, "bmf_cover_score_f4: ld_bytes must be a positive multiple of 128");
   BMF_REQUIRE(cand_pop != nullptr || bias_scale == 0, "bmf_cover_score_f4: a bias needs cand_pop");
   int rc = check_cuda(cudaMemsetAsync(gain, 0, sizeof(int64_t) * cand_pad, as_stream(stream)), "bmf_cover_score_f4");
@@ -1025,6 +1248,9 @@ extern "C" int bmf_cover_score_f4(const uint8_t* cand_plane, int64_t cand_pad, c
   ea.cand_pop = cand_pop;
   ea.bias_scale = bias_scale;
   ea.gain = reinterpret_cast<unsigned long long*>(gain);
+  if (rows_pad % tc::f4::SUPER_ROWS == 0 && !tc::f4::super_tiles_disabled())
+    return tc::f4::launch_gemm_f4s<tc::EPI_GAIN>(cand_plane, cand_pad, rows_plane, rows_pad, ld_bytes, ea, as_stream(stream));
+  BMF_REQUIRE(rows_pad % tc::f4::BN4 == 0, "bmf_cover_score_f4: rows_pad must be a multiple of 240 for the plain-tile kernel");
   return tc::f4::launch_gemm_f4<tc::EPI_GAIN>(cand_plane, cand_pad, rows_plane, rows_pad, ld_bytes, ea, as_stream(stream));
 }
 

@@ -19,6 +19,7 @@ import torch
 from . import _native, device
 
 ROW_ALIGN = 256        # shard boundaries are multiples of the MMA N tile (and of 64-bit u words)
+F4_ROW_PAD = 496       # BMF_F4_SUPER_ROWS: data rows of the FP4 planes are padded to whole super tiles (256 + 240)
 
 
 def integer_weights(w_fp, w_fn, max_int=127, max_shift=30):
@@ -213,7 +214,7 @@ class CoverEngine:
     def _build_basis(self, tau: float):
         n, m_loc = self.n, self.m_loc
         n_pad = device.round_up(n, 256)
-        ldc = max(n_pad, device.round_up(n, 240))              # the FP4 kernel's data-row tiles are 240 wide
+        ldc = max(n_pad, device.round_up(n, F4_ROW_PAD))       # the FP4 kernel walks data rows in super tiles of 496
         cnt = device.zeros((n_pad, ldc), torch.int32)
         if m_loc > 0:
             xt_bits = device.pack_csr(self._ip, self._ix, m_loc, n, transposed=True)
@@ -223,7 +224,7 @@ class CoverEngine:
                 xt_plane = device.empty((max(n_pad, ldc), ldk), torch.uint8)
                 _native.call("bmf_expand_bits_f4", xt_bits, None, n, m_loc, xt_bits.shape[1], 2, 0, 0, xt_plane,
                              xt_plane.shape[0], ldk)
-                _native.call("bmf_gemm_f4_nt", xt_plane, n_pad, xt_plane, device.round_up(n, 240), ldk, cnt, ldc)
+                _native.call("bmf_gemm_f4_nt", xt_plane, n_pad, xt_plane, device.round_up(n, F4_ROW_PAD), ldk, cnt, ldc)
                 del xt_plane
             elif self.assoc_kind == "tcgen05":
                 xt_plane = device.expand_bits_i8(xt_bits, n, m_loc, 1, 0, 256)
@@ -273,7 +274,7 @@ class CoverEngine:
         one, zero, covered = self._plane_values()
         if self.operand == "f4":
             lib = _native.load()
-            rows_pad = device.round_up(max(self.m_loc, 1), 240)
+            rows_pad = device.round_up(max(self.m_loc, 1), F4_ROW_PAD)
             if self.rows_plane is None:
                 self.rows_plane = device.empty((rows_pad, self.ld4), torch.uint8)
             _native.call("bmf_expand_bits_f4", self.x_bits, self.c_bits, self.m_loc, self.n, self.words,

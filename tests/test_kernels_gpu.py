@@ -335,8 +335,9 @@ def _pack_f4(values, ld_bytes):
     return (codes[:, 0::2] | (codes[:, 1::2] << 4)).astype(np.uint8)
 
 
-@pytest.mark.parametrize("ma,nb,k", [(256, 240, 256), (256, 480, 1024), (512, 240, 2304), (768, 720, 17920)])
-def test_gemm_f4_tcgen05_exact(nat, ma, nb, k):
+@pytest.mark.parametrize("ma,nb,k", [(256, 240, 256), (256, 480, 1024), (512, 240, 2304), (768, 720, 17920),
+                                     (256, 496, 256), (512, 992, 1280), (768, 1488, 17920), (256, 7440, 512)])
+def test_gemm_f4_tcgen05_exact(nat, ma, nb, k, monkeypatch):
     """tcgen05 kind::mxf4 with unit block scales on small-integer operands is EXACT (FP32 accumulate of integers)"""
     _native, device = nat
     rng = np.random.RandomState(ma + nb + k)
@@ -346,11 +347,16 @@ def test_gemm_f4_tcgen05_exact(nat, ma, nb, k):
     B[: nb // 4] = 6                                                  # dense rows: sums up to 6*0.4*k
     assert _native.load().bmf_e2m1_code(5) == -1 and _native.load().bmf_e2m1_code(6) == 7
     ld_bytes = k // 2
-    c = device.zeros((ma, nb), torch.int32) - 1
-    _native.call("bmf_gemm_f4_nt", _dev(_pack_f4(A, ld_bytes)), ma, _dev(_pack_f4(B, ld_bytes)), nb, ld_bytes, c, nb)
     want = A @ B.T
     assert want.max() > 4000 or k < 2000
-    assert np.array_equal(c.cpu().numpy().astype(np.int64), want)
+    a_d, b_d = _dev(_pack_f4(A, ld_bytes)), _dev(_pack_f4(B, ld_bytes))
+    for no_super in ("0", "1"):                                       # rows % 496 == 0 -> super-tile kernel (256 + 240)
+        if no_super == "1" and nb % 240:
+            continue
+        monkeypatch.setenv("BMF_F4_NO_SUPER", no_super)
+        c = device.zeros((ma, nb), torch.int32) - 1
+        _native.call("bmf_gemm_f4_nt", a_d, ma, b_d, nb, ld_bytes, c, nb)
+        assert np.array_equal(c.cpu().numpy().astype(np.int64), want)
 
 
 @pytest.mark.parametrize("rows,ncols", [(5, 70), (300, 500), (241, 257)])
@@ -369,9 +375,10 @@ def test_expand_bits_f4(nat, rows, ncols):
     assert np.array_equal(plane.cpu().numpy(), _pack_f4(vals, ld_bytes))
 
 
+@pytest.mark.parametrize("row_pad", [240, 496])
 @pytest.mark.parametrize("m,n,w", [(70, 50, (0.5, 0.5)), (300, 200, (0.25, 0.75)), (1000, 500, (0.75, 0.25)),
                                    (5000, 2100, (0.5, 0.5))])
-def test_cover_score_f4_tcgen05(nat, m, n, w):
+def test_cover_score_f4_tcgen05(nat, m, n, w, row_pad):
     """FP4 scorer == integer gains, and the plane kept current by bmf_cover_apply_f4 == a fresh expansion"""
     _native, device = nat
     X, C, B, alive = _cover_inputs(m * 7 + n, m, n)
@@ -382,7 +389,7 @@ def test_cover_score_f4_tcgen05(nat, m, n, w):
     assert c_one >= 0 and c_cov >= 0
     words = device.words_for(n)
     ld_bytes = device.round_up(n, 256) // 2
-    rows_pad, cand_pad = device.round_up(m, 240), device.round_up(n, 256)
+    rows_pad, cand_pad = device.round_up(m, row_pad), device.round_up(n, 256)   # 496 -> super-tile kernel
     x_d, c_d, b_d = _dev(device.dense_to_words(X)), _dev(device.dense_to_words(C)), _dev(device.dense_to_words(B))
     rows_plane = device.empty((rows_pad, ld_bytes), torch.uint8)
     cand_plane = device.empty((cand_pad, ld_bytes), torch.uint8)
