@@ -641,50 +641,22 @@ confusion_kernel(const uint64_t* __restrict__ gt, const uint64_t* __restrict__ p
 // ncu on the row-stream kernels above at m = 1M, n = 100k, k = 64 (profiles/r01_c5_*): the V^T rows a
 // data row selects are re-fetched from L2 (2.5x the HBM bytes through L1) and the XU pipe (POPC) is
 // 68 % busy at 52 % of HBM peak, i.e. four POPCs per 64-bit word cap the kernel near 5 TB/s.
-// Here a CTA owns a panel of <= PANEL_MAX_CHUNKS x 256 bit-words (2 KB per row and chunk) of ALL k
-// rows of V^T in shared memory; its warps stream two data rows at a time through the panel, so
+// Here a CTA owns a panel of one or two chunks of 256 bit-words (2 KB per row and chunk) of ALL k <= 64
+// rows of V^T in shared memory; its warps stream their data rows through the panel, so
 //  * V^T is read from L2 once per CTA, the selected rows are ORed from shared memory (conflict free:
 //    a warp reads 512 contiguous bytes), and HBM only carries the ground truth / the product;
 //  * set bits are counted with a Harley-Seal carry-save adder tree (LOP3 on the ALU pipe): 16 words
-//    cost 15 CSAs and ONE popcount instead of 16, which takes the XU pipe out of the picture.
+//    cost 15 CSAs and ONE popcount instead of 16, which takes the XU pipe out of the picture
+//    (HarleySeal8 below folds the 8 words a lane holds per row and pairs two rows per popcount).
 // =========================================================================================
 constexpr int CH_PAIRS = 128;            // 16-byte pairs per chunk and row: 32 lanes x 4
 constexpr int PANEL_THREADS = 512;
-constexpr int PANEL_SMEM_MAX = 200 * 1024;
 
 __device__ __forceinline__ void csa64(uint64_t& h, uint64_t& l, uint64_t a, uint64_t b, uint64_t c) {
   const uint64_t u = a ^ b;
   h = (a & b) | (u & c);                 // majority -> one LOP3 per 32-bit half
   l = u ^ c;                             // parity   -> one LOP3 per 32-bit half
 }
-struct HarleySeal {
-  uint64_t ones = 0, twos = 0, fours = 0, eights = 0;
-  long long sixteens = 0;                // popcounts of the "sixteens" words
-  __device__ __forceinline__ void add16(const uint64_t (&w)[16]) {
-    uint64_t t2a, t2b, t4a, t4b, t8a, t8b, t16;
-    csa64(t2a, ones, ones, w[0], w[1]);
-    csa64(t2b, ones, ones, w[2], w[3]);
-    csa64(t4a, twos, twos, t2a, t2b);
-    csa64(t2a, ones, ones, w[4], w[5]);
-    csa64(t2b, ones, ones, w[6], w[7]);
-    csa64(t4b, twos, twos, t2a, t2b);
-    csa64(t8a, fours, fours, t4a, t4b);
-    csa64(t2a, ones, ones, w[8], w[9]);
-    csa64(t2b, ones, ones, w[10], w[11]);
-    csa64(t4a, twos, twos, t2a, t2b);
-    csa64(t2a, ones, ones, w[12], w[13]);
-    csa64(t2b, ones, ones, w[14], w[15]);
-    csa64(t4b, twos, twos, t2a, t2b);
-    csa64(t8b, fours, fours, t4a, t4b);
-    csa64(t16, eights, eights, t8a, t8b);
-    sixteens += __popcll(t16);
-  }
-  __device__ __forceinline__ long long total() const {
-    return 16 * sixteens + 8 * (long long)__popcll(eights) + 4 * (long long)__popcll(fours) +
-           2 * (long long)__popcll(twos) + (long long)__popcll(ones);
-  }
-};
-
 // V^T panel -> shared memory: Vs[l][p] (pairs), zero beyond the matrix
 __device__ __forceinline__ void load_vt_panel(ulonglong2* Vs, const uint64_t* __restrict__ vt, int64_t k,
                                               int64_t words, int64_t pair0, int panel_pairs) {
