@@ -4,7 +4,7 @@ sys.path.insert(0, os.getcwd())
 import torch
 from pybmf_b200 import synth
 from pybmf_b200.engine import CoverEngine
-X = synth.config_c4(rows=(0, 456960))
+X = synth.config_c4(rows=(0, 453840))
 eng = CoverEngine(X, 0.5, 0.5, assoc="tcgen05_i8")
 eng.build_basis(0.5)
 best = 1e9

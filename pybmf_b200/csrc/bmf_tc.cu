@@ -77,6 +77,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
+// One elected lane of a CONVERGED warp (elect.sync).  The MMA issuer runs its loop with the whole warp so that every
+// operand of tcgen05.mma / tcgen05.commit is warp-uniform and lives in uniform registers; issuing from inside an
+// `if (lane == 0)` region instead makes the compiler wrap every instruction in an ELECT + R2UR.BROADCAST loop (7
+// moves per MMA), which made the ISSUER the bottleneck: 150 instead of 128 cycles per kind::mxf4 instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
@@ -275,29 +286,34 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer (whole warp, converged -- see elect_one) =====
+    {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t tb = warp_uniform(tmem_base), sb = warp_uniform(smem_base);
       for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);       // epilogue has drained this accumulator
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tb + (uint32_t)(acc * BN);
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(full_bar(stage), phase);              // TMA bytes have landed
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
+          const uint32_t a_addr = sb + stage * STAGE_BYTES;
           const uint64_t da = make_smem_desc(a_addr), db = make_smem_desc(a_addr + A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            tcgen05_mma_i8(d_tmem, da + (uint64_t)(k * (UMMA_K >> 4)), db + (uint64_t)(k * (UMMA_K >> 4)),
-                           IDESC_I8, (uint32_t)((kb | k) != 0));
-          tcgen05_commit(empty_bar(stage));               // smem slot free once these MMAs retire
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              tcgen05_mma_i8(d_tmem, da + (uint64_t)(k * (UMMA_K >> 4)), db + (uint64_t)(k * (UMMA_K >> 4)),
+                             IDESC_I8, (uint32_t)((kb | k) != 0));
+            tcgen05_commit(empty_bar(stage));             // smem slot free once these MMAs retire
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        tcgen05_commit(tfull_bar(acc));                   // accumulator complete -> epilogue
+        if (elect_one()) tcgen05_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -517,29 +533,34 @@ gemm_i8_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer (leader CTA only) =====
-    if (leader && lane == 0) {
+    // ===== MMA issuer (leader CTA only; whole warp, converged -- see elect_one) =====
+    if (leader) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t tb = warp_uniform(tmem_base), sb = warp_uniform(smem_base);
       for (int64_t t = pair; t < total_tiles; t += num_pairs) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tb + (uint32_t)(acc * BN);
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_base + stage * STAGE_BYTES2;
+          const uint32_t a_addr = sb + stage * STAGE_BYTES2;
           const uint64_t da = make_smem_desc(a_addr), db = make_smem_desc(a_addr + OP_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            tcgen05_mma_i8_2sm(d_tmem, da + (uint64_t)(k * (UMMA_K >> 4)), db + (uint64_t)(k * (UMMA_K >> 4)),
-                               IDESC_I8_2SM, (uint32_t)((kb | k) != 0));
-          tcgen05_commit_2sm(empty_bar(stage));           // frees the slot in BOTH CTAs
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              tcgen05_mma_i8_2sm(d_tmem, da + (uint64_t)(k * (UMMA_K >> 4)), db + (uint64_t)(k * (UMMA_K >> 4)),
+                                 IDESC_I8_2SM, (uint32_t)((kb | k) != 0));
+            tcgen05_commit_2sm(empty_bar(stage));         // frees the slot in BOTH CTAs
+          }
+          __syncwarp();
           if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
         }
-        tcgen05_commit_2sm(tfull_bar(acc));               // accumulator halves ready in BOTH CTAs
+        if (elect_one()) tcgen05_commit_2sm(tfull_bar(acc));   // accumulator halves ready in BOTH CTAs
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -801,6 +822,9 @@ gemm_f4_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           if (++stage == STAGES4) { stage = 0; phase ^= 1u; }
           continue;
 #endif
+#if defined(BMF_F4_TIMING_PROBE) && BMF_F4_TIMING_PROBE >= 3   /* MMA warp free-runs: no producer, no stage barriers */
+          break;
+#endif
           if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES4);
           const uint32_t a_dst = smem_base + stage * STAGE_BYTES4;
 #ifdef BMF_F4_TIMING_PROBE   /* timing experiment only: every tile re-reads tile (0, 0) -> operands always hit L2 */
@@ -814,29 +838,38 @@ gemm_f4_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader) {                                         // whole warp, converged (see elect_one)
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint32_t sfa = tmem_base + (uint32_t)SF_COL, sfb = tmem_base + (uint32_t)SF_COL + 8u;
+      const uint32_t tb = warp_uniform(tmem_base), sb = warp_uniform(smem_base);
+      const uint32_t sfa = tb + (uint32_t)SF_COL, sfb = tb + (uint32_t)SF_COL + 8u;
       for (int64_t t = pair; t < total_tiles; t += num_pairs) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN4);
+        const uint32_t d_tmem = tb + (uint32_t)(acc * BN4);
         for (int kb = 0; kb < kb_total; ++kb) {
+#if !defined(BMF_F4_TIMING_PROBE) || BMF_F4_TIMING_PROBE < 3
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_base + stage * STAGE_BYTES4;
+#endif
+          const uint32_t a_addr = sb + stage * STAGE_BYTES4;
           const uint64_t da = make_smem_desc(a_addr), db = make_smem_desc(a_addr + A_OP);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)                     // K = 64 elements = 32 bytes per MMA
-            tcgen05_mma_f4_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC_F4,
-                               (uint32_t)((kb | k) != 0), sfa, sfb);
-          tcgen05_commit_2sm(empty_bar(stage));
+            for (int k = 0; k < 4; ++k)                   // K = 64 elements = 32 bytes per MMA
+              tcgen05_mma_f4_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC_F4,
+                                 (uint32_t)((kb | k) != 0), sfa, sfb);
+#if !defined(BMF_F4_TIMING_PROBE) || BMF_F4_TIMING_PROBE < 3 || BMF_F4_TIMING_PROBE == 5
+            tcgen05_commit_2sm(empty_bar(stage));
+#endif
+          }
+          __syncwarp();
           if (++stage == STAGES4) { stage = 0; phase ^= 1u; }
         }
-        tcgen05_commit_2sm(tfull_bar(acc));
+        if (elect_one()) tcgen05_commit_2sm(tfull_bar(acc));
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -998,9 +1031,10 @@ gemm_f4s_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tcgen05_fence_after();
 
   if (warp == 0) {
-    if (lane == 0) {
+    {                                                     // whole warp, converged; one elected lane issues the TMA
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t sb = warp_uniform(smem_base);
       for (int64_t t = pair; t < total_tiles; t += num_pairs) {
         int mt, st;
         tile_coords(t, mt_total, st_total, group_m, mt, st);
@@ -1013,10 +1047,13 @@ gemm_f4s_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           for (int kb = 0; kb < kb_total; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t leader_full = full_bar(stage) & PEER_MASK;
-            if (leader) mbar_expect_tx(full_bar(stage), tx);
-            const uint32_t a_dst = smem_base + stage * STAGE_BYTES_S;
-            tma_load_2d_2sm(a_dst, &tmap_a, leader_full, kb * BK, mt * BM4 + (int)rank * HALFM, ea.policy_a);
-            tma_load_2d_2sm(a_dst + A_OP, mb, leader_full, kb * BK, row0, ea.policy_b);
+            const uint32_t a_dst = sb + stage * STAGE_BYTES_S;
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(full_bar(stage), tx);
+              tma_load_2d_2sm(a_dst, &tmap_a, leader_full, kb * BK, mt * BM4 + (int)rank * HALFM, ea.policy_a);
+              tma_load_2d_2sm(a_dst + A_OP, mb, leader_full, kb * BK, row0, ea.policy_b);
+            }
+            __syncwarp();
             if (++stage == STAGES_S) { stage = 0; phase ^= 1u; }
           }
         }
@@ -1024,30 +1061,35 @@ gemm_f4s_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader) {                                         // whole warp, converged (see elect_one)
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
-      const uint32_t sfa = tmem_base + (uint32_t)SF_COL_S, sfb = tmem_base + (uint32_t)SF_COL_S + 8u;
+      const uint32_t tb = warp_uniform(tmem_base), sb = warp_uniform(smem_base);
+      const uint32_t sfa = tb + (uint32_t)SF_COL_S, sfb = tb + (uint32_t)SF_COL_S + 8u;
       for (int64_t t = pair; t < total_tiles; t += num_pairs) {
 #pragma unroll 1
         for (int sub = 0; sub < 2; ++sub) {
           mbar_wait(tempty_bar(sub), acc_phase ^ 1u);
           tcgen05_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(sub ? SUB0 : 0);
+          const uint32_t d_tmem = tb + (uint32_t)(sub ? SUB0 : 0);
           const uint32_t idesc = sub ? idesc_f4(SUB1) : idesc_f4(SUB0);
           for (int kb = 0; kb < kb_total; ++kb) {
             mbar_wait(full_bar(stage), phase);
             tcgen05_fence_after();
-            const uint32_t a_addr = smem_base + stage * STAGE_BYTES_S;
+            const uint32_t a_addr = sb + stage * STAGE_BYTES_S;
             const uint64_t da = make_smem_desc(a_addr), db = make_smem_desc(a_addr + A_OP);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tcgen05_mma_f4_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                                 (uint32_t)((kb | k) != 0), sfa, sfb);
-            tcgen05_commit_2sm(empty_bar(stage));
+              for (int k = 0; k < 4; ++k)
+                tcgen05_mma_f4_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                   (uint32_t)((kb | k) != 0), sfa, sfb);
+              tcgen05_commit_2sm(empty_bar(stage));
+            }
+            __syncwarp();
             if (++stage == STAGES_S) { stage = 0; phase ^= 1u; }
           }
-          tcgen05_commit_2sm(tfull_bar(sub));
+          if (elect_one()) tcgen05_commit_2sm(tfull_bar(sub));
+          __syncwarp();
         }
         acc_phase ^= 1u;
       }
