@@ -5,10 +5,11 @@ import torch
 from pybmf_b200 import synth
 from pybmf_b200.engine import CoverEngine
 X = synth.config_c4()
-eng = CoverEngine(X, 0.5, 0.5)
+w = float(sys.argv[1]) if len(sys.argv) > 1 else 0.5
+eng = CoverEngine(X, w, 1 - w)
 eng.build_basis(0.5)
 print("operand", eng.operand, flush=True)
-for g in (16, 8, 12, 24, 32, 48, 16):
+for g in (16, 4, 8, 12, 24, 32, 16):
     os.environ["BMF_GROUP_M2"] = str(g)
     best = 1e9
     for _ in range(3):

@@ -267,19 +267,23 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_base_slot);
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer (whole warp, one elected lane issues) =====
+    {
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t sb = warp_uniform(smem_base);
       for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         int mt, nt;
         tile_coords(t, mt_total, nt_total, group_m, mt, nt);
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-          const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
-          tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * BK, mt * BM, ea.policy_a);
-          tma_load_2d(a_dst + A_BYTES, &tmap_b, full_bar(stage), kb * BK, nt * BN, ea.policy_b);
+          const uint32_t a_dst = sb + stage * STAGE_BYTES;
+          if (elect_one()) {
+            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+            tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * BK, mt * BM, ea.policy_a);
+            tma_load_2d(a_dst + A_BYTES, &tmap_b, full_bar(stage), kb * BK, nt * BN, ea.policy_b);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -513,20 +517,24 @@ gemm_i8_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_base_slot);
 
   if (warp == 0) {
-    // ===== TMA producer (both CTAs: own 128 candidate rows + own 128 data rows) =====
-    if (lane == 0) {
+    // ===== TMA producer (both CTAs: own 128 candidate rows + own 128 data rows; whole warp, one elected lane issues) =====
+    {
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t sb = warp_uniform(smem_base);
       for (int64_t t = pair; t < total_tiles; t += num_pairs) {
         int mt, nt;
         tile_coords(t, mt_total, nt_total, group_m, mt, nt);
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t leader_full = full_bar(stage) & PEER_MASK;
-          if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES2);     // bytes of both CTAs
-          const uint32_t a_dst = smem_base + stage * STAGE_BYTES2;
-          tma_load_2d_2sm(a_dst, &tmap_a, leader_full, kb * BK, mt * BM2 + (int)rank * HALF, ea.policy_a);
-          tma_load_2d_2sm(a_dst + OP_BYTES, &tmap_b, leader_full, kb * BK, nt * BN + (int)rank * HALF, ea.policy_b);
+          const uint32_t a_dst = sb + stage * STAGE_BYTES2;
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES2);     // bytes of both CTAs
+            tma_load_2d_2sm(a_dst, &tmap_a, leader_full, kb * BK, mt * BM2 + (int)rank * HALF, ea.policy_a);
+            tma_load_2d_2sm(a_dst + OP_BYTES, &tmap_b, leader_full, kb * BK, nt * BN + (int)rank * HALF, ea.policy_b);
+          }
+          __syncwarp();
           if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
         }
       }
@@ -808,30 +816,35 @@ gemm_f4_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   tcgen05_fence_after();
 
   if (warp == 0) {
-    if (lane == 0) {
+    {                                                     // whole warp, converged; one elected lane issues the TMA
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t sb = warp_uniform(smem_base);
       for (int64_t t = pair; t < total_tiles; t += num_pairs) {
         int mt, nt;
         tile_coords(t, mt_total, nt_total, group_m, mt, nt);
+#ifdef BMF_F4_TIMING_PROBE   /* timing experiment only: every tile re-reads tile (0, 0) -> operands always hit L2 */
+        mt = 0; nt = 0;
+#endif
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t leader_full = full_bar(stage) & PEER_MASK;
 #if defined(BMF_F4_TIMING_PROBE) && BMF_F4_TIMING_PROBE == 2   /* no operand traffic at all: MMA issue + pipe only */
-          if (leader) mbar_arrive(full_bar(stage));
+          if (leader && elect_one()) mbar_arrive(full_bar(stage));
+          __syncwarp();
           if (++stage == STAGES4) { stage = 0; phase ^= 1u; }
           continue;
 #endif
 #if defined(BMF_F4_TIMING_PROBE) && BMF_F4_TIMING_PROBE >= 3   /* MMA warp free-runs: no producer, no stage barriers */
           break;
 #endif
-          if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES4);
-          const uint32_t a_dst = smem_base + stage * STAGE_BYTES4;
-#ifdef BMF_F4_TIMING_PROBE   /* timing experiment only: every tile re-reads tile (0, 0) -> operands always hit L2 */
-          mt = 0; nt = 0;
-#endif
-          tma_load_2d_2sm(a_dst, &tmap_a, leader_full, kb * BK, mt * BM4 + (int)rank * HALFM, ea.policy_a);
-          tma_load_2d_2sm(a_dst + A_OP, &tmap_b, leader_full, kb * BK, nt * BN4 + (int)rank * HALFN, ea.policy_b);
+          const uint32_t a_dst = sb + stage * STAGE_BYTES4;
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES4);
+            tma_load_2d_2sm(a_dst, &tmap_a, leader_full, kb * BK, mt * BM4 + (int)rank * HALFM, ea.policy_a);
+            tma_load_2d_2sm(a_dst + A_OP, &tmap_b, leader_full, kb * BK, nt * BN4 + (int)rank * HALFN, ea.policy_b);
+          }
+          __syncwarp();
           if (++stage == STAGES4) { stage = 0; phase ^= 1u; }
         }
       }
