@@ -81,8 +81,20 @@ def csr_rows_view(X, r0: int, r1: int) -> sp.csr_matrix:
 
 
 def has_stored_zeros(X: sp.csr_matrix) -> bool:
-    """O(nnz) host scan of the value array (the pattern kernels treat every STORED entry as a one)."""
-    return bool(X.nnz) and X.data.dtype != np.bool_ and np.count_nonzero(X.data) != X.nnz
+    """O(nnz) host scan of the value array (the pattern kernels treat every STORED entry as a one).  Memory bound:
+    large arrays are scanned by a few threads (numpy releases the GIL inside count_nonzero)."""
+    if not X.nnz or X.data.dtype == np.bool_:
+        return False
+    data = X.data
+    if data.size < (1 << 22):
+        return np.count_nonzero(data) != data.size
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    nthreads = max(1, min(8, (os.cpu_count() or 1)))
+    bounds = np.linspace(0, data.size, nthreads + 1, dtype=np.int64)
+    with ThreadPoolExecutor(nthreads) as pool:
+        counts = list(pool.map(lambda ab: int(np.count_nonzero(data[ab[0]:ab[1]])), zip(bounds[:-1], bounds[1:])))
+    return sum(counts) != data.size
 
 
 def drop_stored_zeros(X: sp.csr_matrix) -> sp.csr_matrix:

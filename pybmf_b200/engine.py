@@ -185,10 +185,17 @@ class CoverEngine:
         self.tp_tot = 0
         self.fp_tot = 0
         self.launches = 0
+        self.prescored = False
 
     # ---- association + basis (Asso.py:191-235) -------------------------------------------------
-    def build_basis(self, tau: float):
+    def build_basis(self, tau: float, prescore: bool = False):
+        """Association + basis (+ operand planes).  prescore=True also enqueues the first greedy step's scoring pass
+        before the host-side stored-zero scan, so that the scan (0.09 s for 1e8 values) hides behind ~80 ms of GPU
+        work; the caller must then skip its first score_all() (`self.prescored`)."""
         self._build_basis(tau)                                 # enqueued, not waited for
+        if prescore:
+            self.score_all()
+        self.prescored = bool(prescore)
         Xl, self._host_rows = self._host_rows, None
         dirty = torch.tensor([1 if (Xl is not None and device.has_stored_zeros(Xl)) else 0], dtype=torch.int64,
                              device=device.dev())
@@ -206,6 +213,9 @@ class CoverEngine:
             self._host_rows = None
             self.launches += launches
             self._build_basis(tau)
+            if prescore:
+                self.score_all()
+            self.prescored = bool(prescore)
         nb = int(self.alive.sum().item())
         self.sum_x = int(self._ones[0].item())
         self.trace.mark("basis_wait")
@@ -392,24 +402,39 @@ class CoverEngine:
             self._cand_pop_host = self.cand_pop[: self.n].cpu().numpy()
         return int(self._cand_pop_host[j])
 
-    def gather_used_columns(self, ids) -> np.ndarray:
-        """Columns `ids` of U over ALL ranks' rows as uint8 [m, len(ids)] (one device all-gather)."""
+    def gather_used_words(self, ids):
+        """Bit columns `ids` of U over ALL ranks' rows, still packed: a list of (uint64 words [len(ids), w_r], rows_r),
+        one entry per rank in row order (one device all-gather + D2H; unpacking is host work, see unpack_used)."""
         if not ids:
-            return np.zeros((self.m, 0), np.uint8)
+            return []
         local = torch.stack([self.u_cols[i] for i in ids])                       # [c, words_m]
         if self.world == 1:
-            return np.ascontiguousarray(device.words_to_dense(local.cpu().numpy(), self.m_loc).T)
+            return [(local.cpu().numpy(), self.m_loc)]
         import torch.distributed as dist
         wmax = device.words_for(self.plan.rows(0)[1] - self.plan.rows(0)[0])
         padded = device.zeros((len(ids), wmax), torch.int64)
         padded[:, : local.shape[1]] = local
         parts = [torch.empty_like(padded) for _ in range(self.world)]
         dist.all_gather(parts, padded)
-        out = []
-        for r, part in enumerate(parts):
-            a0, a1 = self.plan.rows(r)
-            out.append(device.words_to_dense(part.cpu().numpy(), a1 - a0).T)
-        return np.ascontiguousarray(np.concatenate(out, axis=0))
+        both = torch.stack(parts).cpu().numpy()                                  # one D2H
+        return [(both[r], self.plan.rows(r)[1] - self.plan.rows(r)[0]) for r in range(self.world)]
+
+    @staticmethod
+    def unpack_used(parts, ncols_live) -> np.ndarray:
+        """Packed parts of gather_used_words -> uint8 [m, ncols_live]."""
+        if not parts:
+            return np.zeros((0, ncols_live), np.uint8)
+        return np.ascontiguousarray(np.concatenate([device.words_to_dense(w, rows).T for w, rows in parts], axis=0))
+
+    def gather_used_columns(self, ids) -> np.ndarray:
+        """Columns `ids` of U over ALL ranks' rows as uint8 [m, len(ids)]."""
+        if not ids:
+            return np.zeros((self.m, 0), np.uint8)
+        return self.unpack_used(self.gather_used_words(ids), len(ids))
+
+    def basis_words_host(self, js) -> np.ndarray:
+        idx = torch.as_tensor(list(js), dtype=torch.int64, device=device.dev())
+        return self.basis_bits[idx].cpu().numpy()
 
     # ---- cover rebuilt from a factor list (after the reference's truncation quirk D1) -----------
     def reset_cover(self, kept):

@@ -376,31 +376,39 @@ class Asso(BaseModel):
             self.__dict__.pop(name, None)
 
     def _materialize_factors(self, final=False):
-        """Device bit columns -> host csr (cheap); the reference's lil float64 containers are built
-        from that csr the first time `U` / `V` is read (csr -> lil of a 480189-row matrix costs ~0.5 s)."""
+        """Device bit columns -> host, still PACKED (one small D2H: k x m/8 bytes + the chosen basis rows).  The csr /
+        lil float64 containers of the reference are built from the packed bits the first time `U` / `V` is read
+        (unpacking 480189 x 20 bits and csr -> lil costs ~0.05 + 0.5 s on the host, none of it needed by fit())."""
         kept = self.__dict__.get("_dev_kept")
         if kept is None:
             return
         dev = self.__dict__.get("_dev")
         live = [(p, e) for p, e in enumerate(kept) if e is not None]
-        ncols = len(kept)
+        packed = None
         if live and dev is not None:
-            cols = dev.gather_used_columns([e["ui"] for _p, e in live])            # [m, len(live)] uint8
-            pos = np.array([p for p, _e in live], dtype=np.int64)
-            _r, c = np.nonzero(cols)                                               # row-major order = csr order
-            indptr = np.concatenate([[0], np.cumsum(cols.sum(axis=1, dtype=np.int64))])
-            Uc = csr_matrix((np.ones(len(c)), pos[c], indptr), shape=(self.m, ncols))
-            rows = dev.basis_rows_host([e["j"] for _p, e in live])                 # one D2H for all chosen basis rows
-            vr = [np.flatnonzero(row) for row in rows]
-            Vc = csr_matrix((np.ones(sum(len(v) for v in vr)),
-                             (np.concatenate(vr), np.repeat(pos, [len(v) for v in vr]))), shape=(self.n, ncols))
-        else:
-            Uc, Vc = csr_matrix((self.m, ncols)), csr_matrix((self.n, ncols))
+            packed = (dev.gather_used_words([e["ui"] for _p, e in live]),
+                      dev.basis_words_host([e["j"] for _p, e in live]),
+                      np.array([p for p, _e in live], dtype=np.int64))
         self.__dict__.pop("U", None)
         self.__dict__.pop("V", None)
-        self._host_factors = (Uc, Vc)
+        self._host_factors = (packed, len(kept))
         if final:
             self.__dict__.pop("_dev_kept", None)
+
+    def _unpack_host_factors(self):
+        """(packed bits, ncols) -> (U csr m x ncols, V csr n x ncols), float64 ones."""
+        packed, ncols = self._host_factors
+        if packed is None:
+            return csr_matrix((self.m, ncols)), csr_matrix((self.n, ncols))
+        parts, vwords, pos = packed
+        cols = CoverEngine.unpack_used(parts, len(pos))                            # [m, live] uint8
+        _r, c = np.nonzero(cols)                                                   # row-major order = csr order
+        indptr = np.concatenate([[0], np.cumsum(cols.sum(axis=1, dtype=np.int64))])
+        Uc = csr_matrix((np.ones(len(c)), pos[c], indptr), shape=(self.m, ncols))
+        vr = [np.flatnonzero(row) for row in device.words_to_dense(vwords, self.n)]
+        Vc = csr_matrix((np.ones(sum(len(v) for v in vr)),
+                         (np.concatenate(vr), np.repeat(pos, [len(v) for v in vr]))), shape=(self.n, ncols))
+        return Uc, Vc
 
     def __getattr__(self, name):
         d = self.__dict__
@@ -408,7 +416,7 @@ class Asso(BaseModel):
             if "_dev_kept" in d and "_dev" in d:
                 self._materialize_factors()
             if "_host_factors" in d:
-                Uc, Vc = d["_host_factors"]
+                Uc, Vc = self._unpack_host_factors()
                 d["U"], d["V"] = Uc.tolil(), Vc.tolil()
                 if "_dev_kept" not in d:
                     del d["_host_factors"]
@@ -425,7 +433,7 @@ class Asso(BaseModel):
         super().init_model()
         w_fn = 1 - self.w_fp if self.w_fn is None else self.w_fn
         self._dev = CoverEngine(self.X_train, self.w_fp, w_fn, scorer=self._scorer, assoc=self._assoc_kernel)
-        self._dev_nb = self._dev.build_basis(self.tau)
+        self._dev_nb = self._dev.build_basis(self.tau, prescore=True)
         self.__dict__.pop("assoc", None)
         self.__dict__.pop("basis", None)
 
@@ -449,7 +457,7 @@ class Asso(BaseModel):
         best_score = 0
         n_basis = self._dev_nb
         need_reset = False
-        prescored = False
+        prescored = dev.prescored                              # init_model already enqueued the first scoring pass
         while is_improving:
             best_score = 0 if k == 0 else best_score
             if n_basis == 0:
