@@ -557,6 +557,53 @@ def test_panel_kernels_match_row_stream_kernels(nat, m, n, k, monkeypatch):
     assert list(out["panel"][1]) == [int(tp), int(fp), int(fn)]
 
 
+def test_c5_scale_panel_kernels_properties(nat, monkeypatch):
+    """BASELINE configs[4] scale (200k x 100k bits, k = 64; the 1M-row point runs in bench.py --workload c5 with the same
+    checks): the column-panel kernels equal the row-stream kernels bit for bit, the two confusion forms agree, and
+    TP + FN = |X|, TP + FP = |product|."""
+    _native, device = nat
+    m, n, k = 200_000, 100_000, 64
+    words = device.words_for(n)
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+
+    def rnd(shape, ands):
+        w = torch.randint(-2 ** 63, 2 ** 63 - 1, shape, dtype=torch.int64, device="cuda", generator=g)
+        for _ in range(ands - 1):
+            w &= torch.randint(-2 ** 63, 2 ** 63 - 1, shape, dtype=torch.int64, device="cuda", generator=g)
+        return w
+    uw = rnd((m, 1), 5)                                             # ~2 of 64 factors per row
+    vt = rnd((k, words), 5)
+    vt[:, n // 64] &= (1 << (n % 64)) - 1
+    vt[:, (n + 63) // 64:] = 0
+    out = {}
+    for tag, env in (("panel", "0"), ("rows", "1")):
+        monkeypatch.setenv("BMF_NO_PANEL", env)
+        pd = device.zeros((m, words), torch.int64)
+        _native.call("bmf_bool_product", uw, m, 1, vt, k, words, pd)
+        out[tag] = pd
+    assert torch.equal(out["panel"], out["rows"])
+    pd = out["panel"]
+    del out
+    x = pd ^ rnd((m, words), 4)                                     # ground truth = product with ~6 % of the bits flipped
+    x[:, n // 64] &= (1 << (n % 64)) - 1
+    x[:, (n + 63) // 64:] = 0
+    c_bits = device.zeros((3,), torch.int64)
+    _native.call("bmf_confusion_bits", x, pd, m, words, -1, c_bits, None, None)
+    tp, fp, fn = (int(v) for v in c_bits.cpu().numpy())
+    ones_x = tp + fn
+    for env in ("0", "1"):
+        monkeypatch.setenv("BMF_NO_PANEL", env)
+        for known in (-1, ones_x):
+            c = device.zeros((3,), torch.int64) + 3
+            _native.call("bmf_confusion_factors", x, m, words, uw, 1, vt, k, known, c, None, None)
+            assert [int(v) for v in c.cpu().numpy()] == [tp, fp, fn]
+    cx = device.zeros((3,), torch.int64)
+    _native.call("bmf_confusion_bits", x, x, m, words, -1, cx, None, None)
+    cp = device.zeros((3,), torch.int64)
+    _native.call("bmf_confusion_bits", pd, pd, m, words, -1, cp, None, None)
+    assert int(cx[0].item()) == tp + fn and int(cp[0].item()) == tp + fp
+
+
 def test_confusion_triplets(nat):
     _native, device = nat
     rng = np.random.RandomState(8)
