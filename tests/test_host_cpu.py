@@ -33,7 +33,17 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     from pybmf_b200 import build as B
     sass = subprocess.run(["cuobjdump", "-sass", B.build()], capture_output=True, text=True).stdout
     assert "UTCIMMA" in sass, "tcgen05.mma kind::i8 missing from SASS"
-    assert "UTMALDG" in sass and "LDTM" in sass
+    assert "UTCOMMA" in sass, "tcgen05.mma kind::mxf4 (block-scaled FP4) missing from SASS"
+    assert "UTMALDG" in sass and "LDTM" in sass and "STTM" in sass and "UBLKCP" in sass   # TMA tiles, TMEM ld/st, bulk copy
+    # the four MMAs of a pipeline stage must be issued back to back with uniform-register operands: an ELECT + R2UR loop
+    # between them (what `if (lane == 0)` issue produces) made the issuing thread the bottleneck (profiles/r01c_fp4_issue_rate.md)
+    lines = [ln for ln in sass.splitlines() if "/*" in ln and ";" in ln]
+    ops = [ln.split("*/")[1].strip().split()[0] if "*/" in ln else "" for ln in lines]
+    runs = best = 0
+    for op in ops:
+        runs = runs + 1 if op.startswith("UTCOMMA") else 0
+        best = max(best, runs)
+    assert best >= 4, "FP4 MMAs are no longer issued back to back (found runs of %d)" % best
 
 
 def test_no_compute_without_gpu_fails_loudly():
