@@ -329,9 +329,11 @@ class Asso(BaseModel):
     """The Asso algorithm (Miettinen et al., the discrete basis problem) -- PyBMF/models/Asso.py:10-140.
 
     Parameters are the reference's: `tau`, `k=None`, `tol=0`, `w_fp=0.5`, `w_fn=None` (= 1 - w_fp).
-    Extra keyword-only knobs of this build (not in the reference): `scorer` in
-    {'auto', 'tcgen05', 'popc'} and `assoc_kernel` in {'auto', 'tcgen05', 'popc'} choose
-    between the tensor-core and the bit-packed popcount kernels (both sm_100a CUDA).
+    Extra keyword-only knobs of this build (not in the reference): `scorer` in {'auto', 'tcgen05', 'tcgen05_f4',
+    'tcgen05_i8', 'popc'} and `assoc_kernel` in {'auto', 'tcgen05', 'tcgen05_f4', 'tcgen05_i8', 'popc'} choose between
+    the tensor-core kernels (FP4 `kind::mxf4` when the operand values are E2M1 numbers -- every a/2^s weight pair with
+    a, a+b in {1, 2, 3, 4, 6}, and all non-dyadic weights -- else int8 `kind::i8`) and the bit-packed popcount kernels
+    (all sm_100a CUDA; results are identical).
     """
 
     def __init__(self, tau, k=None, tol=0, w_fp=0.5, w_fn=None, *, scorer="auto", assoc_kernel="auto"):
