@@ -691,8 +691,15 @@ __device__ __forceinline__ void tmem_ld_32x32_x8(uint32_t taddr, uint32_t (&v)[8
 }
 __device__ __forceinline__ int f32_bits_to_int(uint32_t bits) { return __float2int_rn(__uint_as_float(bits)); }
 
+// The general-weights epilogue does ~20 dependent instructions per element (F2I, I2F.F64, DMUL, DADD, DSETP) and, with
+// one epilogue warp per scheduler, ran at IPC ~0.2: it -- not the tensor pipe -- bounded EPI_GAIN2 (168 instead of 128
+// cycles per MMA).  EPI_GAIN2 therefore runs EIGHT epilogue warps (two per TMEM lane quadrant, each taking half of the
+// tile's data rows), so every scheduler has two warps to hide those latencies with.
+template <int EPI> struct F4Threads { static constexpr int value = (EPI == EPI_GAIN2) ? 320 : NUM_THREADS; };
+
 // One FP32 accumulator tile (this thread's TMEM lane = candidate `row`, 240 columns) through the fused epilogue.
 // EPI_GAIN2 on FP4 tiles: 120 data rows per tile, P in columns [0, 120), Q in [120, 240)
+template <int NEPI>
 __device__ __forceinline__ void stage_row_state_f4(RowState* rs, int acc, int et, int nt, const EpiArgs& ea) {
   if (et < HALFN) {
     const int64_t i = (int64_t)nt * HALFN + et;
@@ -708,16 +715,19 @@ __device__ __forceinline__ void stage_row_state_f4(RowState* rs, int acc, int et
     }
     rs[acc * 128 + et] = r;
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");
 }
 
+// `half` (EPI_GAIN2 only): which half of the tile's data rows this warp takes (chunks of 8 rows: [0, 8) and [8, 15))
 template <int EPI>
-__device__ __forceinline__ void epilogue_tile_f4(uint32_t taddr, int64_t row, int nt, const RowState* rs, const EpiArgs& ea) {
+__device__ __forceinline__ void epilogue_tile_f4(uint32_t taddr, int64_t row, int nt, const RowState* rs, const EpiArgs& ea,
+                                                 int half) {
   if (EPI == EPI_GAIN2) {
     const int pop = ea.cand_pop[row];
     long long sum_p = 0, sum_n = 0;
+    const int c_begin = half ? 8 : 0, c_end = half ? HALFN / 8 : 8;
 #pragma unroll 1
-    for (int c = 0; c < HALFN / 8; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
       uint32_t vp[8], vq[8];
       tmem_ld_32x32_x8(taddr + (uint32_t)(c * 8), vp);
       tmem_ld_32x32_x8(taddr + (uint32_t)(HALFN + c * 8), vq);
@@ -766,7 +776,7 @@ __device__ __forceinline__ void epilogue_tile_f4(uint32_t taddr, int64_t row, in
 }
 
 template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F4Threads<EPI>::value, 1)
 gemm_f4_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    int mt_total, int nt_total, int kb_total, int group_m, const EpiArgs ea) {
   extern __shared__ uint8_t smem_raw[];
@@ -788,8 +798,9 @@ gemm_f4_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const int64_t total_tiles = (int64_t)mt_total * nt_total;
 
   if (threadIdx.x == 0) {
+    constexpr int EPI_WARPS = F4Threads<EPI>::value / 32 - 2;               // 4, or 8 for EPI_GAIN2
     for (int s = 0; s < STAGES4; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
@@ -805,7 +816,7 @@ gemm_f4_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_base_slot);
-  if (warp >= 2) {                                        // unit scale factors: all 128 lanes x columns [480, 512)
+  if (warp >= 2 && warp < 6) {                            // unit scale factors: all 128 lanes x columns [480, 512)
     const uint32_t sf_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)SF_COL;
 #pragma unroll
     for (int c = 0; c < 4; ++c) tmem_st_32x32_x8(sf_addr + (uint32_t)(c * 8), SF_ONE);
@@ -894,12 +905,12 @@ gemm_f4_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     for (int64_t t = pair; t < total_tiles; t += num_pairs) {
       int mt, nt;
       tile_coords(t, mt_total, nt_total, group_m, mt, nt);
-      if (EPI == EPI_GAIN2) stage_row_state_f4(row_state, acc, (int)threadIdx.x - 64, nt, ea);
+      if (EPI == EPI_GAIN2) stage_row_state_f4<F4Threads<EPI>::value - 64>(row_state, acc, (int)threadIdx.x - 64, nt, ea);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN4);
       const int64_t row = (int64_t)mt * BM4 + (int64_t)rank * HALFM + quad * 32 + lane;
-      epilogue_tile_f4<EPI>(taddr, row, nt, row_state + acc * 128, ea);
+      epilogue_tile_f4<EPI>(taddr, row, nt, row_state + acc * 128, ea, (warp - 2) >> 2);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
@@ -940,7 +951,7 @@ static int launch_gemm_f4(const uint8_t* a, int64_t a_rows, const uint8_t* b, in
   const int pairs = (int)(tiles < pairs_max ? tiles : pairs_max);
   int group_m = 16;
   if (const char* e = getenv("BMF_GROUP_M2")) { int v = atoi(e); if (v >= 1 && v <= 64) group_m = v; }
-  gemm_f4_2sm_kernel<EPI><<<2 * pairs, NUM_THREADS, SMEM_BYTES4, stream>>>(ma, mb, mt, nt, kb, group_m, ea);
+  gemm_f4_2sm_kernel<EPI><<<2 * pairs, F4Threads<EPI>::value, SMEM_BYTES4, stream>>>(ma, mb, mt, nt, kb, group_m, ea);
   return check_cuda(cudaGetLastError(), "gemm_f4_2sm_kernel launch");
 }
 
