@@ -18,6 +18,7 @@
 //   warp 0: TMA producer (one lane)      warp 1: TMEM allocator + MMA issuer (one lane)
 //   warps 2-5: epilogue (TMEM lane quadrant = warp_id % 4)
 #include <cuda.h>
+#include <math.h>
 #include <stdlib.h>
 
 #include "bmf_common.cuh"
@@ -54,6 +55,8 @@ struct EpiArgs {
   int64_t m_rows;                  // EPI_GAIN2: true number of data rows (the rest is padding)
   double neg_w_fp, w_fn;           // EPI_GAIN2
   uint64_t policy_a, policy_b;     // L2 eviction policy of the candidate (A) and data-row (B) TMA loads
+  long long w_fn_fix, w_fp_fix;    // EPI_GAIN2 (FP4): round(w * 2^20) for the fixed-point pre-decision of the row test
+  int fix_ok;                      // ... usable: weights finite and |w| < 1024
 };
 struct __align__(16) RowState { double s_old; int tpo; int fpo; };
 
@@ -726,6 +729,15 @@ __device__ __forceinline__ void epilogue_tile_f4(uint32_t taddr, int64_t row, in
     const int pop = ea.cand_pop[row];
     long long sum_p = 0, sum_n = 0;
     const int c_begin = half ? 8 : 0, c_end = half ? HALFN / 8 : 8;
+    // B200's vector FP64 pipe is narrow: evaluating the fp64 row test for all 8.5e9 elements of a step bounds the kernel
+    // (math-pipe throttle = 66 % of the stall samples).  So each element is first decided in fixed point:
+    //   d = round(w_fn 2^20) P - round(w_fp 2^20) N  differs from 2^20 (w_fn P - w_fp N) by at most (P + N) / 2, and the fp64
+    //   evaluation of s_new - s_old is off by < 2^-35, hence |d| > P + N + 2 fixes the outcome of the fp64 comparison;
+    // only the undecided elements (exact or near ties such as 0.8 P = 0.2 N) go through the literal fp64 expression, one
+    // per lane and pass, so the number of fp64 passes per chunk is the LARGEST per-lane count, not the number of
+    // elements that are undecided in some lane.  The result is identical to evaluating fp64 everywhere.
+    const long long w_fn_fix = ea.w_fn_fix, w_fp_fix = ea.w_fp_fix;
+    const bool fix_ok = ea.fix_ok != 0;
 #pragma unroll 1
     for (int c = c_begin; c < c_end; ++c) {
       uint32_t vp[8], vq[8];
@@ -733,14 +745,28 @@ __device__ __forceinline__ void epilogue_tile_f4(uint32_t taddr, int64_t row, in
       tmem_ld_32x32_x8(taddr + (uint32_t)(HALFN + c * 8), vq);
       tmem_ld_wait();
       int part_p = 0, part_n = 0;
+      int P[8], N[8];
+      uint32_t undecided = 0;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const RowState r = rs[c * 8 + q];
-        const int P = f32_bits_to_int(vp[q]);
-        const int N = pop - f32_bits_to_int(vq[q]) - P;
-        const bool use = cover_score_f64(ea.neg_w_fp, ea.w_fn, r.fpo + N, r.tpo + P) > r.s_old;
-        part_p += use ? P : 0;
-        part_n += use ? N : 0;
+        P[q] = f32_bits_to_int(vp[q]);
+        N[q] = pop - f32_bits_to_int(vq[q]) - P[q];
+        const long long d = w_fn_fix * P[q] - w_fp_fix * N[q];
+        const int margin = P[q] + N[q] + 2;
+        const bool use = d > margin;
+        if (!fix_ok || (d <= margin && d >= -margin)) undecided |= 1u << q;
+        else { part_p += use ? P[q] : 0; part_n += use ? N[q] : 0; }
+      }
+      while (__any_sync(0xffffffffu, undecided != 0)) {     // fp64 passes: one undecided element per lane and pass
+        if (undecided) {
+          const int q = __ffs((int)undecided) - 1;
+          undecided &= undecided - 1;
+          int Pq = 0, Nq = 0;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) if (e == q) { Pq = P[e]; Nq = N[e]; }
+          const RowState r = rs[c * 8 + q];
+          if (cover_score_f64(ea.neg_w_fp, ea.w_fn, r.fpo + Nq, r.tpo + Pq) > r.s_old) { part_p += Pq; part_n += Nq; }
+        }
       }
       sum_p += part_p;
       sum_n += part_n;
@@ -1343,5 +1369,10 @@ extern "C" int bmf_cover_score_f4_general(const uint8_t* cand_plane, int64_t can
   ea.m_rows = m;
   ea.neg_w_fp = -w_fp;
   ea.w_fn = w_fn;
+  const bool fix_ok = (w_fp == w_fp) && (w_fn == w_fn) && w_fp > -1024.0 && w_fp < 1024.0 && w_fn > -1024.0 && w_fn < 1024.0;
+  const char* no_fix = getenv("BMF_NO_FIXED_PREDECISION");
+  ea.fix_ok = (fix_ok && !(no_fix && no_fix[0] == '1')) ? 1 : 0;
+  ea.w_fp_fix = fix_ok ? llrint(w_fp * 1048576.0) : 0;
+  ea.w_fn_fix = fix_ok ? llrint(w_fn * 1048576.0) : 0;
   return tc::f4::launch_gemm_f4<tc::EPI_GAIN2>(cand_plane, cand_pad, pq_plane, plane_rows, ld_bytes, ea, as_stream(stream));
 }

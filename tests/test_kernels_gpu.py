@@ -250,9 +250,12 @@ def test_cover_score_i8_general_tcgen05(nat, m, n, w, gemm_variant):
 
 @pytest.mark.parametrize("m,n,w", [(70, 50, (0.2, 0.8)), (300, 200, (0.3, 0.6)), (121, 257, (0.2, 0.8)),
                                    (3000, 1100, (0.15, 0.85))])
-def test_cover_score_f4_general_tcgen05(nat, m, n, w):
+@pytest.mark.parametrize("no_fix", ["0", "1"])
+def test_cover_score_f4_general_tcgen05(nat, m, n, w, no_fix, monkeypatch):
     """general weights on the FP4 pipe: packed E2M1 P/Q planes in blocks of 120 rows, fp64 row test in the epilogue;
-    the plane kept current by bmf_cover_apply_f4_general equals a fresh expansion"""
+    the plane kept current by bmf_cover_apply_f4_general equals a fresh expansion.  no_fix = 1 switches off the fixed-point
+    pre-decision of the row test (fp64 for every element): both must equal the oracle"""
+    monkeypatch.setenv("BMF_NO_FIXED_PREDECISION", no_fix)
     _native, device = nat
     X, C, B, alive = _cover_inputs(m * 13 + n, m, n)
     alive[:] = 1
