@@ -492,7 +492,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": desc, "m": m, "n": n, "nnz": int(X.nnz), "candidates": nb, "scorer": args.scorer,
                            "parallelism": "rows sharded over %d rank(s), one int64 all-reduce per step" % world,
-                           "l2": "operand planes (%.1f GB) exceed L2; no flush needed" % (m * float(n) / 1e9)},
+                           "l2": "operand planes (%.1f GB) exceed L2; no flush needed" % (m * float(n) / (2e9 if operand == "f4" else 1e9))},
                 "clocks": clocks, "gpu_launches": launches, "setup_seconds": setup_s,
                 "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
                 "fit_seconds": e2e["fit_seconds"] if e2e else None}
