@@ -79,6 +79,43 @@ def test_integer_weights_agree_with_oracle():
     assert integer_weights(0.2, 0.8) is None and integer_weights(200.0, 1.0) is None
 
 
+def test_csr_row_views_and_stored_zero_scan():
+    """host side of the row sharding: zero-copy row ranges and the (threaded) stored-zero scan"""
+    import numpy as np
+    import scipy.sparse as sp
+    from pybmf_b200 import device
+    X = sp.random(700, 300, density=0.1, format="csr", random_state=3)
+    X.data[:] = 1
+    for r0, r1 in ((0, 700), (0, 256), (256, 512), (512, 700), (700, 700), (5, 5)):
+        V = device.csr_rows_view(X, r0, r1)
+        assert V.shape == (r1 - r0, 300) and (V.toarray() == X[r0:r1].toarray()).all()
+        if r1 > r0 and (r0, r1) != (0, 700):
+            assert np.shares_memory(V.indices, X.indices)            # a view, not a copy
+    assert not device.has_stored_zeros(X)
+    big = sp.csr_matrix((np.ones(1 << 23, dtype=np.int64), np.zeros(1 << 23, dtype=np.int32), np.array([0, 1 << 23])),
+                        shape=(1, 1))
+    assert not device.has_stored_zeros(big)                          # threaded path
+    big.data[(1 << 23) - 7] = 0
+    assert device.has_stored_zeros(big)
+    Y = X.copy()
+    Y.data[11] = 0
+    assert device.has_stored_zeros(Y) and device.drop_stored_zeros(Y).nnz == X.nnz - 1
+
+
+def test_e2m1_codes_gate_the_fp4_path():
+    """bmf_e2m1_code is a host function: which small integers the FP4 operand planes can hold exactly"""
+    from pybmf_b200 import _native
+    lib = _native.load()
+    want = {0: 0, 1: 2, 2: 4, 3: 5, 4: 6, 6: 7}
+    for v in range(-2, 130):
+        assert lib.bmf_e2m1_code(v) == want.get(v, -1), v
+    # decode the E2M1 bit patterns (sign 1, exponent 2, mantissa 1) to check the table itself
+    def e2m1(code):
+        e, m = (code >> 1) & 3, code & 1
+        return (0.5 * m) if e == 0 else (1 + 0.5 * m) * 2 ** (e - 1)
+    assert all(e2m1(c) == v for v, c in want.items())
+
+
 def test_shard_plan():
     from pybmf_b200.engine import ROW_ALIGN, ShardPlan
     for m, world in [(480189, 8), (480189, 4), (480189, 2), (480189, 1), (1000, 8), (6040, 4), (3, 2), (256, 2)]:
