@@ -143,9 +143,11 @@ class CoverEngine:
         lib = _native.load()
         f4_ok = (enc == "pq") or (self.integer_mode and enc == "zero" and lib.bmf_e2m1_code(self.wa) >= 0
                                   and lib.bmf_e2m1_code(self.wa + self.wb) >= 0)       # the P/Q planes are 0/1: always fine
+        if max(self.wa + self.wb, 1) * self.n >= (1 << 24):    # every partial sum must stay an exact FP32 integer
+            f4_ok = False
         if operand == "f4" and scorer == "tcgen05" and not f4_ok:
             raise ValueError("the FP4 scorer needs integer weights whose values wa=%d and wa+wb=%d are E2M1 numbers "
-                             "(0, 1, 2, 3, 4, 6)" % (self.wa, self.wa + self.wb))
+                             "(0, 1, 2, 3, 4, 6) and (wa+wb)*n < 2^24" % (self.wa, self.wa + self.wb))
         self.operand = "f4" if (scorer == "tcgen05" and f4_ok and operand in ("auto", "f4")) else "i8"
         if assoc in ("tcgen05_i8", "tcgen05_f4"):
             self.assoc_operand, assoc = assoc[-2:], "tcgen05"
