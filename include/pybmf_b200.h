@@ -137,13 +137,15 @@ int bmf_cover_score_i8_general(const int8_t* cand_plane, int64_t cand_pad, const
  * code or returns -1 when E2M1 cannot represent it (the caller then stays on the int8 kernels).
  * bmf_gemm_f4_nt: c[i][j] = sum_k a[i][k]*b[j][k] as int32 (a rows multiple of 256, b rows multiple of 240, or
  * of 496 = BMF_F4_SUPER_ROWS, which selects the faster super-tile kernel; likewise rows_pad of bmf_cover_score_f4).
+ * accumulate != 0 (496-padded b rows only): c += ..., so K (the data rows of X^T X) can be split over several launches
+ * and the association of one row chunk overlaps the host-to-device copy of the next.
  * bmf_cover_score_f4: the zero-dominant encoding of bmf_cover_score_i8 (sign = +1) on f4 planes. */
 int bmf_e2m1_code(int32_t value);
 int bmf_expand_bits_f4(const uint64_t* bits, const uint64_t* mask_bits, int64_t rows, int64_t ncols, int64_t words,
                        int32_t one, int32_t zero, int32_t masked, uint8_t* plane, int64_t rows_pad, int64_t ld_bytes,
                        bmf_stream_t stream);
 int bmf_gemm_f4_nt(const uint8_t* a_plane, int64_t a_rows_pad, const uint8_t* b_plane, int64_t b_rows_pad,
-                   int64_t ld_bytes, int32_t* c, int64_t ldc, bmf_stream_t stream);
+                   int64_t ld_bytes, int32_t* c, int64_t ldc, int32_t accumulate, bmf_stream_t stream);
 int bmf_cover_score_f4(const uint8_t* cand_plane, int64_t cand_pad, const uint8_t* rows_plane, int64_t rows_pad,
                        int64_t ld_bytes, const int32_t* cand_pop, int32_t bias_scale, int64_t* gain,
                        bmf_stream_t stream);

@@ -35,7 +35,7 @@ SIGNATURES = {
     "bmf_cover_apply_general": [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _f64, _f64, _p, _i64, _p, _p, _p],
     "bmf_e2m1_code": [_i32],
     "bmf_expand_bits_f4": [_p, _p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _i64, _i64, _p],
-    "bmf_gemm_f4_nt": [_p, _i64, _p, _i64, _i64, _p, _i64, _p],
+    "bmf_gemm_f4_nt": [_p, _i64, _p, _i64, _i64, _p, _i64, _i32, _p],
     "bmf_cover_score_f4": [_p, _i64, _p, _i64, _i64, _p, _i32, _p, _p],
     "bmf_cover_apply_f4": [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i32, _i32, _p, _i64, _i32, _p, _p, _p],
     "bmf_expand_bits_pq_f4": [_p, _p, _i64, _i64, _i64, _p, _i64, _p],

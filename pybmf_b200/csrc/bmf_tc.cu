@@ -50,6 +50,7 @@ struct EpiArgs {
   unsigned long long* gain_n;      // EPI_GAIN2: sum_use N
   int32_t* C;                      // EPI_STORE
   int64_t ldc;
+  int accumulate;                  // EPI_STORE (FP4 super-tile kernel): C += D instead of C = D (K split over launches)
   const int32_t* tp_old;           // EPI_GAIN2: per data row counts of the current cover
   const int32_t* fp_old;
   int64_t m_rows;                  // EPI_GAIN2: true number of data rows (the rest is padding)
@@ -1020,10 +1021,20 @@ __device__ __forceinline__ void epilogue_cols_f4(uint32_t taddr, int64_t row, in
       relu_sum += part;
     } else {
       int4* dst = reinterpret_cast<int4*>(ea.C + row * ea.ldc + col0 + c * 16);
-      dst[0] = make_int4(f32_bits_to_int(lo[0]), f32_bits_to_int(lo[1]), f32_bits_to_int(lo[2]), f32_bits_to_int(lo[3]));
-      dst[1] = make_int4(f32_bits_to_int(lo[4]), f32_bits_to_int(lo[5]), f32_bits_to_int(lo[6]), f32_bits_to_int(lo[7]));
-      dst[2] = make_int4(f32_bits_to_int(hi[0]), f32_bits_to_int(hi[1]), f32_bits_to_int(hi[2]), f32_bits_to_int(hi[3]));
-      dst[3] = make_int4(f32_bits_to_int(hi[4]), f32_bits_to_int(hi[5]), f32_bits_to_int(hi[6]), f32_bits_to_int(hi[7]));
+      int4 o[4];
+      o[0] = make_int4(f32_bits_to_int(lo[0]), f32_bits_to_int(lo[1]), f32_bits_to_int(lo[2]), f32_bits_to_int(lo[3]));
+      o[1] = make_int4(f32_bits_to_int(lo[4]), f32_bits_to_int(lo[5]), f32_bits_to_int(lo[6]), f32_bits_to_int(lo[7]));
+      o[2] = make_int4(f32_bits_to_int(hi[0]), f32_bits_to_int(hi[1]), f32_bits_to_int(hi[2]), f32_bits_to_int(hi[3]));
+      o[3] = make_int4(f32_bits_to_int(hi[4]), f32_bits_to_int(hi[5]), f32_bits_to_int(hi[6]), f32_bits_to_int(hi[7]));
+      if (ea.accumulate) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int4 p = dst[q];
+          o[q].x += p.x; o[q].y += p.y; o[q].z += p.z; o[q].w += p.w;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[q] = o[q];
     }
   }
   if (EPI == EPI_GAIN && relu_sum != 0) atomicAdd(ea.gain + row, (unsigned long long)relu_sum);
@@ -1308,7 +1319,7 @@ extern "C" int bmf_cover_score_i8_general(const int8_t* cand_plane, int64_t cand
 
 // ---- FP4 (kind::mxf4) entry points -------------------------------------------------------------------
 extern "C" int bmf_gemm_f4_nt(const uint8_t* a_plane, int64_t a_rows_pad, const uint8_t* b_plane, int64_t b_rows_pad,
-                              int64_t ld_bytes, int32_t* c, int64_t ldc, bmf_stream_t stream) {
+                              int64_t ld_bytes, int32_t* c, int64_t ldc, int32_t accumulate, bmf_stream_t stream) {
   BMF_REQUIRE(a_plane && b_plane && c, "bmf_gemm_f4_nt: null pointer");
   BMF_REQUIRE(a_rows_pad > 0 && a_rows_pad % tc::f4::BM4 == 0, "bmf_gemm_f4_nt: a rows must be a positive multiple of 256");
   BMF_REQUIRE(b_rows_pad > 0 && (b_rows_pad % tc::f4::BN4 == 0 || b_rows_pad % tc::f4::SUPER_ROWS == 0),
@@ -1318,6 +1329,9 @@ extern "C" int bmf_gemm_f4_nt(const uint8_t* a_plane, int64_t a_rows_pad, const 
   tc::EpiArgs ea = {};
   ea.C = c;
   ea.ldc = ldc;
+  ea.accumulate = accumulate ? 1 : 0;
+  BMF_REQUIRE(!accumulate || (b_rows_pad % tc::f4::SUPER_ROWS == 0 && !tc::f4::super_tiles_disabled()),
+              "bmf_gemm_f4_nt: accumulate needs b rows padded to 496 (super-tile kernel)");
   if (b_rows_pad % tc::f4::SUPER_ROWS == 0 && !tc::f4::super_tiles_disabled())
     return tc::f4::launch_gemm_f4s<tc::EPI_STORE>(a_plane, a_rows_pad, b_plane, b_rows_pad, ld_bytes, ea, as_stream(stream));
   BMF_REQUIRE(b_rows_pad % tc::f4::BN4 == 0, "bmf_gemm_f4_nt: b rows must be a multiple of 240 for the plain-tile kernel");

@@ -162,8 +162,14 @@ class CoverEngine:
         self.ld = device.round_up(self.n, 128)                  # K extent of the int8 cover planes (bytes)
         self.ld4 = device.round_up(self.n, 256) // 2            # ... of the packed FP4 planes (bytes)
         m_alloc = max(self.m_loc, 1)
-        self._ip, self._ix = device.upload_csr(Xl)
-        self.x_bits = device.pack_csr(self._ip, self._ix, self.m_loc, self.n)
+        self.cnt = None
+        self.launches = 0
+        self._ip = self._ix = None
+        if self.assoc_kind == "tcgen05" and self.assoc_operand == "f4" and self.m_loc > 0:
+            self._upload_pack_associate(Xl)                     # chunked: H2D of chunk c+1 overlaps X^T X of chunk c
+        else:
+            self._ip, self._ix = device.upload_csr(Xl)
+            self.x_bits = device.pack_csr(self._ip, self._ix, self.m_loc, self.n)
         ones = device.zeros((3,), torch.int64)
         if self.m_loc > 0:                                      # |X| of this rank's rows: TP of X against itself
             _native.call("bmf_confusion_bits", self.x_bits, self.x_bits, self.m_loc, self.words, -1, ones, None, None)
@@ -183,10 +189,8 @@ class CoverEngine:
         self.gain_n = device.zeros((self.cand_pad,), torch.int64)
         self.record = device.zeros((8,), torch.int64)           # [winner, score bits, used, sumP, sumN]
         self.u_cols = []                                        # device bit vectors, one per chosen factor
-        self.cnt = None
         self.tp_tot = 0
         self.fp_tot = 0
-        self.launches = 0
         self.prescored = False
 
     # ---- association + basis (Asso.py:191-235) -------------------------------------------------
@@ -223,20 +227,66 @@ class CoverEngine:
         self.trace.mark("basis_wait")
         return nb
 
+    def _cnt_shape(self):
+        n_pad = device.round_up(self.n, 256)
+        return n_pad, max(n_pad, device.round_up(self.n, F4_ROW_PAD))   # the FP4 kernel walks data rows in super tiles of 496
+
+    def _upload_pack_associate(self, Xl: sp.csr_matrix):
+        """FP4 association path: the csr rows go up in a few chunks on a copy stream; as soon as a chunk has landed the
+        main stream packs its bit rows, packs / expands its slice of X^T (K = the chunk's rows) and ACCUMULATES that
+        slice's X^T X into cnt, while the (host-blocking, pageable) copy of the next chunk is in flight.  At c4 the copy
+        (38 ms) and the association (36 ms) used to run back to back."""
+        n, m_loc = self.n, self.m_loc
+        n_pad, ldc = self._cnt_shape()
+        d = device.dev()
+        self.x_bits = device.zeros((m_loc, self.words), torch.int64)
+        cnt = device.zeros((n_pad, ldc), torch.int32)
+        nchunks = 3 if Xl.nnz >= (1 << 24) else 1
+        step = device.round_up(-(-m_loc // nchunks), 256)      # chunk boundaries: multiples of 256 rows (K tiles, bit words)
+        main = torch.cuda.current_stream()
+        copy = torch.cuda.Stream() if nchunks > 1 else main
+        indptr, indices = Xl.indptr, Xl.indices
+        first = True
+        for a in range(0, m_loc, step):
+            b = min(a + step, m_loc)
+            ia, ib = int(indptr[a]), int(indptr[b])
+            ip_h = torch.from_numpy(np.ascontiguousarray((indptr[a:b + 1] - indptr[a]).astype(np.int64, copy=False)))
+            ix_h = torch.from_numpy(np.ascontiguousarray(indices[ia:ib].astype(np.int32, copy=False)))
+            with torch.cuda.stream(copy):
+                ip_d, ix_d = ip_h.to(d, non_blocking=True), ix_h.to(d, non_blocking=True)
+                landed = torch.cuda.Event()
+                landed.record(copy)
+            main.wait_event(landed)
+            ip_d.record_stream(main)
+            ix_d.record_stream(main)
+            rows = b - a
+            if ib > ia:
+                _native.call("bmf_pack_csr", ip_d, ix_d, rows, n, 0, self.x_bits[a:b], self.words)
+                xt_bits = device.pack_csr(ip_d, ix_d, rows, n, transposed=True)            # [n, words(rows)]
+                ldk = device.round_up(rows, 256) // 2
+                xt_plane = device.empty((max(n_pad, ldc), ldk), torch.uint8)
+                _native.call("bmf_expand_bits_f4", xt_bits, None, n, rows, xt_bits.shape[1], 2, 0, 0, xt_plane,
+                             xt_plane.shape[0], ldk)
+                _native.call("bmf_gemm_f4_nt", xt_plane, n_pad, xt_plane, device.round_up(n, F4_ROW_PAD), ldk, cnt, ldc,
+                             0 if first else 1)
+                first = False
+                self.launches += 4
+                del xt_plane, xt_bits
+        self.cnt = cnt
+
     def _build_basis(self, tau: float):
         n, m_loc = self.n, self.m_loc
-        n_pad = device.round_up(n, 256)
-        ldc = max(n_pad, device.round_up(n, F4_ROW_PAD))       # the FP4 kernel walks data rows in super tiles of 496
-        cnt = device.zeros((n_pad, ldc), torch.int32)
-        if m_loc > 0:
+        n_pad, ldc = self._cnt_shape()
+        cnt = self.cnt if self.cnt is not None else device.zeros((n_pad, ldc), torch.int32)
+        if m_loc > 0 and self.cnt is None:
             xt_bits = device.pack_csr(self._ip, self._ix, m_loc, n, transposed=True)
             if self.assoc_kind == "tcgen05" and self.assoc_operand == "f4":
-                # X^T as packed E2M1 0/1; A operand = rows padded to 256, B operand = the same plane padded to 240
+                # X^T as packed E2M1 0/1; A operand = rows padded to 256, B operand = the same plane padded to 496
                 ldk = device.round_up(m_loc, 256) // 2
                 xt_plane = device.empty((max(n_pad, ldc), ldk), torch.uint8)
                 _native.call("bmf_expand_bits_f4", xt_bits, None, n, m_loc, xt_bits.shape[1], 2, 0, 0, xt_plane,
                              xt_plane.shape[0], ldk)
-                _native.call("bmf_gemm_f4_nt", xt_plane, n_pad, xt_plane, device.round_up(n, F4_ROW_PAD), ldk, cnt, ldc)
+                _native.call("bmf_gemm_f4_nt", xt_plane, n_pad, xt_plane, device.round_up(n, F4_ROW_PAD), ldk, cnt, ldc, 0)
                 del xt_plane
             elif self.assoc_kind == "tcgen05":
                 xt_plane = device.expand_bits_i8(xt_bits, n, m_loc, 1, 0, 256)

@@ -358,8 +358,11 @@ def test_gemm_f4_tcgen05_exact(nat, ma, nb, k, monkeypatch):
             continue
         monkeypatch.setenv("BMF_F4_NO_SUPER", no_super)
         c = device.zeros((ma, nb), torch.int32) - 1
-        _native.call("bmf_gemm_f4_nt", a_d, ma, b_d, nb, ld_bytes, c, nb)
+        _native.call("bmf_gemm_f4_nt", a_d, ma, b_d, nb, ld_bytes, c, nb, 0)
         assert np.array_equal(c.cpu().numpy().astype(np.int64), want)
+        if no_super == "0" and nb % 496 == 0:                         # accumulate mode: c += a b^T
+            _native.call("bmf_gemm_f4_nt", a_d, ma, b_d, nb, ld_bytes, c, nb, 1)
+            assert np.array_equal(c.cpu().numpy().astype(np.int64), 2 * want)
 
 
 @pytest.mark.parametrize("rows,ncols", [(5, 70), (300, 500), (241, 257)])
