@@ -137,8 +137,10 @@ int bmf_cover_score_i8_general(const int8_t* cand_plane, int64_t cand_pad, const
  * code or returns -1 when E2M1 cannot represent it (the caller then stays on the int8 kernels).
  * bmf_gemm_f4_nt: c[i][j] = sum_k a[i][k]*b[j][k] as int32 (a rows multiple of 256, b rows multiple of 240, or
  * of 496 = BMF_F4_SUPER_ROWS, which selects the faster super-tile kernel; likewise rows_pad of bmf_cover_score_f4).
- * accumulate != 0 (496-padded b rows only): c += ..., so K (the data rows of X^T X) can be split over several launches
- * and the association of one row chunk overlaps the host-to-device copy of the next.
+ * accumulate bit 0 (496-padded b rows only): c += ..., so K (the data rows of X^T X) can be split over several launches
+ * and the association of one row chunk overlaps the host-to-device copy of the next.  accumulate bit 1 (a_plane ==
+ * b_plane, i.e. X^T X): the product is symmetric, super tiles entirely below the diagonal are skipped (their part of c
+ * is left untouched) -- see bmf_basis_threshold_rows(symmetric).
  * bmf_cover_score_f4: the zero-dominant encoding of bmf_cover_score_i8 (sign = +1) on f4 planes. */
 int bmf_e2m1_code(int32_t value);
 int bmf_expand_bits_f4(const uint64_t* bits, const uint64_t* mask_bits, int64_t rows, int64_t ncols, int64_t words,
@@ -193,6 +195,50 @@ int bmf_cover_apply_general(const uint64_t* x_bits, uint64_t* c_bits, int64_t m,
                             const uint64_t* basis_bits, uint8_t* alive, const int64_t* winner, int32_t* tp_old,
                             int32_t* fp_old, double w_fp, double w_fn, int8_t* pq_plane, int64_t ld,
                             uint64_t* u_bits, int64_t* totals, bmf_stream_t stream);
+
+/* ---- device-resident greedy loop (Asso._fit, PyBMF/models/Asso.py:62-110, without a host round trip per step) ----
+ * bmf_greedy_select is bmf_select_first_max with the loop state in device memory:
+ *   state[0] = bits of the inherited best score (Asso.py:71), [1] = TP total, [2] = FP total of the cover,
+ *   [3] = stopped (a step found no improving candidate: Asso.py:98-100), [4] = number of steps selected.
+ *   table_row (8 x int64, one per greedy step): winner, score bits, #used rows, sum P, sum N, TP total after,
+ *   FP total after, status (0 no winner, 1 winner chosen / counters pending, 2 complete).
+ * `tail` = (#used, sum P, sum N) of the PREVIOUS step's apply summed over all ranks -- the three counters ride at the
+ * end of the all-reduced gain vector, so a step needs one collective -- and is folded into state / prev_row first;
+ * tail_zero (the rank-local copy, may alias tail) and *nused are cleared for the coming apply.  first != 0 resets
+ * the threshold to 0 (step 0).  table_row == NULL only folds the counters (the flush after the last step).
+ * The winner is removed from alive[] here (Asso.py:106-107) and written to record[0] for bmf_cover_apply*.
+ *
+ * bmf_cover_apply_compact = bmf_cover_apply (integer weights) plus, for INCREMENTAL rescoring, the operand-plane rows of
+ * the used data rows before (comp_old) and after (comp_new) the update, compacted at slots drawn from *nused
+ * (kind 1: packed E2M1 codes v_one / v_zero / v_covered, kind 2: int8 values; kind 0: no compaction), rows
+ * [*nused, round_up(*nused, tile_rows)) zeroed.  Only rows the winner uses change state, hence
+ *   gain_j(t+1) = gain_j(t) - sum_{i used} relu(D_ij(t)) + sum_{i used} relu(D_ij(t+1)),
+ * which bmf_cover_rescore_f4 / _i8 add to the running gain vector (gain_sign = -1 on comp_old, +1 on comp_new; the
+ * kernels are the scoring GEMMs with the row-tile count read from *dyn_rows; gain is NOT cleared).
+ * Optional extras: u_words/kw/factor_bit (bit of the row-major usage words), vt_row (copy of the winner's basis row). */
+int bmf_greedy_select(const int64_t* gain_p, const int64_t* gain_n, const int64_t* tail, int64_t* tail_zero,
+                      uint8_t* alive, int64_t n, int32_t wa, int32_t wb, double scale, double w_fp, double w_fn,
+                      int32_t first, int64_t* state, int64_t* table_row, int64_t* prev_row, int64_t* record,
+                      int32_t* nused, bmf_stream_t stream);
+int bmf_cover_apply_compact(const uint64_t* x_bits, uint64_t* c_bits, int64_t m, int64_t n, int64_t words,
+                            const uint64_t* basis_bits, uint8_t* alive, const int64_t* winner, int32_t* tp_old,
+                            int32_t* fp_old, int32_t wa, int32_t wb, int32_t kind, int32_t v_one, int32_t v_zero,
+                            int32_t v_covered, uint8_t* comp_old, uint8_t* comp_new, int64_t comp_ld, int64_t comp_cap,
+                            int32_t tile_rows, int32_t* nused, uint64_t* u_bits, uint64_t* u_words, int64_t kw,
+                            int32_t factor_bit, uint64_t* vt_row, int64_t* totals, bmf_stream_t stream);
+int bmf_cover_rescore_f4(const uint8_t* cand_plane, int64_t cand_pad, const uint8_t* compact_plane, int64_t rows_cap,
+                         int64_t ld_bytes, const int32_t* cand_pop, int32_t bias_scale, const int32_t* dyn_rows,
+                         int32_t gain_sign, int64_t* gain, bmf_stream_t stream);
+int bmf_cover_rescore_i8(const int8_t* cand_plane, int64_t cand_pad, const int8_t* compact_plane, int64_t rows_cap,
+                         int64_t ld, int32_t sign, const int32_t* cand_pop, int32_t bias_scale, const int32_t* dyn_rows,
+                         int32_t gain_sign, int64_t* gain, bmf_stream_t stream);
+/* bmf_basis_threshold on a row window [row0, row0 + nrows) (all pointers at row row0): with the rows of X sharded, every
+ * rank thresholds the block of X^T X it received from the reduce-scatter and the bit rows are all-gathered.
+ * symmetric != 0 (row0 = 0): entries below the diagonal were skipped by bmf_gemm_f4_nt(accumulate bit 1) and are read
+ * as cnt[min(i,j)][max(i,j)]. */
+int bmf_basis_threshold_rows(const int32_t* cnt_rows, int64_t ldc, int64_t n, int64_t row0, int64_t nrows,
+                             int32_t symmetric, double tau, uint64_t* basis_rows, int64_t words, uint8_t* alive_rows,
+                             int32_t* pop_rows, bmf_stream_t stream);
 
 /* ---- Boolean product and confusion counts ------------------------------------------------
  * get_prediction / matmul(boolean=True): PyBMF/utils/common.py:98-107, boolean_utils.py:61-84.

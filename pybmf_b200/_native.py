@@ -48,6 +48,12 @@ SIGNATURES = {
     "bmf_confusion_bits": [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p],
     "bmf_bits_combine": [_p, _p, _i64, _i64, C.c_int, _p, _p],
     "bmf_confusion_triplets": [_p, _p, _p, _i64, _p, _i64, _p, _p, _p],
+    "bmf_greedy_select": [_p, _p, _p, _p, _p, _i64, _i32, _i32, _f64, _f64, _f64, _i32, _p, _p, _p, _p, _p, _p],
+    "bmf_cover_apply_compact": [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p,
+                                _i64, _i64, _i32, _p, _p, _p, _i64, _i32, _p, _p, _p],
+    "bmf_cover_rescore_f4": [_p, _i64, _p, _i64, _i64, _p, _i32, _p, _i32, _p, _p],
+    "bmf_cover_rescore_i8": [_p, _i64, _p, _i64, _i64, _i32, _p, _i32, _p, _i32, _p, _p],
+    "bmf_basis_threshold_rows": [_p, _i64, _i64, _i64, _i64, _i32, _f64, _p, _i64, _p, _p, _p],
     "bmf_refine_column": [_p, _i64, _i64, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _f64, _f64, _p, _p],
 }
 

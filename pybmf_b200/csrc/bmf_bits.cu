@@ -64,6 +64,29 @@ __device__ __forceinline__ uint32_t spread8(uint32_t x) {
   return x;
 }
 
+// 32 data bits + 32 mask bits -> 32 E2M1 codes (16 bytes): `masked` where the mask bit is set, else `one` / `zero`
+__device__ __forceinline__ uint4 f4_codes32(uint32_t b32, uint32_t k32, uint32_t valid, uint32_t one, uint32_t zero,
+                                            uint32_t masked) {
+  const uint32_t s_one = b32 & ~k32 & valid, s_zero = ~b32 & ~k32 & valid, s_mask = k32 & valid;
+  uint32_t out[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    out[q] = spread8((s_one >> (8 * q)) & 0xFFu) * one + spread8((s_zero >> (8 * q)) & 0xFFu) * zero +
+             spread8((s_mask >> (8 * q)) & 0xFFu) * masked;
+  return make_uint4(out[0], out[1], out[2], out[3]);
+}
+// 16 data bits + 16 mask bits -> 16 int8 values
+__device__ __forceinline__ uint4 i8_bytes16(uint32_t b16, uint32_t k16, uint32_t valid16, int one, int zero, int masked) {
+  uint32_t out[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    int v = 0;
+    if ((valid16 >> i) & 1u) v = ((k16 >> i) & 1u) ? masked : (((b16 >> i) & 1u) ? one : zero);
+    out[i >> 2] |= (uint32_t)(uint8_t)(int8_t)v << ((i & 3) * 8);
+  }
+  return make_uint4(out[0], out[1], out[2], out[3]);
+}
+
 // 32 bits -> 32 E2M1 codes (16 bytes) per thread, one 128-bit store; element k of a row lives in byte k/2,
 // low nibble for even k
 __global__ void expand_bits_f4_kernel(const uint64_t* __restrict__ bits, const uint64_t* __restrict__ mask,
@@ -207,15 +230,20 @@ __global__ void __launch_bounds__(256) assoc_counts_popc_kernel(const uint64_t* 
 }
 
 // basis bit (i, j) = cnt[i][j] / cnt[i][i] > tau, one warp per row, one 64-bit word per lane pass
-__global__ void basis_threshold_kernel(const int32_t* __restrict__ cnt, int64_t ldc, int64_t n, double tau,
+// Rows [row0, row0 + nrows) of the n x n matrix; cnt / basis_bits / cand_plane / alive / row_pop point at row row0
+// (multi-GPU: every rank thresholds the row block it received from the reduce-scatter).  symmetric != 0 (row0 = 0
+// only): the counts below the diagonal were never computed, cnt[i][j] is read as cnt[min][max].
+__global__ void basis_threshold_kernel(const int32_t* __restrict__ cnt, int64_t ldc, int64_t n, int64_t row0,
+                                       int64_t nrows, int symmetric, double tau,
                                        uint64_t* __restrict__ basis_bits, int64_t words,
                                        int8_t* __restrict__ cand_plane, int64_t ld,
                                        uint8_t* __restrict__ alive, int32_t* __restrict__ row_pop) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t i = warp0; i < n; i += nwarps) {
-    const int32_t si = cnt[i * ldc + i];
+  for (int64_t i = warp0; i < nrows; i += nwarps) {
+    const int64_t gi = row0 + i;                 // global row = diagonal column
+    const int32_t si = cnt[i * ldc + gi];
     const double s = (double)si;
     int any = 0, pop = 0;
     for (int64_t w = 0; w < words; ++w) {       // each pass: 2 x 32 columns -> one word
@@ -224,7 +252,10 @@ __global__ void basis_threshold_kernel(const int32_t* __restrict__ cnt, int64_t 
       for (int h = 0; h < 2; ++h) {
         const int64_t j = w * 64 + h * 32 + lane;
         bool bit = false;
-        if (j < n && si > 0) bit = ((double)cnt[i * ldc + j] / s) > tau;   // IEEE division, strict >
+        if (j < n && si > 0) {
+          const int32_t cij = (symmetric && j < gi) ? cnt[j * ldc + gi] : cnt[i * ldc + j];
+          bit = ((double)cij / s) > tau;                                     // IEEE division, strict >
+        }
         if (cand_plane != nullptr && j < ld) cand_plane[i * ld + j] = bit ? 1 : 0;
         const uint32_t bal = __ballot_sync(0xffffffffu, bit);
         word |= (uint64_t)bal << (h * 32);
@@ -392,19 +423,155 @@ select_first_max_kernel(const int64_t* __restrict__ gain_p, const int64_t* __res
 }
 
 // =========================================================================================
+// The argmax of a DEVICE-RESIDENT greedy loop: the inherited threshold, the running TP / FP totals and the per-step
+// result table live in device memory, so k greedy steps are enqueued back to back without a host round trip.
+//   state[0] = bits of the inherited best score, [1] = TP total, [2] = FP total, [3] = stopped, [4] = steps selected
+//   table row (8 x int64): winner, score bits, #used rows, sum P, sum N, TP total after, FP total after, status
+//   status: 0 = no winner, 1 = winner chosen (counters pending), 2 = complete
+// `tail` holds (#used, sum P, sum N) of the PREVIOUS step's apply, already summed over the ranks (it travels at the end
+// of the all-reduced gain vector, so a step needs ONE collective); they are folded into the state and the previous
+// table row first.  tail_zero (the local copy) and *nused are cleared for the coming apply.
+// =========================================================================================
+__global__ void __launch_bounds__(1024)
+greedy_select_kernel(const int64_t* __restrict__ gain_p, const int64_t* __restrict__ gain_n,
+                     const long long* __restrict__ tail, long long* __restrict__ tail_zero,
+                     uint8_t* __restrict__ alive, int64_t n, int wa, int wb, double scale, double neg_w_fp,
+                     double w_fn, int first, long long* __restrict__ state, long long* __restrict__ row,
+                     long long* __restrict__ prev_row, long long* __restrict__ record, int* __restrict__ nused) {
+  __shared__ double s_val[32];
+  __shared__ long long s_idx[32];
+  __shared__ long long s_tp, s_fp;
+  __shared__ int s_go;
+  if (threadIdx.x == 0) {
+    long long tp = state[1], fp = state[2];
+    if (prev_row != nullptr && prev_row[7] == 1) {
+      const long long used = tail[0], sp = tail[1], sn = tail[2];
+      tp += sp;
+      fp += sn;
+      state[1] = tp;
+      state[2] = fp;
+      prev_row[2] = used; prev_row[3] = sp; prev_row[4] = sn; prev_row[5] = tp; prev_row[6] = fp; prev_row[7] = 2;
+    }
+    if (tail_zero != nullptr) { tail_zero[0] = 0; tail_zero[1] = 0; tail_zero[2] = 0; }
+    if (nused != nullptr) *nused = 0;
+    s_tp = tp;
+    s_fp = fp;
+    s_go = (row != nullptr) && state[3] == 0;
+    if (!s_go) {
+      record[0] = -1;
+      if (row != nullptr) { row[0] = -1; row[7] = 0; }
+    }
+  }
+  __syncthreads();
+  if (!s_go) return;
+  const long long tp_tot = s_tp, fp_tot = s_fp;
+  const long long base_int = (long long)wb * tp_tot - (long long)wa * fp_tot;
+  double best = 0.0;
+  long long idx = -1;
+  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+    if (!alive[j]) continue;
+    double sc;
+    if (wa | wb)
+      sc = __dmul_rn((double)(base_int + gain_p[j]), scale);
+    else
+      sc = __dadd_rn(__dmul_rn(neg_w_fp, (double)(fp_tot + gain_n[j])),
+                     __dmul_rn(w_fn, (double)(tp_tot + gain_p[j])));
+    if (idx < 0 || sc > best) { best = sc; idx = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (oi >= 0 && (idx < 0 || ov > best || (ov == best && oi < idx))) { best = ov; idx = oi; }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_val[warp] = best; s_idx[warp] = idx; }
+  __syncthreads();
+  if (warp == 0) {
+    best = s_val[lane];
+    idx = s_idx[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (oi >= 0 && (idx < 0 || ov > best || (ov == best && oi < idx))) { best = ov; idx = oi; }
+    }
+    if (lane == 0) {
+      const double best_score = first ? 0.0 : __longlong_as_double(state[0]);       // Asso.py:71
+      if (idx >= 0 && !(best > best_score)) idx = -1;                                // Asso.py:94 `score > best_score`
+      const long long bits = __double_as_longlong(idx >= 0 ? best : best_score);
+      record[0] = idx;
+      record[1] = bits;
+      row[0] = idx;
+      row[1] = bits;
+      row[2] = 0; row[3] = 0; row[4] = 0; row[5] = tp_tot; row[6] = fp_tot;
+      row[7] = idx >= 0 ? 1 : 0;
+      if (idx >= 0) {
+        state[0] = bits;
+        alive[idx] = 0;                                                              // Asso.py:106-107
+      } else {
+        state[3] = 1;                                                                // nothing improves: the loop is over
+      }
+      state[4] += 1;
+    }
+  }
+}
+
+// rows [*nused, round_up(*nused, tile)) of both compact planes := 0, so that the last (partial) row tile of the
+// incremental GEMMs sees padding rows (which score relu(-bias) = 0)
+__global__ void compact_tail_zero_kernel(uint8_t* __restrict__ a, uint8_t* __restrict__ b, int64_t ld, int64_t cap,
+                                         const int* __restrict__ nused, int tile) {
+  const int64_t used = *nused < cap ? *nused : cap;
+  int64_t end = (used + tile - 1) / tile * tile;
+  if (end > cap) end = cap;
+  const int64_t chunks = ld >> 4;
+  const int64_t total = (end - used) * chunks;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = used + t / chunks, ch = t % chunks;
+    reinterpret_cast<uint4*>(a + r * ld)[ch] = z;
+    reinterpret_cast<uint4*>(b + r * ld)[ch] = z;
+  }
+}
+
+// =========================================================================================
 // apply the chosen candidate: one warp per data row, 128-bit row streams
 // =========================================================================================
+// Extras of the device-resident greedy loop (all optional, zero-initialised = the plain kernel):
+//  * compaction for incremental rescoring: every USED row's operand-plane row is written twice, as it was before the
+//    update (comp_old) and as it is after (comp_new), at a slot drawn from the device counter *nused; the scoring GEMM
+//    then runs over those few rows only: gain += sum relu(new) - sum relu(old).  The rows are generated from the bit
+//    rows (x, c) with the same codes bmf_expand_bits_* uses, so the big plane need not be kept current.
+//  * u_words: bit `factor_bit` of the row-major usage words (the form bmf_confusion_factors / bmf_bool_product read);
+//  * vt_row: a copy of the winner's basis row (row `factor_bit` of the selected-V^T matrix).
+struct ApplyExtra {
+  uint8_t* comp_old;
+  uint8_t* comp_new;
+  int64_t comp_ld;          // bytes per compact row
+  int64_t comp_cap;         // rows the buffers hold
+  int* nused;               // device counter, zeroed by bmf_greedy_select
+  int comp_kind;            // 0 none, 1 packed E2M1, 2 int8
+  int v_one, v_zero, v_cov; // operand values (E2M1 codes for kind 1, int8 values for kind 2)
+  uint64_t* u_words;
+  int64_t kw;
+  int factor_bit;
+  uint64_t* vt_row;
+};
+
 __global__ void __launch_bounds__(256)
 cover_apply_kernel(const uint64_t* __restrict__ xb, uint64_t* __restrict__ cb, int64_t m, int64_t n,
                    int64_t words, const uint64_t* __restrict__ basis, uint8_t* __restrict__ alive,
                    const int64_t* __restrict__ winner, int32_t* __restrict__ tp_old,
                    int32_t* __restrict__ fp_old, int wa, int wb, double neg_w_fp, double w_fn,
                    int8_t* __restrict__ rows_plane, int64_t ld, int covered_value, int pq_layout,
-                   unsigned long long* __restrict__ u_bits, unsigned long long* __restrict__ totals) {
+                   unsigned long long* __restrict__ u_bits, unsigned long long* __restrict__ totals,
+                   const ApplyExtra ex) {
   const int64_t j = *winner;
   if (j < 0) return;
   const uint64_t* __restrict__ b = basis + j * words;
   const int lane = threadIdx.x & 31;
+  if (ex.vt_row != nullptr && blockIdx.x == 0)
+    for (int64_t q = threadIdx.x; q < words; q += blockDim.x) ex.vt_row[q] = b[q];
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t pairs = words >> 1;
@@ -422,10 +589,46 @@ cover_apply_kernel(const uint64_t* __restrict__ xb, uint64_t* __restrict__ cb, i
     N = warp_sum(N) - P;
     const int tpo = tp_old[i], fpo = fp_old[i];
     if (!row_uses(wa, wb, neg_w_fp, w_fn, tpo, fpo, P, N)) continue;    // warp-uniform
+    int64_t slot = -1;
+    if (ex.comp_kind) {
+      int s0 = 0;
+      if (lane == 0) s0 = atomicAdd(ex.nused, 1);
+      s0 = __shfl_sync(0xffffffffu, s0, 0);
+      slot = s0 < ex.comp_cap ? s0 : -1;                                // capacity = all rows: never exceeded
+    }
     for (int64_t p = lane; p < pairs; p += 32) {
       ulonglong2* cp = reinterpret_cast<ulonglong2*>(cb + i * words + 2 * p);
       ulonglong2 c = *cp;
       const ulonglong2 v = ld_words2(b + 2 * p);
+      if (slot >= 0) {                                                  // this row before / after the update
+        const ulonglong2 x = ld_words2(xb + i * words + 2 * p);
+        const uint64_t xw[2] = {x.x, x.y}, cw[2] = {c.x, c.y}, nw[2] = {c.x | v.x, c.y | v.y};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int64_t col0 = (2 * p + h) * 64;
+          const int64_t left = n - col0;
+          const uint64_t valid = left >= 64 ? ~0ull : (left <= 0 ? 0ull : ((1ull << left) - 1ull));
+          if (ex.comp_kind == 1) {                                      // 64 bits -> 32 bytes of packed E2M1
+            uint4* o = reinterpret_cast<uint4*>(ex.comp_old + slot * ex.comp_ld + (2 * p + h) * 32);
+            uint4* q = reinterpret_cast<uint4*>(ex.comp_new + slot * ex.comp_ld + (2 * p + h) * 32);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const uint32_t x32 = (uint32_t)(xw[h] >> (32 * g)), vd = (uint32_t)(valid >> (32 * g));
+              o[g] = f4_codes32(x32, (uint32_t)(cw[h] >> (32 * g)), vd, ex.v_one, ex.v_zero, ex.v_cov);
+              q[g] = f4_codes32(x32, (uint32_t)(nw[h] >> (32 * g)), vd, ex.v_one, ex.v_zero, ex.v_cov);
+            }
+          } else {                                                      // 64 bits -> 64 int8
+            uint4* o = reinterpret_cast<uint4*>(ex.comp_old + slot * ex.comp_ld + (2 * p + h) * 64);
+            uint4* q = reinterpret_cast<uint4*>(ex.comp_new + slot * ex.comp_ld + (2 * p + h) * 64);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t x16 = (uint32_t)(xw[h] >> (16 * g)) & 0xffffu, vd = (uint32_t)(valid >> (16 * g)) & 0xffffu;
+              o[g] = i8_bytes16(x16, (uint32_t)(cw[h] >> (16 * g)) & 0xffffu, vd, ex.v_one, ex.v_zero, ex.v_cov);
+              q[g] = i8_bytes16(x16, (uint32_t)(nw[h] >> (16 * g)) & 0xffffu, vd, ex.v_one, ex.v_zero, ex.v_cov);
+            }
+          }
+        }
+      }
       if (rows_plane != nullptr) {
         uint64_t s0 = v.x & ~c.x, s1 = v.y & ~c.y;                      // newly covered columns
         if (!pq_layout) {
@@ -475,6 +678,7 @@ cover_apply_kernel(const uint64_t* __restrict__ xb, uint64_t* __restrict__ cb, i
       tp_old[i] = tpo + P;
       fp_old[i] = fpo + N;
       atomicOr(u_bits + (i >> 6), 1ull << (i & 63));
+      if (ex.u_words != nullptr) ex.u_words[i * ex.kw + (ex.factor_bit >> 6)] |= 1ull << (ex.factor_bit & 63);
       t_used += 1; t_p += P; t_n += N;
     }
   }
@@ -1082,9 +1286,25 @@ extern "C" int bmf_basis_threshold(const int32_t* cnt, int64_t ldc, int64_t n, d
   BMF_REQUIRE(words % 2 == 0 && words * 64 >= n, "bmf_basis_threshold: words must be even and cover n");
   BMF_REQUIRE(cand_plane == nullptr || (ld % 128 == 0 && ld >= n), "bmf_basis_threshold: bad ld");
   int64_t blocks = ceil_div(n, 8);
-  basis_threshold_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(cnt, ldc, n, tau, basis_bits, words,
+  basis_threshold_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(cnt, ldc, n, 0, n, 0, tau, basis_bits, words,
                                                                         cand_plane, ld, alive, row_pop);
   BMF_LAUNCH_CHECK("bmf_basis_threshold");
+  return 0;
+}
+
+extern "C" int bmf_basis_threshold_rows(const int32_t* cnt_rows, int64_t ldc, int64_t n, int64_t row0, int64_t nrows,
+                                        int32_t symmetric, double tau, uint64_t* basis_rows, int64_t words,
+                                        uint8_t* alive_rows, int32_t* pop_rows, bmf_stream_t stream) {
+  BMF_REQUIRE(cnt_rows && basis_rows && alive_rows && n > 0 && ldc >= n, "bmf_basis_threshold_rows: bad arguments");
+  BMF_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= n, "bmf_basis_threshold_rows: row window outside the matrix");
+  BMF_REQUIRE(words % 2 == 0 && words * 64 >= n, "bmf_basis_threshold_rows: words must be even and cover n");
+  BMF_REQUIRE(!symmetric || row0 == 0, "bmf_basis_threshold_rows: the symmetric read needs the whole matrix (row0 = 0)");
+  if (nrows == 0) return 0;
+  int64_t blocks = ceil_div(nrows, 8);
+  basis_threshold_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(cnt_rows, ldc, n, row0, nrows, symmetric ? 1 : 0,
+                                                                        tau, basis_rows, words, nullptr, 0, alive_rows,
+                                                                        pop_rows);
+  BMF_LAUNCH_CHECK("bmf_basis_threshold_rows");
   return 0;
 }
 
@@ -1133,7 +1353,7 @@ static int launch_cover_apply(const uint64_t* x_bits, uint64_t* c_bits, int64_t 
                               const uint64_t* basis_bits, uint8_t* alive, const int64_t* winner, int32_t* tp_old,
                               int32_t* fp_old, int32_t wa, int32_t wb, double w_fp, double w_fn, int8_t* rows_plane,
                               int64_t ld, int covered_value, int pq_layout, uint64_t* u_bits, int64_t* totals,
-                              bmf_stream_t stream) {
+                              bmf_stream_t stream, const ApplyExtra& ex = ApplyExtra{}) {
   BMF_REQUIRE(x_bits && c_bits && basis_bits && alive && winner && tp_old && fp_old && u_bits && totals,
               "bmf_cover_apply: null pointer");
   BMF_REQUIRE(m > 0 && n > 0 && words % 2 == 0 && words * 64 >= n, "bmf_cover_apply: bad shape");
@@ -1144,8 +1364,50 @@ static int launch_cover_apply(const uint64_t* x_bits, uint64_t* c_bits, int64_t 
   cover_apply_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
       x_bits, c_bits, m, n, words, basis_bits, alive, winner, tp_old, fp_old, wa, wb, -w_fp, w_fn, rows_plane,
       ld, covered_value, pq_layout, reinterpret_cast<unsigned long long*>(u_bits),
-      reinterpret_cast<unsigned long long*>(totals));
+      reinterpret_cast<unsigned long long*>(totals), ex);
   BMF_LAUNCH_CHECK("bmf_cover_apply");
+  return 0;
+}
+
+extern "C" int bmf_greedy_select(const int64_t* gain_p, const int64_t* gain_n, const int64_t* tail, int64_t* tail_zero,
+                                 uint8_t* alive, int64_t n, int32_t wa, int32_t wb, double scale, double w_fp,
+                                 double w_fn, int32_t first, int64_t* state, int64_t* table_row, int64_t* prev_row,
+                                 int64_t* record, int32_t* nused, bmf_stream_t stream) {
+  BMF_REQUIRE(gain_p && alive && state && record && n > 0, "bmf_greedy_select: bad arguments");
+  BMF_REQUIRE((wa | wb) != 0 || gain_n != nullptr, "bmf_greedy_select: general mode needs gain_n");
+  BMF_REQUIRE(prev_row == nullptr || tail != nullptr, "bmf_greedy_select: prev_row needs the tail counters");
+  greedy_select_kernel<<<1, 1024, 0, as_stream(stream)>>>(
+      gain_p, gain_n, reinterpret_cast<const long long*>(tail), reinterpret_cast<long long*>(tail_zero), alive, n, wa,
+      wb, scale, -w_fp, w_fn, first, reinterpret_cast<long long*>(state), reinterpret_cast<long long*>(table_row),
+      reinterpret_cast<long long*>(prev_row), reinterpret_cast<long long*>(record), nused);
+  BMF_LAUNCH_CHECK("bmf_greedy_select");
+  return 0;
+}
+
+extern "C" int bmf_cover_apply_compact(const uint64_t* x_bits, uint64_t* c_bits, int64_t m, int64_t n, int64_t words,
+                                       const uint64_t* basis_bits, uint8_t* alive, const int64_t* winner,
+                                       int32_t* tp_old, int32_t* fp_old, int32_t wa, int32_t wb, int32_t kind,
+                                       int32_t v_one, int32_t v_zero, int32_t v_covered, uint8_t* comp_old,
+                                       uint8_t* comp_new, int64_t comp_ld, int64_t comp_cap, int32_t tile_rows,
+                                       int32_t* nused, uint64_t* u_bits, uint64_t* u_words, int64_t kw,
+                                       int32_t factor_bit, uint64_t* vt_row, int64_t* totals, bmf_stream_t stream) {
+  BMF_REQUIRE((wa | wb) != 0, "bmf_cover_apply_compact: integer weights only");
+  BMF_REQUIRE(kind == 0 || ((kind == 1 || kind == 2) && comp_old && comp_new && nused && comp_cap > 0 && tile_rows > 0),
+              "bmf_cover_apply_compact: kind 1 (E2M1) / 2 (int8) needs the compact planes and the counter");
+  BMF_REQUIRE(kind == 0 || (comp_ld % 128 == 0 && comp_ld * (kind == 1 ? 2 : 1) >= words * 64),
+              "bmf_cover_apply_compact: comp_ld must cover words*64 columns");
+  BMF_REQUIRE(kind != 1 || ((v_one | v_zero | v_covered) & ~7) == 0, "bmf_cover_apply_compact: E2M1 codes are 0..7");
+  BMF_REQUIRE(u_words == nullptr || (kw > 0 && factor_bit >= 0 && factor_bit < kw * 64),
+              "bmf_cover_apply_compact: factor_bit outside the usage words");
+  ApplyExtra ex = {};
+  ex.comp_old = comp_old; ex.comp_new = comp_new; ex.comp_ld = comp_ld; ex.comp_cap = comp_cap; ex.nused = nused;
+  ex.comp_kind = kind; ex.v_one = v_one; ex.v_zero = v_zero; ex.v_cov = v_covered;
+  ex.u_words = u_words; ex.kw = kw; ex.factor_bit = factor_bit; ex.vt_row = vt_row;
+  int rc = launch_cover_apply(x_bits, c_bits, m, n, words, basis_bits, alive, winner, tp_old, fp_old, wa, wb, 0.0, 0.0,
+                              nullptr, 0, 0, 0, u_bits, totals, stream, ex);
+  if (rc || kind == 0) return rc;
+  compact_tail_zero_kernel<<<64, 256, 0, as_stream(stream)>>>(comp_old, comp_new, comp_ld, comp_cap, nused, tile_rows);
+  BMF_LAUNCH_CHECK("bmf_cover_apply_compact");
   return 0;
 }
 

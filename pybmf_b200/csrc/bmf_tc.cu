@@ -58,6 +58,10 @@ struct EpiArgs {
   uint64_t policy_a, policy_b;     // L2 eviction policy of the candidate (A) and data-row (B) TMA loads
   long long w_fn_fix, w_fp_fix;    // EPI_GAIN2 (FP4): round(w * 2^20) for the fixed-point pre-decision of the row test
   int fix_ok;                      // ... usable: weights finite and |w| < 1024
+  const int32_t* dyn_rows;         // EPI_GAIN (incremental rescoring): device-side count of valid data rows; the tile grid
+                                   // shrinks to ceil(*dyn_rows / tile) row tiles (nullable: all rows_pad rows are walked)
+  int gain_sign;                   // EPI_GAIN: gain[j] += gain_sign * sum relu (-1 retracts the used rows' old contribution)
+  int symmetric;                   // EPI_STORE (X^T X): row tiles entirely below the diagonal are skipped (C = C^T)
 };
 struct __align__(16) RowState { double s_old; int tpo; int fpo; };
 
@@ -227,15 +231,25 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int64_t row, int n
           dst[q] = make_int4((int)v[4 * q], (int)v[4 * q + 1], (int)v[4 * q + 2], (int)v[4 * q + 3]);
       }
     }
-    if (EPI == EPI_GAIN && relu_sum != 0) atomicAdd(ea.gain + row, (unsigned long long)relu_sum);
+    if (EPI == EPI_GAIN && relu_sum != 0)
+      atomicAdd(ea.gain + row, (unsigned long long)(ea.gain_sign < 0 ? -relu_sum : relu_sum));   // two's complement: exact
   }
+}
+
+// incremental rescoring: the number of row tiles comes from a device counter written by bmf_cover_apply_compact
+__device__ __forceinline__ int dyn_row_tiles(const EpiArgs& ea, int nt_total, int tile_rows) {
+  if (ea.dyn_rows == nullptr) return nt_total;
+  const int rows = *reinterpret_cast<const volatile int32_t*>(ea.dyn_rows);
+  const int nt = (rows + tile_rows - 1) / tile_rows;
+  return nt < nt_total ? nt : nt_total;
 }
 
 template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               int mt_total, int nt_total, int kb_total, int group_m, const EpiArgs ea) {
+               int mt_total, int nt_total_in, int kb_total, int group_m, const EpiArgs ea) {
   extern __shared__ uint8_t smem_raw[];
+  const int nt_total = dyn_row_tiles(ea, nt_total_in, BN);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then tmem base
@@ -482,8 +496,9 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t local_bar) {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_i8_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   int mt_total, int nt_total, int kb_total, int group_m, const EpiArgs ea) {
+                   int mt_total, int nt_total_in, int kb_total, int group_m, const EpiArgs ea) {
   extern __shared__ uint8_t smem_raw[];
+  const int nt_total = dyn_row_tiles(ea, nt_total_in, BN);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE_BYTES2);
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES2 + 4);
@@ -799,7 +814,8 @@ __device__ __forceinline__ void epilogue_tile_f4(uint32_t taddr, int64_t row, in
       dst[3] = make_int4(f32_bits_to_int(hi[4]), f32_bits_to_int(hi[5]), f32_bits_to_int(hi[6]), f32_bits_to_int(hi[7]));
     }
   }
-  if (EPI == EPI_GAIN && relu_sum != 0) atomicAdd(ea.gain + row, (unsigned long long)relu_sum);
+  if (EPI == EPI_GAIN && relu_sum != 0)
+    atomicAdd(ea.gain + row, (unsigned long long)(ea.gain_sign < 0 ? -relu_sum : relu_sum));
 }
 
 template <int EPI>
@@ -1037,15 +1053,24 @@ __device__ __forceinline__ void epilogue_cols_f4(uint32_t taddr, int64_t row, in
       for (int q = 0; q < 4; ++q) dst[q] = o[q];
     }
   }
-  if (EPI == EPI_GAIN && relu_sum != 0) atomicAdd(ea.gain + row, (unsigned long long)relu_sum);
+  if (EPI == EPI_GAIN && relu_sum != 0)
+    atomicAdd(ea.gain + row, (unsigned long long)(ea.gain_sign < 0 ? -relu_sum : relu_sum));
+}
+
+// X^T X is symmetric: a super tile whose last data row lies before its first candidate row is entirely below the
+// diagonal; bmf_basis_threshold(symmetric) reads cnt[min(i,j)][max(i,j)] instead.  All three warp roles evaluate the
+// same predicate, so the pipeline protocol is untouched.
+__device__ __forceinline__ bool skip_lower(const EpiArgs& ea, int mt, int st) {
+  return ea.symmetric && ((int64_t)st * SUPER_ROWS + (SUPER_ROWS - 1) < (int64_t)mt * BM4);
 }
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_f4s_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b0,
-                    const __grid_constant__ CUtensorMap tmap_b1, int mt_total, int st_total, int kb_total, int group_m,
+                    const __grid_constant__ CUtensorMap tmap_b1, int mt_total, int st_total_in, int kb_total, int group_m,
                     const EpiArgs ea) {
   extern __shared__ uint8_t smem_raw[];
+  const int st_total = dyn_row_tiles(ea, st_total_in, SUPER_ROWS);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES_S * STAGE_BYTES_S);
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES_S + 4);
@@ -1099,6 +1124,7 @@ gemm_f4s_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int64_t t = pair; t < total_tiles; t += num_pairs) {
         int mt, st;
         tile_coords(t, mt_total, st_total, group_m, mt, st);
+        if (EPI == EPI_STORE && skip_lower(ea, mt, st)) continue;
 #pragma unroll 1
         for (int sub = 0; sub < 2; ++sub) {
           const int half = sub ? SUB1 / 2 : SUB0 / 2;                       // data rows this CTA stages
@@ -1128,6 +1154,11 @@ gemm_f4s_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t tb = warp_uniform(tmem_base), sb = warp_uniform(smem_base);
       const uint32_t sfa = tb + (uint32_t)SF_COL_S, sfb = tb + (uint32_t)SF_COL_S + 8u;
       for (int64_t t = pair; t < total_tiles; t += num_pairs) {
+        if (EPI == EPI_STORE && ea.symmetric) {
+          int mt, st;
+          tile_coords(t, mt_total, st_total, group_m, mt, st);
+          if (skip_lower(ea, mt, st)) continue;
+        }
 #pragma unroll 1
         for (int sub = 0; sub < 2; ++sub) {
           mbar_wait(tempty_bar(sub), acc_phase ^ 1u);
@@ -1162,6 +1193,7 @@ gemm_f4s_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     for (int64_t t = pair; t < total_tiles; t += num_pairs) {
       int mt, st;
       tile_coords(t, mt_total, st_total, group_m, mt, st);
+      if (EPI == EPI_STORE && skip_lower(ea, mt, st)) continue;
       const int64_t row = (int64_t)mt * BM4 + (int64_t)rank * HALFM + quad * 32 + lane;
       const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
       mbar_wait(tfull_bar(0), acc_phase);
@@ -1287,8 +1319,29 @@ extern "C" int bmf_cover_score_i8(const int8_t* cand_plane, int64_t cand_pad, co
   ea.sign = sign;
   ea.cand_pop = cand_pop;
   ea.bias_scale = bias_scale;
+  ea.gain_sign = 1;
   ea.gain = reinterpret_cast<unsigned long long*>(gain);
   return tc::dispatch_gemm<tc::EPI_GAIN>(0, cand_plane, cand_pad, rows_plane, rows_pad, ld, ea, as_stream(stream));
+}
+
+extern "C" int bmf_cover_rescore_i8(const int8_t* cand_plane, int64_t cand_pad, const int8_t* compact_plane,
+                                    int64_t rows_cap, int64_t ld, int32_t sign, const int32_t* cand_pop,
+                                    int32_t bias_scale, const int32_t* dyn_rows, int32_t gain_sign, int64_t* gain,
+                                    bmf_stream_t stream) {
+  BMF_REQUIRE(sign == 1 || sign == -1, "bmf_cover_rescore_i8: sign must be +1 or -1");
+  BMF_REQUIRE(gain_sign == 1 || gain_sign == -1, "bmf_cover_rescore_i8: gain_sign must be +1 or -1");
+  BMF_REQUIRE(cand_plane && compact_plane && gain && dyn_rows, "bmf_cover_rescore_i8: null pointer");
+  BMF_REQUIRE(cand_pad > 0 && cand_pad % tc::BM == 0, "bmf_cover_rescore_i8: cand_pad must be a positive multiple of 128");
+  BMF_REQUIRE(rows_cap > 0 && rows_cap % tc::BN == 0, "bmf_cover_rescore_i8: rows_cap must be a positive multiple of 256");
+  BMF_REQUIRE(ld > 0 && ld % tc::BK == 0, "bmf_cover_rescore_i8: ld must be a positive multiple of 128");
+  tc::EpiArgs ea = {};
+  ea.sign = sign;
+  ea.cand_pop = cand_pop;
+  ea.bias_scale = bias_scale;
+  ea.gain_sign = gain_sign;
+  ea.dyn_rows = dyn_rows;
+  ea.gain = reinterpret_cast<unsigned long long*>(gain);
+  return tc::dispatch_gemm<tc::EPI_GAIN>(0, cand_plane, cand_pad, compact_plane, rows_cap, ld, ea, as_stream(stream));
 }
 
 extern "C" int bmf_cover_score_i8_general(const int8_t* cand_plane, int64_t cand_pad, const int8_t* pq_plane,
@@ -1329,9 +1382,11 @@ extern "C" int bmf_gemm_f4_nt(const uint8_t* a_plane, int64_t a_rows_pad, const 
   tc::EpiArgs ea = {};
   ea.C = c;
   ea.ldc = ldc;
-  ea.accumulate = accumulate ? 1 : 0;
+  ea.accumulate = (accumulate & 1) ? 1 : 0;
+  ea.symmetric = (accumulate & 2) ? 1 : 0;      // bit 1: a_plane == b_plane (X^T X), tiles below the diagonal are skipped
   BMF_REQUIRE(!accumulate || (b_rows_pad % tc::f4::SUPER_ROWS == 0 && !tc::f4::super_tiles_disabled()),
-              "bmf_gemm_f4_nt: accumulate needs b rows padded to 496 (super-tile kernel)");
+              "bmf_gemm_f4_nt: accumulate / symmetric need b rows padded to 496 (super-tile kernel)");
+  BMF_REQUIRE(!ea.symmetric || a_plane == b_plane, "bmf_gemm_f4_nt: symmetric needs a_plane == b_plane");
   if (b_rows_pad % tc::f4::SUPER_ROWS == 0 && !tc::f4::super_tiles_disabled())
     return tc::f4::launch_gemm_f4s<tc::EPI_STORE>(a_plane, a_rows_pad, b_plane, b_rows_pad, ld_bytes, ea, as_stream(stream));
   BMF_REQUIRE(b_rows_pad % tc::f4::BN4 == 0, "bmf_gemm_f4_nt: b rows must be a multiple of 240 for the plain-tile kernel");
@@ -1353,11 +1408,31 @@ extern "C" int bmf_cover_score_f4(const uint8_t* cand_plane, int64_t cand_pad, c
   ea.sign = 1;
   ea.cand_pop = cand_pop;
   ea.bias_scale = bias_scale;
+  ea.gain_sign = 1;
   ea.gain = reinterpret_cast<unsigned long long*>(gain);
   if (rows_pad % tc::f4::SUPER_ROWS == 0 && !tc::f4::super_tiles_disabled())
     return tc::f4::launch_gemm_f4s<tc::EPI_GAIN>(cand_plane, cand_pad, rows_plane, rows_pad, ld_bytes, ea, as_stream(stream));
   BMF_REQUIRE(rows_pad % tc::f4::BN4 == 0, "bmf_cover_score_f4: rows_pad must be a multiple of 240 for the plain-tile kernel");
   return tc::f4::launch_gemm_f4<tc::EPI_GAIN>(cand_plane, cand_pad, rows_plane, rows_pad, ld_bytes, ea, as_stream(stream));
+}
+
+extern "C" int bmf_cover_rescore_f4(const uint8_t* cand_plane, int64_t cand_pad, const uint8_t* compact_plane,
+                                    int64_t rows_cap, int64_t ld_bytes, const int32_t* cand_pop, int32_t bias_scale,
+                                    const int32_t* dyn_rows, int32_t gain_sign, int64_t* gain, bmf_stream_t stream) {
+  BMF_REQUIRE(cand_plane && compact_plane && gain && dyn_rows, "bmf_cover_rescore_f4: null pointer");
+  BMF_REQUIRE(gain_sign == 1 || gain_sign == -1, "bmf_cover_rescore_f4: gain_sign must be +1 or -1");
+  BMF_REQUIRE(cand_pad > 0 && cand_pad % tc::f4::BM4 == 0, "bmf_cover_rescore_f4: cand_pad must be a positive multiple of 256");
+  BMF_REQUIRE(rows_cap > 0 && rows_cap % tc::f4::SUPER_ROWS == 0, "bmf_cover_rescore_f4: rows_cap must be a positive multiple of 496");
+  BMF_REQUIRE(ld_bytes > 0 && ld_bytes % tc::BK == 0, "bmf_cover_rescore_f4: ld_bytes must be a positive multiple of 128");
+  BMF_REQUIRE(cand_pop != nullptr || bias_scale == 0, "bmf_cover_rescore_f4: a bias needs cand_pop");
+  tc::EpiArgs ea = {};
+  ea.sign = 1;
+  ea.cand_pop = cand_pop;
+  ea.bias_scale = bias_scale;
+  ea.gain_sign = gain_sign;
+  ea.dyn_rows = dyn_rows;
+  ea.gain = reinterpret_cast<unsigned long long*>(gain);
+  return tc::f4::launch_gemm_f4s<tc::EPI_GAIN>(cand_plane, cand_pad, compact_plane, rows_cap, ld_bytes, ea, as_stream(stream));
 }
 
 extern "C" int bmf_cover_score_f4_general(const uint8_t* cand_plane, int64_t cand_pad, const uint8_t* pq_plane, int64_t m,

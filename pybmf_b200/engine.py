@@ -92,7 +92,8 @@ class _Trace:
 class CoverEngine:
     """All device buffers and kernel launches behind Asso.init_model / Asso._fit."""
 
-    def __init__(self, X: sp.csr_matrix, w_fp: float, w_fn: float, scorer: str = "auto", assoc: str = "auto"):
+    def __init__(self, X: sp.csr_matrix, w_fp: float, w_fn: float, scorer: str = "auto", assoc: str = "auto",
+                 rescore: str = "auto"):
         _native.require_gpu()
         self.trace = _Trace()
         self.rank, self.world = dist_ctx()
@@ -105,7 +106,7 @@ class CoverEngine:
         # indices need no host-side canonicalisation; explicitly stored zeros do matter, but scanning 1e8 values
         # takes the host ~0.1 s, so the scan runs in build_basis() WHILE the GPU packs and computes X^T X, and only
         # a matrix that really stores zeros (rare) is cleaned and rebuilt.  |X| is counted on the device.
-        self._ctor_args = (w_fp, w_fn, scorer, assoc)
+        self._ctor_args = (w_fp, w_fn, scorer, assoc, rescore)
         Xl = device.csr_rows_view(X, r0, r1)
         self._host_rows = Xl
         self.trace.mark("host_csr")
@@ -156,6 +157,19 @@ class CoverEngine:
         if max(self.r1 - self.r0, 1) >= (1 << 24):             # co-occurrence counts must stay below 2^24 for FP32
             self.assoc_operand = "i8"
         self.assoc_kind = "tcgen05" if assoc == "auto" else assoc
+        # rescore: how the gain vector of step t+1 is obtained.  'full' = one whole contraction per greedy step;
+        # 'incremental' = only the rows the winner used are re-scored, before and after the update (exact: no other row
+        # changed state) -- integer weights on the tensor-core scorers; 'auto' picks incremental where it exists.
+        rescore = os.environ.get("BMF_RESCORE", rescore)
+        assert rescore in ("auto", "full", "incremental")
+        can_inc = self.integer_mode and scorer == "tcgen05" and enc in ("zero", "signed")
+        if rescore == "incremental" and not can_inc:
+            raise ValueError("incremental rescoring needs integer weights (a/2^s) and a tensor-core scorer")
+        self.rescore = "incremental" if (can_inc and rescore != "full") else "full"
+        # X^T X is symmetric: on one GPU the FP4 association skips the tiles below the diagonal (with sharded rows every
+        # rank needs complete row blocks for the reduce-scatter, and its share of the GEMM is 1/world anyway)
+        self.assoc_symmetric = (self.world == 1 and os.environ.get("BMF_ASSOC_SYMMETRIC", "1") == "1")
+        self.cnt_is_upper = False
 
         self.words = device.words_for(self.n)
         self.words_m = device.words_for(max(self.m_loc, 1))
@@ -185,9 +199,25 @@ class CoverEngine:
         self.cand_pad = device.round_up(self.n, 256)           # multiple of 256 -> the 2-SM (cta_group::2) kernel
         self.cand_plane = None
         self.rows_plane = None
-        self.gain_p = device.zeros((self.cand_pad,), torch.int64)
-        self.gain_n = device.zeros((self.cand_pad,), torch.int64)
+        # gain buffer [gain_p | tail (8) | gain_n]: the tail carries (#used, sum P, sum N) of the last apply, so ONE
+        # all-reduce per greedy step moves the gains and the counters (integer mode reduces only gain_p + tail)
+        cp = self.cand_pad
+        self.gbuf = device.zeros((2 * cp + 8,), torch.int64)
+        self.gain_p, self.tail, self.gain_n = self.gbuf[:cp], self.gbuf[cp:cp + 8], self.gbuf[cp + 8:]
+        self.red_len = cp + 8 if self.integer_mode else 2 * cp + 8
+        if self.world > 1:                                      # reduced copy (select reads it; gbuf keeps the local sums)
+            self.gred = device.zeros((2 * cp + 8,), torch.int64)
+            self.gain_p_red, self.tail_red, self.gain_n_red = self.gred[:cp], self.gred[cp:cp + 8], self.gred[cp + 8:]
+        else:
+            self.gred, self.gain_p_red, self.tail_red, self.gain_n_red = self.gbuf, self.gain_p, self.tail, self.gain_n
         self.record = device.zeros((8,), torch.int64)           # [winner, score bits, used, sumP, sumN]
+        self.state = device.zeros((8,), torch.int64)            # device-resident loop state (see bmf_greedy_select)
+        self.nused = device.zeros((2,), torch.int32)
+        self.table = None                                       # [kcap + 1, 8] per-step results
+        self.u_all = None                                       # [kcap, words_m] usage bit columns
+        self.comp_old = self.comp_new = None
+        self.plane_stale = False
+        self.score_events = None                                # bench: list of (start, end) CUDA events per scoring pass
         self.u_cols = []                                        # device bit vectors, one per chosen factor
         self.tp_tot = 0
         self.fp_tot = 0
@@ -240,7 +270,8 @@ class CoverEngine:
         n_pad, ldc = self._cnt_shape()
         d = device.dev()
         self.x_bits = device.zeros((m_loc, self.words), torch.int64)
-        cnt = device.zeros((n_pad, ldc), torch.int32)
+        cnt = device.zeros((self._cnt_rows(n_pad), ldc), torch.int32)
+        self.cnt_is_upper = self.assoc_symmetric
         nchunks = 3 if Xl.nnz >= (1 << 24) else 1
         step = device.round_up(-(-m_loc // nchunks), 256)      # chunk boundaries: multiples of 256 rows (K tiles, bit words)
         main = torch.cuda.current_stream()
@@ -268,16 +299,30 @@ class CoverEngine:
                 _native.call("bmf_expand_bits_f4", xt_bits, None, n, rows, xt_bits.shape[1], 2, 0, 0, xt_plane,
                              xt_plane.shape[0], ldk)
                 _native.call("bmf_gemm_f4_nt", xt_plane, n_pad, xt_plane, device.round_up(n, F4_ROW_PAD), ldk, cnt, ldc,
-                             0 if first else 1)
+                             (0 if first else 1) | (2 if self.assoc_symmetric else 0))
                 first = False
                 self.launches += 4
                 del xt_plane, xt_bits
         self.cnt = cnt
 
+    def _cnt_rows(self, n_pad):
+        """Rows of the count matrix: with sharded rows it is reduce-scattered in `world` equal row blocks."""
+        if self.world == 1:
+            return n_pad
+        return self.world * (-(-n_pad // self.world))
+
+    def counts_full(self):
+        """X^T X as a full n x n int32 tensor (the symmetric GEMM leaves the part below the diagonal unwritten)."""
+        c = self.cnt[: self.n, : self.n]
+        if not self.cnt_is_upper:
+            return c
+        up = torch.triu(c)
+        return up + torch.triu(c, 1).T
+
     def _build_basis(self, tau: float):
         n, m_loc = self.n, self.m_loc
         n_pad, ldc = self._cnt_shape()
-        cnt = self.cnt if self.cnt is not None else device.zeros((n_pad, ldc), torch.int32)
+        cnt = self.cnt if self.cnt is not None else device.zeros((self._cnt_rows(n_pad), ldc), torch.int32)
         if m_loc > 0 and self.cnt is None:
             xt_bits = device.pack_csr(self._ip, self._ix, m_loc, n, transposed=True)
             if self.assoc_kind == "tcgen05" and self.assoc_operand == "f4":
@@ -286,7 +331,9 @@ class CoverEngine:
                 xt_plane = device.empty((max(n_pad, ldc), ldk), torch.uint8)
                 _native.call("bmf_expand_bits_f4", xt_bits, None, n, m_loc, xt_bits.shape[1], 2, 0, 0, xt_plane,
                              xt_plane.shape[0], ldk)
-                _native.call("bmf_gemm_f4_nt", xt_plane, n_pad, xt_plane, device.round_up(n, F4_ROW_PAD), ldk, cnt, ldc, 0)
+                _native.call("bmf_gemm_f4_nt", xt_plane, n_pad, xt_plane, device.round_up(n, F4_ROW_PAD), ldk, cnt, ldc,
+                             2 if self.assoc_symmetric else 0)
+                self.cnt_is_upper = self.assoc_symmetric
                 del xt_plane
             elif self.assoc_kind == "tcgen05":
                 xt_plane = device.expand_bits_i8(xt_bits, n, m_loc, 1, 0, 256)
@@ -297,15 +344,46 @@ class CoverEngine:
             self.launches += 3
             del xt_bits
         self.trace.mark("assoc_counts")
-        all_reduce_sum(cnt)
-        self.trace.mark("assoc_allreduce")
         self.cnt = cnt
+        self.cand_pop = device.zeros((max(self.cand_pad, self._cnt_rows(n_pad)),), torch.int32)
         if self.scorer == "tcgen05" and self.operand == "i8":
             self.cand_plane = device.zeros((self.cand_pad, self.ld), torch.int8)
-        self.cand_pop = device.zeros((self.cand_pad,), torch.int32)
-        _native.call("bmf_basis_threshold", cnt, ldc, n, float(tau), self.basis_bits, self.words,
-                     self.cand_plane, self.ld, self.alive, self.cand_pop)
-        self.launches += 1
+        if self.world > 1:
+            # partial counts -> reduce-scatter by row blocks -> every rank thresholds ITS n/R rows ->
+            # all-gather of the bit rows (39.5 MB at c4 instead of all-reducing 1.28 GB of int32)
+            import torch.distributed as dist
+            per = cnt.shape[0] // self.world
+            mine = device.empty((per, ldc), torch.int32)
+            dist.reduce_scatter_tensor(mine, cnt, op=dist.ReduceOp.SUM)
+            self.trace.mark("assoc_reduce_scatter")
+            row0 = self.rank * per
+            nrows = max(0, min(n, row0 + per) - row0)
+            blk_bits = device.zeros((per, self.words), torch.int64)
+            blk_alive = device.zeros((per,), torch.uint8)
+            blk_pop = device.zeros((per,), torch.int32)
+            if nrows > 0:
+                _native.call("bmf_basis_threshold_rows", mine, ldc, n, row0, nrows, 0, float(tau), blk_bits, self.words,
+                             blk_alive, blk_pop)
+            all_bits = device.empty((per * self.world, self.words), torch.int64)
+            all_alive = device.empty((per * self.world,), torch.uint8)
+            all_pop = device.empty((per * self.world,), torch.int32)
+            dist.all_gather_into_tensor(all_bits, blk_bits)
+            dist.all_gather_into_tensor(all_alive, blk_alive)
+            dist.all_gather_into_tensor(all_pop, blk_pop)
+            self.basis_bits = all_bits[:n]
+            self.alive = all_alive[:n].contiguous()
+            self.cand_pop[: all_pop.shape[0]] = all_pop
+            self.cnt = None                                   # only this rank's row block is complete: not kept
+            self._cnt_block = (mine, row0, nrows)
+            if self.cand_plane is not None:                   # int8 candidate rows from the gathered bits
+                self.cand_plane = device.expand_bits_i8(self.basis_bits, n, n, 1, 0, 256, out=self.cand_plane)
+            self.launches += 1
+        else:
+            _native.call("bmf_basis_threshold_rows", cnt, ldc, n, 0, n, 1 if self.cnt_is_upper else 0, float(tau),
+                         self.basis_bits, self.words, self.alive, self.cand_pop)
+            if self.cand_plane is not None:
+                self.cand_plane = device.expand_bits_i8(self.basis_bits, n, n, 1, 0, 256, out=self.cand_plane)
+            self.launches += 1
         if self.scorer == "tcgen05" and self.operand == "f4":   # candidate rows as packed E2M1 0/1
             self.cand_plane = device.empty((self.cand_pad, self.ld4), torch.uint8)
             _native.call("bmf_expand_bits_f4", self.basis_bits, None, n, n, self.words, 2, 0, 0, self.cand_plane,
@@ -317,6 +395,7 @@ class CoverEngine:
 
     def _rebuild_rows_plane(self):
         """rows_plane[i][k] = 0 if covered, +wb if x, -wa otherwise (the signed operand of D = wb*P - wa*N)."""
+        self.plane_stale = False
         if self.encoding == "pq" and self.operand == "f4":
             if self.rows_plane is None:
                 self.rows_plane = device.empty((2 * device.round_up(max(self.m_loc, 1), 120), self.ld4), torch.uint8)
@@ -356,8 +435,7 @@ class CoverEngine:
 
     def assoc_host(self):
         """The reference's `assoc` attribute (n x n float64) from the device counts."""
-        n = self.n
-        cnt = self.cnt[:n, :n].cpu().numpy().astype(np.float64)
+        cnt = self.counts_full().cpu().numpy().astype(np.float64)
         s = np.diag(cnt).copy()
         out = np.zeros_like(cnt)
         nz = s > 0
@@ -371,32 +449,20 @@ class CoverEngine:
 
     # ---- one greedy step (Asso.py:62-110) ------------------------------------------------------
     def score_all(self):
-        if self.m_loc == 0:                                   # a rank without rows only joins the exchange
-            self.gain_p.zero_()
-            self.gain_n.zero_()
-        elif self.scorer == "tcgen05" and self.encoding == "pq" and self.operand == "f4":
-            _native.call("bmf_cover_score_f4_general", self.cand_plane, self.cand_pad, self.rows_plane, self.m_loc,
-                         self.ld4, self.cand_pop, self.tp_old, self.fp_old, self.w_fp, self.w_fn, self.gain_p,
-                         self.gain_n)
-        elif self.scorer == "tcgen05" and self.encoding == "pq":
-            _native.call("bmf_cover_score_i8_general", self.cand_plane, self.cand_pad, self.rows_plane, self.m_loc,
-                         self.ld, self.cand_pop, self.tp_old, self.fp_old, self.w_fp, self.w_fn, self.gain_p,
-                         self.gain_n)
-        elif self.scorer == "tcgen05" and self.operand == "f4":
-            _native.call("bmf_cover_score_f4", self.cand_plane, self.cand_pad, self.rows_plane,
-                         self.rows_plane.shape[0], self.ld4, self.cand_pop, self.wa, self.gain_p)
-        elif self.scorer == "tcgen05":
-            _native.call("bmf_cover_score_i8", self.cand_plane, self.cand_pad, self.rows_plane,
-                         self.rows_plane.shape[0], self.ld, self.plane_sign,
-                         self.cand_pop if self.encoding == "zero" else None, self.wa, self.gain_p)
-        else:
-            _native.call("bmf_cover_score_popc", self.x_bits, self.c_bits, self.m_loc, self.n, self.words,
-                         self.basis_bits, self.alive, self.tp_old, self.fp_old, self.wa, self.wb, self.w_fp,
-                         self.w_fn, self.gain_p, self.gain_n)
-        self.launches += 1
-        all_reduce_sum(self.gain_p)
-        if not self.integer_mode:
-            all_reduce_sum(self.gain_n)
+        """One full scoring pass + the exchange (step-wise API: tests, bench `value` loop, rescore='full')."""
+        self._score_into_gains()
+        self._reduce_gains()
+
+    def _reduce_gains(self, tail_only=False):
+        """Local gains (+ the three counters of the last apply) -> sums over all ranks: ONE all-reduce per greedy step."""
+        if self.world == 1:
+            return
+        if tail_only:
+            self.tail_red.copy_(self.tail)
+            all_reduce_sum(self.tail_red)
+            return
+        self.gred[: self.red_len].copy_(self.gbuf[: self.red_len])
+        all_reduce_sum(self.gred[: self.red_len])
 
     def select_and_apply(self, best_score: float):
         """argmax + apply without a host round trip in between; one small D2H read at the end.
@@ -404,9 +470,9 @@ class CoverEngine:
         base_int = self.wb * self.tp_tot - self.wa * self.fp_tot
         scale = 1.0 / float(1 << self.shift)
         self.record.zero_()
-        _native.call("bmf_select_first_max", self.gain_p, self.gain_n if not self.integer_mode else None, self.alive,
-                     self.n, self.wa, self.wb, base_int, scale, self.w_fp, self.w_fn, self.tp_tot, self.fp_tot,
-                     float(best_score), self.record)
+        _native.call("bmf_select_first_max", self.gain_p_red, self.gain_n_red if not self.integer_mode else None,
+                     self.alive, self.n, self.wa, self.wb, base_int, scale, self.w_fp, self.w_fn, self.tp_tot,
+                     self.fp_tot, float(best_score), self.record)
         u_bits = device.zeros((self.words_m,), torch.int64)
         if self.m_loc > 0 and self.scorer == "tcgen05" and self.encoding == "pq" and self.operand == "f4":
             _native.call("bmf_cover_apply_f4_general", self.x_bits, self.c_bits, self.m_loc, self.n, self.words,
@@ -440,6 +506,178 @@ class CoverEngine:
         self.tp_tot += sp_
         self.fp_tot += sn_
         return winner, score, used, sp_, sn_
+
+    # ---- the device-resident greedy loop (Asso.py:62-110 without a host round trip per step) -----------------
+    def ensure_capacity(self, kcap: int):
+        """Per-step result table and usage bit columns for `kcap` greedy steps (+ compact planes when incremental)."""
+        if self.table is None or self.table.shape[0] < kcap + 1:
+            table = device.zeros((kcap + 1, 8), torch.int64)
+            u_all = device.zeros((kcap, self.words_m), torch.int64)
+            if self.table is not None:
+                table[: self.table.shape[0]] = self.table
+                u_all[: self.u_all.shape[0]] = self.u_all
+            self.table, self.u_all = table, u_all
+        if self.rescore == "incremental" and self.comp_old is None and self.m_loc > 0:
+            rows, ld = self.rows_plane.shape
+            dt = self.rows_plane.dtype
+            self.comp_old = device.zeros((rows, ld), dt)           # capacity = every row: a winner can use them all
+            self.comp_new = device.zeros((rows, ld), dt)
+
+    def _score_into_gains(self):
+        """One FULL scoring pass of the current cover into the local gain vector(s) (kernel only, no exchange)."""
+        ev = None
+        if self.score_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(torch.cuda.current_stream())
+        if self.m_loc == 0:
+            _native.call("bmf_fill_zero", self.gbuf, 8 * self.cand_pad)
+            if not self.integer_mode:
+                _native.call("bmf_fill_zero", self.gain_n, 8 * self.cand_pad)
+        else:
+            if self.scorer == "tcgen05" and self.plane_stale:
+                self._rebuild_rows_plane()
+            self._launch_scorer()
+        if ev is not None:
+            ev[1].record(torch.cuda.current_stream())
+            self.score_events.append(ev)
+
+    def _launch_scorer(self):
+        if self.scorer == "tcgen05" and self.encoding == "pq" and self.operand == "f4":
+            _native.call("bmf_cover_score_f4_general", self.cand_plane, self.cand_pad, self.rows_plane, self.m_loc,
+                         self.ld4, self.cand_pop, self.tp_old, self.fp_old, self.w_fp, self.w_fn, self.gain_p,
+                         self.gain_n)
+        elif self.scorer == "tcgen05" and self.encoding == "pq":
+            _native.call("bmf_cover_score_i8_general", self.cand_plane, self.cand_pad, self.rows_plane, self.m_loc,
+                         self.ld, self.cand_pop, self.tp_old, self.fp_old, self.w_fp, self.w_fn, self.gain_p,
+                         self.gain_n)
+        elif self.scorer == "tcgen05" and self.operand == "f4":
+            _native.call("bmf_cover_score_f4", self.cand_plane, self.cand_pad, self.rows_plane,
+                         self.rows_plane.shape[0], self.ld4, self.cand_pop, self.wa, self.gain_p)
+        elif self.scorer == "tcgen05":
+            _native.call("bmf_cover_score_i8", self.cand_plane, self.cand_pad, self.rows_plane,
+                         self.rows_plane.shape[0], self.ld, self.plane_sign,
+                         self.cand_pop if self.encoding == "zero" else None, self.wa, self.gain_p)
+        else:
+            _native.call("bmf_cover_score_popc", self.x_bits, self.c_bits, self.m_loc, self.n, self.words,
+                         self.basis_bits, self.alive, self.tp_old, self.fp_old, self.wa, self.wb, self.w_fp,
+                         self.w_fn, self.gain_p, self.gain_n)
+        self.launches += 1
+
+    def first_pass(self):
+        """Gains of the empty cover (enqueued by init_model so that host work hides behind it)."""
+        self._score_into_gains()
+        self._reduce_gains()
+
+    def enqueue_steps(self, t0: int, count: int, rescore_last: bool = True):
+        """Enqueue greedy steps t0 .. t0+count-1: select -> apply -> re-score -> exchange, all on the device.
+        Precondition: the (reduced) gain vector describes the cover before step t0.  rescore_last=False skips the
+        re-scoring after the final step (the caller knows the loop ends there)."""
+        self.ensure_capacity(t0 + count)
+        scale = 1.0 / float(1 << self.shift)
+        gn_red = None if self.integer_mode else self.gain_n_red
+        for t in range(t0, t0 + count):
+            _native.call("bmf_greedy_select", self.gain_p_red, gn_red, self.tail_red, self.tail, self.alive, self.n,
+                         self.wa, self.wb, scale, self.w_fp, self.w_fn, 1 if t == 0 else 0, self.state, self.table[t],
+                         self.table[t - 1] if t > 0 else None, self.record, self.nused)
+            self.launches += 1
+            last = (t == t0 + count - 1) and not rescore_last
+            self._apply_winner(t, compact=(self.rescore == "incremental" and not last))
+            if last:
+                self._reduce_gains(tail_only=True)
+            else:
+                if self.rescore == "incremental":
+                    self._rescore_used_rows()
+                else:
+                    self._score_into_gains()
+                self._reduce_gains()
+            if len(self.u_cols) <= t:
+                self.u_cols.extend([None] * (t + 1 - len(self.u_cols)))
+            self.u_cols[t] = self.u_all[t]
+        # fold the last step's counters into the state and its table row
+        _native.call("bmf_greedy_select", self.gain_p_red, gn_red, self.tail_red, self.tail, self.alive, self.n, self.wa,
+                     self.wb, scale, self.w_fp, self.w_fn, 0, self.state, None, self.table[t0 + count - 1], self.record,
+                     self.nused)
+        self.launches += 1
+
+    def _apply_winner(self, t: int, compact: bool):
+        """bmf_cover_apply* for the winner in self.record: usage column t, cover, per-row counters, counters into the
+        gain tail; incremental mode also compacts the used rows' operand rows before / after the update."""
+        if self.m_loc == 0:
+            return
+        u_bits = self.u_all[t]
+        lib = _native.load()
+        if self.rescore == "incremental":
+            if self.operand == "f4":
+                kind, (one, zero, cov) = 1, [lib.bmf_e2m1_code(v) for v in self._plane_values()]
+                tile = F4_ROW_PAD
+            else:
+                kind, (one, zero, cov) = 2, self._plane_values()
+                tile = 256
+            _native.call("bmf_cover_apply_compact", self.x_bits, self.c_bits, self.m_loc, self.n, self.words,
+                         self.basis_bits, self.alive, self.record, self.tp_old, self.fp_old, self.wa, self.wb,
+                         kind if compact else 0, one, zero, cov, self.comp_old, self.comp_new,
+                         self.comp_old.shape[1], self.comp_old.shape[0], tile, self.nused, u_bits, None, 0, 0, None,
+                         self.tail)
+            self.plane_stale = True                            # the big plane is no longer patched
+            self.launches += 2 if compact else 1
+            return
+        if self.scorer == "tcgen05" and self.encoding == "pq" and self.operand == "f4":
+            _native.call("bmf_cover_apply_f4_general", self.x_bits, self.c_bits, self.m_loc, self.n, self.words,
+                         self.basis_bits, self.alive, self.record, self.tp_old, self.fp_old, self.w_fp, self.w_fn,
+                         self.rows_plane, self.ld4, u_bits, self.tail)
+        elif self.scorer == "tcgen05" and self.encoding == "pq":
+            _native.call("bmf_cover_apply_general", self.x_bits, self.c_bits, self.m_loc, self.n, self.words,
+                         self.basis_bits, self.alive, self.record, self.tp_old, self.fp_old, self.w_fp, self.w_fn,
+                         self.rows_plane, self.ld, u_bits, self.tail)
+        elif self.scorer == "tcgen05" and self.operand == "f4":
+            _native.call("bmf_cover_apply_f4", self.x_bits, self.c_bits, self.m_loc, self.n, self.words,
+                         self.basis_bits, self.alive, self.record, self.tp_old, self.fp_old, self.wa, self.wb,
+                         self.rows_plane, self.ld4, lib.bmf_e2m1_code(self.wa), u_bits, self.tail)
+        else:
+            _native.call("bmf_cover_apply", self.x_bits, self.c_bits, self.m_loc, self.n, self.words, self.basis_bits,
+                         self.alive, self.record, self.tp_old, self.fp_old, self.wa, self.wb, self.w_fp, self.w_fn,
+                         self.rows_plane if self.scorer == "tcgen05" else None, self.ld,
+                         self._plane_values()[2] if self.scorer == "tcgen05" else 0, u_bits, self.tail)
+        self.launches += 1
+
+    def _rescore_used_rows(self):
+        """gain += sum_{used rows} relu(D after) - relu(D before): two small scoring GEMMs over the compacted rows."""
+        if self.m_loc == 0:
+            return
+        cap = self.comp_old.shape[0]
+        for plane, sign in ((self.comp_old, -1), (self.comp_new, 1)):
+            if self.operand == "f4":
+                _native.call("bmf_cover_rescore_f4", self.cand_plane, self.cand_pad, plane, cap, self.ld4, self.cand_pop,
+                             self.wa, self.nused, sign, self.gain_p)
+            else:
+                _native.call("bmf_cover_rescore_i8", self.cand_plane, self.cand_pad, plane, cap, self.ld, self.plane_sign,
+                             self.cand_pop if self.encoding == "zero" else None, self.wa, self.nused, sign, self.gain_p)
+        self.launches += 2
+
+    def read_table(self, t0: int, t1: int) -> np.ndarray:
+        """Rows t0..t1-1 of the per-step table (one D2H, the only sync of the loop)."""
+        return self.table[t0:t1].cpu().numpy()
+
+    def rollback(self, t_keep: int, discarded_winners, kept, best_score: float):
+        """After the reference's truncation quirk D1 at step t_keep-1: speculative steps >= t_keep are void.  Their
+        winners return to the candidate list, the cover is rebuilt from the factors in `kept` (Asso.py:80 recomputes
+        X_pd from the truncated U, V), the inherited threshold is `best_score`, and the gains are re-scored in full."""
+        for w in discarded_winners:
+            if w >= 0:
+                self.alive[int(w)] = 1
+        if self.u_all is not None and t_keep < self.u_all.shape[0]:
+            self.u_all[t_keep:].zero_()
+            self.table[t_keep:].zero_()
+        self.reset_cover(kept)
+        st = np.zeros(8, dtype=np.int64)
+        st[0] = np.float64(best_score).view(np.int64)
+        st[1], st[2], st[4] = self.tp_tot, self.fp_tot, t_keep
+        self.state.copy_(torch.from_numpy(st).to(self.state.device))
+        self.tail.zero_()
+        if self.world > 1:
+            self.tail_red.zero_()
+        self._score_into_gains()
+        self._reduce_gains()
 
     def basis_row_host(self, j: int) -> np.ndarray:
         return device.words_to_dense(self.basis_bits[j:j + 1].cpu().numpy(), self.n)[0]
@@ -497,19 +735,20 @@ class CoverEngine:
         self.tp_old.zero_()
         self.fp_old.zero_()
         self.tp_tot = self.fp_tot = 0
-        if kept and self.m_loc > 0:
-            k = len(kept)
-            kw = (k + 63) // 64
-            cols = [device.words_to_dense(self.u_cols[ui].cpu().numpy().reshape(1, -1), self.m_loc)[0]
-                    for (ui, _j) in kept]
-            uw = torch.from_numpy(device.dense_to_words(np.stack(cols, axis=1), words=kw)).to(device.dev())
-            vt = torch.stack([self.basis_bits[j] for (_ui, j) in kept]).contiguous()
-            _native.call("bmf_bool_product", uw, self.m_loc, kw, vt, k, self.words, self.c_bits)
+        if kept:
             counts = device.zeros((3,), torch.int64)
-            _native.call("bmf_confusion_bits", self.x_bits, self.c_bits, self.m_loc, self.words, -1, counts,
-                         self.tp_old, self.fp_old)
-            self.launches += 2
-            all_reduce_sum(counts)
+            if self.m_loc > 0:                                 # only ranks that own rows launch kernels ...
+                k = len(kept)
+                kw = (k + 63) // 64
+                cols = [device.words_to_dense(self.u_cols[ui].cpu().numpy().reshape(1, -1), self.m_loc)[0]
+                        for (ui, _j) in kept]
+                uw = torch.from_numpy(device.dense_to_words(np.stack(cols, axis=1), words=kw)).to(device.dev())
+                vt = torch.stack([self.basis_bits[j] for (_ui, j) in kept]).contiguous()
+                _native.call("bmf_bool_product", uw, self.m_loc, kw, vt, k, self.words, self.c_bits)
+                _native.call("bmf_confusion_bits", self.x_bits, self.c_bits, self.m_loc, self.words, -1, counts,
+                             self.tp_old, self.fp_old)
+                self.launches += 2
+            all_reduce_sum(counts)                             # ... but EVERY rank joins the exchange
             c = counts.cpu().numpy()
             self.tp_tot, self.fp_tot = int(c[0]), int(c[1])
         if self.scorer == "tcgen05":

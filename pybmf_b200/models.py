@@ -204,7 +204,25 @@ class BaseModel:
             c, r = self._evaluate(name, info, mets)
             columns += c
             results += r
+        batch = self.__dict__.get("_dev_log_batch")
+        if batch is not None and not verbose:                  # rows are appended in one go by _flush_logs()
+            batch.append((df_name, columns, [pd.Timestamp.now().strftime("%d/%m/%y %I:%M:%S")] + results))
+            return
+        self._flush_logs()
         U_.record(df_dict=self.logs, df_name=df_name, columns=columns, records=results, verbose=verbose)
+
+    def _flush_logs(self):
+        """Turn the batched log rows into DataFrame rows (one construction per table instead of one pandas `.loc`
+        assignment per greedy step, which costs ~2 ms each)."""
+        batch = self.__dict__.get("_dev_log_batch")
+        if not batch:
+            return
+        by_name = {}
+        for df_name, columns, row in batch:
+            by_name.setdefault(df_name, (columns, []))[1].append(row)
+        del batch[:]
+        for df_name, (columns, rows) in by_name.items():
+            U_.record_many(self.logs, df_name, columns, rows)
 
     def _evaluate(self, name, info, metrics):
         counts = self._split_counts(name)
@@ -298,6 +316,15 @@ class BaseModel:
         if name == "basis" and "_dev_host_basis" in d:          # candidates left after the fit (Asso.py:106-107)
             d["basis"] = lil_matrix(d["_dev_host_basis"].astype(int))
             return d["basis"]
+        if name == "basis" and "_dev_basis_bits" in d:          # wide matrices: unpacked from the device bit rows on demand
+            bits, alive, n = d.pop("_dev_basis_bits")
+            keep = alive.cpu().numpy().astype(bool)
+            rows = U_._bits_to_csr(bits[torch.from_numpy(np.flatnonzero(keep)).to(bits.device)], int(keep.sum()), n)
+            d["basis"] = rows.tolil()
+            return d["basis"]
+        if name == "assoc" and "_dev_basis_bits" in d:
+            raise AttributeError("assoc: the n x n float64 association matrix is not kept for n > 8192 (it would be "
+                                 "%.1f GB); use `basis`, or refit a column subset" % (8e-9 * d["_dev_basis_bits"][2] ** 2))
         raise AttributeError(name)
 
     def predict_X(self, U=None, V=None, u=None, v=None, us=None, vs=None, boolean=True):
@@ -336,17 +363,20 @@ class Asso(BaseModel):
     (all sm_100a CUDA; results are identical).
     """
 
-    def __init__(self, tau, k=None, tol=0, w_fp=0.5, w_fn=None, *, scorer="auto", assoc_kernel="auto"):
-        self._scorer, self._assoc_kernel = scorer, assoc_kernel
+    def __init__(self, tau, k=None, tol=0, w_fp=0.5, w_fn=None, *, scorer="auto", assoc_kernel="auto", rescore="auto"):
+        self._scorer, self._assoc_kernel, self._rescore = scorer, assoc_kernel, rescore
         self.check_params(tau=tau, k=k, tol=tol, w_fp=w_fp, w_fn=w_fn)
 
     def fit(self, X_train, X_val=None, X_test=None, **kwargs):
         self.__dict__.pop("U", None)                           # a fit always starts from empty factors
         self.__dict__.pop("V", None)
         super().fit(X_train, X_val, X_test, **kwargs)
+        self._dev_log_batch = []
         try:
             self._fit()
         finally:
+            self._flush_logs()
+            self.__dict__.pop("_dev_log_batch", None)
             self._materialize_factors(final=True)
             if "_dev" in self.__dict__:
                 self._dev.trace.mark("factors_to_host")
@@ -434,7 +464,8 @@ class Asso(BaseModel):
     def init_model(self):
         super().init_model()
         w_fn = 1 - self.w_fp if self.w_fn is None else self.w_fn
-        self._dev = CoverEngine(self.X_train, self.w_fp, w_fn, scorer=self._scorer, assoc=self._assoc_kernel)
+        self._dev = CoverEngine(self.X_train, self.w_fp, w_fn, scorer=self._scorer, assoc=self._assoc_kernel,
+                                rescore=self.__dict__.get("_rescore", "auto"))
         self._dev_nb = self._dev.build_basis(self.tau, prescore=True)
         self.__dict__.pop("assoc", None)
         self.__dict__.pop("basis", None)
@@ -445,53 +476,60 @@ class Asso(BaseModel):
             # keep what the lazy `assoc` / `basis` attributes need, as host arrays
             self._dev_launches = dev.launches
             if dev.n <= 8192 and dev.cnt is not None:
-                self._dev_host_cnt = dev.cnt[: dev.n, : dev.n].cpu().numpy()
+                self._dev_host_cnt = dev.counts_full().cpu().numpy()
                 self._dev_host_basis = dev.basis_host()
+            else:                                              # wide matrices: keep the compact form (bit rows + alive mask)
+                self._dev_basis_bits = (dev.basis_bits, dev.alive, dev.n)
+        self.__dict__.pop("_dev_split_cache", None)
         self.__dict__.pop("_dev_nb", None)
 
     # ---- the greedy loop (Asso.py:62-140) ------------------------------------------------------
     def _fit(self):
+        """The k greedy steps run as ONE device-resident sequence (select -> apply -> re-score -> exchange per step, no
+        host round trip: CoverEngine.enqueue_steps); the host then reads the per-step table once and replays the
+        reference's bookkeeping on it -- log rows, `early_stop` (incl. quirks D1 / D2), factor placement.  Steps that
+        the reference would not have run (everything after a D1 truncation) are rolled back and re-run from the
+        truncated factors.  With val / test splits the loop advances one step at a time (their counts are per step)."""
         dev = self._dev
         m, n = self.m, self.n
         size = m * n
-        k = 0
-        is_improving = True
-        best_score = 0
         n_basis = self._dev_nb
-        need_reset = False
-        prescored = dev.prescored                              # init_model already enqueued the first scoring pass
+        stepwise = self.X_val is not None or self.X_test is not None or dev.trace.on
+        chunk = 1 if stepwise else (self.k if self.k is not None else 16)
+        k = 0                                                 # next greedy step to book (the reference's `k`)
+        enq = 0                                               # steps enqueued so far
+        table = None
+        base = 0
+        best_score = 0
+        is_improving = True
+        if not dev.prescored:
+            dev.first_pass()
+        self.fit_steps_ = []                                  # per greedy step: winner, score, used, tp, fp (see digest.py)
         while is_improving:
             best_score = 0 if k == 0 else best_score
             if n_basis == 0:
                 is_improving = self.early_stop(msg="Candidate list is empty", k=k)
                 break
-            if need_reset:                                   # factors were truncated (D1): cover = current U o V^T
-                dev.reset_cover([(e["ui"], e["j"]) for e in self._dev_kept if e is not None])
-                need_reset = False
-                prescored = False
-            if not prescored:
-                dev.score_all()
-            prescored = False
-            winner, score, used, sum_p, sum_n = dev.select_and_apply(best_score)
-            dev.trace.mark("greedy_steps")
+            if k == enq:                                      # nothing pending: enqueue the next stretch and read it back
+                count = chunk if self.k is None else max(1, min(chunk, self.k - enq))
+                ends_here = self.k is not None and enq + count >= self.k
+                dev.enqueue_steps(enq, count, rescore_last=not ends_here)
+                base, enq = enq, enq + count
+                table = dev.read_table(base, enq)
+                dev.trace.mark("greedy_steps")
+            row = table[k - base]
+            winner = int(row[0])
             if winner < 0:
                 is_improving = self.early_stop(msg="No pattern found.", k=k)
                 break
-            best_score = score
+            best_score = float(row[1:2].view(np.float64)[0])
+            used, tp, fp = int(row[2]), int(row[5]), int(row[6])
+            dev.tp_tot, dev.fp_tot = tp, fp
             rowsum = dev.cand_pop_host(winner)                # |b_winner|; the row itself is fetched once, at the end
-            self._place_factor(k, {"ui": len(dev.u_cols) - 1, "j": winner, "used": used, "rowsum": rowsum})
+            self._place_factor(k, {"ui": k, "j": winner, "used": used, "rowsum": rowsum})
+            self.fit_steps_.append({"k": k, "winner": winner, "score": best_score, "used": used, "tp": tp, "fp": fp})
             n_basis -= 1
-
-            tp, fp = dev.tp_tot, dev.fp_tot
             fn = dev.sum_x - tp
-            # The next step's scoring pass depends only on device state, so it is enqueued BEFORE this step's log row
-            # is built on the host (pandas, ~2 ms) -- unless the early-stop rules below are about to end the loop or to
-            # truncate the factors (D1), both of which are decided by these integer counters alone.
-            will_stop = (hasattr(self, "tol") and U_.rates(tp, fp, fn, size)["ERR"] <= self.tol) or \
-                        (self.k is not None and k + 1 >= self.k) or n_basis == 0
-            if not will_stop and not dev.trace.on:
-                dev.score_all()
-                prescored = True
             tp_a, fp_a, fn_a = (np.array(v, dtype=np.int64) for v in (tp, fp, fn))
             score_05 = -0.5 * fp_a + 0.5 * tp_a                                     # Asso.py:119
             u_sum = np.float64(sum(e["used"] for e in self._dev_kept if e is not None))
@@ -507,17 +545,55 @@ class Asso(BaseModel):
             err = U_.rates(tp, fp, fn, size)["ERR"]
             ncols_before = len(self._dev_kept)
             is_improving = self.early_stop(error=err, k=k)     # Asso.py:135 (0-based k: quirk D1)
-            if len(self._dev_kept) != ncols_before:
-                need_reset = True
+            truncated = len(self._dev_kept) != ncols_before
             is_improving = self.early_stop(n_factor=k + 1)     # Asso.py:136 overwrites the flag
             k += 1
+            if truncated and is_improving:                     # D1: the cover is U o V^T of the TRUNCATED factors
+                dev.rollback(k, [int(r[0]) for r in table[k - base:]],
+                             [(e["ui"], e["j"]) for e in self._dev_kept if e is not None], best_score)
+                enq = k
         self.__dict__.pop("_dev_counts", None)
 
     def _split_counts(self, name):
         # the training split's counts are already on the host (integer counters of the cover state)
         if name == "train" and "_dev_counts" in self.__dict__ and self.task == "reconstruction":
             return self._dev_counts
-        return super()._split_counts(name)
+        dev = self.__dict__.get("_dev")
+        X = getattr(self, "X_" + name)
+        if dev is None or "_dev_counts" not in self.__dict__ or X.shape != (self.m, self.n):
+            return super()._split_counts(name)
+        # During a fit the cover U o V^T of this rank's rows IS dev.c_bits: the split is packed once per fit and every
+        # step costs one or two streaming passes (no factor materialisation, no re-upload).
+        # reconstruction: counts over the whole matrix; prediction: over the STORED entries (evaluate_utils.py:32-44),
+        # i.e. ones (TP / FN) and explicitly stored zeros (FP / TN) separately.
+        cache = self.__dict__.setdefault("_dev_split_cache", {})
+        key = (name, self.task)
+        if key not in cache:
+            Xl = device.csr_rows_view(X, dev.r0, dev.r1)
+            ones = Xl.copy()
+            ones.eliminate_zeros()
+            entry = {"ones": U_._bits_on_device(ones) if dev.m_loc > 0 else None, "n_ones": int(ones.nnz)}
+            if self.task == "prediction":
+                zeros = Xl.copy()
+                zeros.data = (zeros.data == 0).astype(np.int8)
+                zeros.eliminate_zeros()
+                entry["zeros"] = U_._bits_on_device(zeros) if dev.m_loc > 0 else None
+                entry["n_stored"] = int(Xl.nnz)
+            cache[key] = entry
+        e = cache[key]
+        counts = device.zeros((6,), torch.int64)
+        if dev.m_loc > 0:
+            _native.call("bmf_confusion_bits", e["ones"], dev.c_bits, dev.m_loc, dev.words, e["n_ones"], counts[:3], None, None)
+            if self.task == "prediction":
+                _native.call("bmf_confusion_bits", e["zeros"], dev.c_bits, dev.m_loc, dev.words, -1, counts[3:], None, None)
+        stored = torch.tensor([e.get("n_stored", 0)], dtype=torch.int64, device=counts.device)
+        both = torch.cat([counts, stored])
+        all_reduce_sum(both)
+        c = both.cpu().numpy()
+        if self.task == "reconstruction":
+            return int(c[0]), int(c[1]), int(c[2]), self.m * self.n
+        # ones: TP = |G1 & C|, FN = |G1 \ C|; stored zeros: FP = |G0 & C| (the TP slot of the second pass)
+        return int(c[0]), int(c[3]), int(c[2]), int(c[6])
 
 
 class AssoIter(Asso):
@@ -535,7 +611,12 @@ class AssoIter(Asso):
     def fit(self, X_train, X_val=None, X_test=None, **kwargs):
         BaseModel.fit(self, X_train, X_val, X_test, **kwargs)
         self.__dict__.pop("X_pd", None)
-        self._fit()
+        self._dev_log_batch = []
+        try:
+            self._fit()
+        finally:
+            self._flush_logs()
+            self.__dict__.pop("_dev_log_batch", None)
         self.__dict__.pop("X_pd", None)
         self.finish(show_logs=self.show_logs, save_model=self.save_model, show_result=self.show_result)
 
@@ -567,20 +648,35 @@ class AssoIter(Asso):
         best_error = U_.rates(tp, fp, sum_x - tp, size)["ERR"]
         n_stop = 0
         is_improving = True
-        out = device.zeros((5,), torch.int64)
+        # A sweep over the k columns is deterministic on the device (U[:, k] is ALWAYS replaced, AssoIter.py:60): all k
+        # refinements are enqueued back to back into a per-column table, read with one sync, and the accept / skip / stop
+        # bookkeeping is replayed on the host.  If the reference would have stopped in the middle of the sweep, the usage
+        # words are restored from the snapshot and the sweep is re-run up to that column.
+        table = device.zeros((max(self.k, 1), 5), torch.int64)
+        with_splits = self.X_val is not None or self.X_test is not None
+
+        def write_back():                                       # usage words -> the lil U the caller holds (in place: D7)
+            cols = uw.cpu().numpy()
+            for c in range(kU):
+                col = ((cols[:, c // 64] >> (c % 64)) & 1).astype(np.uint8)
+                self.U[:, c] = _column(col, m)
+            self.__dict__.pop("X_pd", None)
+
+        def sweep(upto):
+            table.zero_()
+            for c in range(upto):
+                _native.call("bmf_refine_column", x_bits, m, n, words, uw, kw, vt, kU, c, wa, wb, float(w_fp),
+                             float(w_fn), table[c])
+            return table.cpu().numpy()
+
         while is_improving:
+            if self.k > kU:                                                       # U[:, idx] in AssoIter.py:85-86
+                raise IndexError("index (%d) out of range" % (self.k - 1))
+            snapshot = uw.clone()
+            rows = sweep(self.k)
             for k in range(self.k):
-                if self.k > kU:                                                   # U[:, idx] in AssoIter.py:85-86
-                    raise IndexError("index (%d) out of range" % (self.k - 1))
-                out.zero_()
-                _native.call("bmf_refine_column", x_bits, m, n, words, uw, kw, vt, kU, k, wa, wb, float(w_fp),
-                             float(w_fn), out)
-                o = out.cpu().numpy()
-                tp, fp = int(o[0]), int(o[1])
+                tp, fp = int(rows[k][0]), int(rows[k][1])
                 score = -w_fp * np.array(fp, dtype=np.int64) + w_fn * np.array(tp, dtype=np.int64)
-                col = ((uw[:, k // 64] >> (k % 64)) & 1).to(torch.uint8).cpu().numpy()
-                self.U[:, k] = _column(col, m)                                    # AssoIter.py:60: always replaced
-                self.__dict__.pop("X_pd", None)
                 fn = sum_x - tp
                 error = U_.rates(tp, fp, fn, size)["ERR"]
                 if error < best_error:
@@ -588,6 +684,12 @@ class AssoIter(Asso):
                         k, best_error, error, float(best_score), float(score)))
                     best_error, best_score = error, score
                     self._dev_counts = (tp, fp, fn, size)
+                    if with_splits:                                               # val / test counts read self.U as of now
+                        now = uw.clone()
+                        uw.copy_(snapshot)
+                        sweep(k + 1)
+                        write_back()
+                        uw.copy_(now)
                     self.evaluate(df_name="refinements", head_info={"k": k},
                                   train_info={"score": best_score, "error": best_error})
                     n_stop = 0
@@ -597,7 +699,11 @@ class AssoIter(Asso):
                     if n_stop == self.k:
                         _say("[I] Error stops decreasing.")
                         is_improving = False
+                        if k < self.k - 1:                                        # undo the columns the reference never reached
+                            uw.copy_(snapshot)
+                            sweep(k + 1)
                         break
+        write_back()
         self.__dict__.pop("_dev_counts", None)
 
 

@@ -415,3 +415,19 @@ def record(df_dict, df_name, columns, records, verbose=False):
     df.loc[len(df.index)] = ts + records
     if verbose:
         print(df.tail())
+
+
+def record_many(df_dict, df_name, columns, rows):
+    """`record` for several rows at once (each row already starts with its timestamp): same table layout -- a `time`
+    column first, MultiIndex columns when the names are tuples, object dtype like the reference's row-wise `.loc`."""
+    if isinstance(columns[0], tuple):
+        cols = pd_.MultiIndex.from_tuples(header(["time"], levels=len(columns[0])) + columns)
+    else:
+        cols = ["time"] + columns
+    new = pd_.DataFrame([list(r) for r in rows], columns=cols, dtype=object)
+    if df_name in df_dict and len(df_dict[df_name].index):
+        old = df_dict[df_name]
+        new.index = range(len(old.index), len(old.index) + len(new.index))
+        df_dict[df_name] = pd_.concat([old, new])
+    else:
+        df_dict[df_name] = new

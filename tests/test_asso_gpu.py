@@ -241,27 +241,98 @@ def test_utils_route_to_kernels(M):
     assert sp.isspmatrix_lil(res_) and np.array_equal(_dense(res_), gt & (1 - want))
 
 
-def test_c2_shape_first_steps_match_oracle(M):
-    """BASELINE.json configs[1] shape (6040 x 3706, 4.5 %): first greedy steps against the oracle."""
+def _load_digest(name):
+    import json
+    import os
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, name + "_digest.json")
+    if not os.path.exists(path):
+        pytest.skip(name + "_digest.json not generated yet (oracle/make_digests.py)")
+    with open(path) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("scorer,rescore", [("tcgen05", "auto"), ("tcgen05", "full"), ("tcgen05_i8", "incremental"),
+                                            ("tcgen05_i8", "full"), ("popc", "full")])
+def test_c2_k20_matches_oracle_digest(M, scorer, rescore):
+    """BASELINE.json configs[1] at FULL size and FULL rank: Asso(k=20) on 6040 x 3706 against the fixture written by the
+    bit-packed C restatement (oracle/make_digests.py; itself equal to the numpy restatement at k=20): all 20 winners,
+    scores (bit for bit), #used rows, TP / FP per step and SHA-256 of the U and V columns."""
+    from pybmf_b200 import synth
+    from pybmf_b200.digest import DIGEST_KEYS, result_digest
+    want = _load_digest("c2")
+    X = synth.config_c2()
+    mdl = M.Asso(tau=0.5, k=20, w_fp=0.5, scorer=scorer, rescore=rescore)
+    mdl.fit(X, **FIT_KW)
+    got = result_digest(mdl)
+    for key in DIGEST_KEYS:
+        assert got[key] == want[key], key
+    df = mdl.logs["updates"]
+    assert [int(v) for v in df[("train", 0, "TP")]] == want["tp"] and [int(v) for v in df[("train", 0, "FP")]] == want["fp"]
+    assert [[int(a), int(b)] for a, b in df[("train", 0, "shape")]] == [[u, r] for u, r in zip(want["used"], want["rowsum"])]
+    assert int(mdl.U.sum()) == sum(want["used"]) and mdl.U.shape == (6040, 20)
+    # the digest computed from the unpacked lil factors is the same as the one computed from the packed bits
+    assert result_digest(mdl)["u_sha256"] == want["u_sha256"]
+
+
+def test_c2_k20_log_rows_match_numpy_oracle(M):
+    """Every logged column of the 20 steps (incl. the float rates) against the numpy restatement."""
     from pybmf_b200 import synth
     X = synth.config_c2()
-    mdl = M.Asso(tau=0.5, k=2, w_fp=0.5)
+    mdl = M.Asso(tau=0.5, k=20, w_fp=0.5)
     mdl.fit(X, **FIT_KW)
-    r = O.asso_fit(X, 2, 0.5, 0.5)
+    r = O.asso_fit(X, 20, 0.5, 0.5)
     assert np.array_equal(_dense(mdl.U), r["U"]) and np.array_equal(_dense(mdl.V), r["V"])
     df = mdl.logs["updates"]
     for col in LOG_COLS:
         assert [float(v) for v in df[("train", 0, col)]] == [float(l[col]) for l in r["logs"]], col
 
 
-def test_c3_shape_assoiter_matches_oracle(M):
-    """BASELINE.json configs[2]: AssoIter on the 6040 x 3706 shape, refinement trace against the oracle."""
+def test_c3_k20_assoiter_matches_oracle_digest(M):
+    """BASELINE.json configs[2]: AssoIter on the k=20 model of the 6040 x 3706 shape: the pass-by-pass accept / skip
+    trace, the logged scores / errors and the final U against the C restatement's fixture."""
+    import hashlib
+    import io
+    from contextlib import redirect_stdout
     from pybmf_b200 import synth
+    want = _load_digest("c3")
     X = synth.config_c2()
-    mdl = M.Asso(tau=0.5, k=4, w_fp=0.5)
+    mdl = M.Asso(tau=0.5, k=20, w_fp=0.5)
+    mdl.fit(X, **FIT_KW)
+    it = M.AssoIter(model=mdl, w_fp=0.5)
+    M.SILENT = False
+    buf = io.StringIO()
+    try:
+        with redirect_stdout(buf):
+            it.fit(X, **FIT_KW)
+    finally:
+        M.SILENT = True
+    trace = []
+    for line in buf.getvalue().splitlines():
+        if "Refined column" in line:
+            trace.append([int(line.split("column i:")[1].split(",")[0]), 1])
+        elif "Skipped column" in line:
+            trace.append([int(line.split("column i:")[1].strip(" .")), 0])
+    assert trace == want["trace"]
+    h = hashlib.sha256()
+    U = _dense(it.U)
+    for c in range(U.shape[1]):
+        h.update(np.packbits(U[:, c], bitorder="little").tobytes())
+    assert h.hexdigest() == want["u_sha256"] and int(U.sum()) == want["u_ones"]
+    if want["score_bits"]:
+        df = it.logs["refinements"]
+        assert [np.float64(v).tobytes().hex() for v in df[("train", 0, "score")]] == want["score_bits"]
+        assert [np.float64(v).tobytes().hex() for v in df[("train", 0, "error")]] == want["error_bits"]
+
+
+def test_assoiter_with_refinements_matches_oracle(M):
+    """AssoIter where refinements DO happen (a noisy planted matrix, k=8): trace and final U against the numpy oracle."""
+    from pybmf_b200 import synth
+    X = synth.planted(900, 700, 8, 0.15, 0.15, 0.25, 0.03, seed=11)
+    mdl = M.Asso(tau=0.35, k=8, w_fp=0.5)
     mdl.fit(X, **FIT_KW)
     U0, V0 = _dense(mdl.U), _dense(mdl.V)
-    ref = O.asso_iter_fit(X, U0, V0, 4, 0.5)
+    ref = O.asso_iter_fit(X, U0, V0, 8, 0.5)
     it = M.AssoIter(model=mdl, w_fp=0.5)
     it.fit(X, **FIT_KW)
     assert np.array_equal(_dense(it.U), ref["U"])
@@ -271,6 +342,72 @@ def test_c3_shape_assoiter_matches_oracle(M):
         assert [int(v) for v in df.iloc[:, 1]] == accepted
         assert [float(v) for v in df[("train", 0, "score")]] == [r["score"] for r in ref["refinements"]]
         assert [float(v) for v in df[("train", 0, "error")]] == [r["error"] for r in ref["refinements"]]
+
+
+@pytest.mark.parametrize("rescore", ["auto", "full"])
+def test_c4_k20_matches_oracle_digest(M, rescore):
+    """BASELINE.json configs[3] at FULL size: Asso(k=20).fit() on the 480189 x 17770 matrix -- the fit whose seconds are
+    the headline -- against the fixture of the CPU restatement (20 full greedy steps on the host, oracle/make_digests.py):
+    winners, score bits, #used, TP / FP per step and the hashes of U and V."""
+    from pybmf_b200 import synth
+    from pybmf_b200.digest import DIGEST_KEYS, result_digest
+    want = _load_digest("c4")
+    X = synth.config_c4()
+    assert int(X.nnz) == want["nnz"]
+    mdl = M.Asso(tau=0.5, k=20, w_fp=0.5, rescore=rescore)
+    mdl.fit(X, **FIT_KW)
+    got = result_digest(mdl)
+    for key in DIGEST_KEYS:
+        assert got[key] == want[key], key
+
+
+def test_device_loop_incremental_equals_full_rescoring(M):
+    """The device-resident loop: after every stretch of steps the incrementally maintained gain vector equals a fresh
+    full scoring pass of the same cover (all live candidates), for the FP4 and the int8 operand planes."""
+    from pybmf_b200 import synth
+    from pybmf_b200.engine import CoverEngine
+    X = synth.planted(2100, 900, 10, 0.12, 0.12, 0.15, 0.02, seed=3)
+    for scorer, w_fp in (("tcgen05_f4", 0.5), ("tcgen05_i8", 0.5), ("tcgen05_i8", 0.25), ("tcgen05_f4", 0.75)):
+        inc = CoverEngine(X, w_fp, 1 - w_fp, scorer=scorer, rescore="incremental")
+        full = CoverEngine(X, w_fp, 1 - w_fp, scorer=scorer, rescore="full")
+        assert inc.rescore == "incremental" and full.rescore == "full"
+        for e in (inc, full):
+            e.build_basis(0.4)
+            e.first_pass()
+        done = 0
+        for count in (1, 3, 2):
+            inc.enqueue_steps(done, count)
+            full.enqueue_steps(done, count)
+            done += count
+            ti, tf = inc.read_table(0, done), full.read_table(0, done)
+            assert np.array_equal(ti, tf), (scorer, done)
+            live = full.alive.bool()
+            assert torch.equal(inc.alive, full.alive)
+            assert torch.equal(inc.gain_p[: inc.n][live], full.gain_p[: full.n][live]), (scorer, done)
+            assert torch.equal(inc.c_bits, full.c_bits) and torch.equal(inc.tp_old, full.tp_old)
+        assert (ti[:, 7] == 2).all() and (ti[:, 0] >= 0).all()
+        st = inc.state.cpu().numpy()
+        assert st[1] == ti[-1, 5] and st[2] == ti[-1, 6] and st[4] == done
+
+
+def test_symmetric_association_equals_full(M, monkeypatch):
+    """X^T X with the tiles below the diagonal skipped + the mirrored read gives the basis of the full product."""
+    from pybmf_b200 import synth
+    from pybmf_b200.engine import CoverEngine
+    X = synth.planted(1500, 1300, 8, 0.1, 0.1, 0.1, 0.02, seed=9)
+    sym = CoverEngine(X, 0.5, 0.5)
+    assert sym.assoc_symmetric
+    sym.build_basis(0.3)
+    monkeypatch.setenv("BMF_ASSOC_SYMMETRIC", "0")
+    ref = CoverEngine(X, 0.5, 0.5)
+    assert not ref.assoc_symmetric
+    ref.build_basis(0.3)
+    assert sym.cnt_is_upper and not ref.cnt_is_upper
+    assert torch.equal(sym.counts_full(), ref.counts_full())
+    assert torch.equal(sym.basis_bits, ref.basis_bits) and torch.equal(sym.alive, ref.alive)
+    assert torch.equal(sym.cand_pop[: sym.n], ref.cand_pop[: ref.n])
+    want = O.assoc_counts(X)
+    assert np.array_equal(sym.counts_full().cpu().numpy().astype(np.int64), want)
 
 
 def test_transposed_model(M):
@@ -299,7 +436,7 @@ def test_c4_full_size_properties(M):
     assert eng4.operand == "f4" and eng4.assoc_operand == "f4"
     nb4 = eng4.build_basis(0.5)
     eng4.score_all()
-    g_f4, cnt_f4, basis_f4 = eng4.gain_p.clone(), eng4.cnt[: eng4.n, : eng4.n].clone(), eng4.basis_bits.clone()
+    g_f4, cnt_f4, basis_f4 = eng4.gain_p.clone(), eng4.counts_full().clone(), eng4.basis_bits.clone()
     w4, s4, used4, sp4, sn4 = eng4.select_and_apply(0.0)
     eng4.score_all()
     g_f4_step2 = eng4.gain_p.clone()
@@ -309,7 +446,7 @@ def test_c4_full_size_properties(M):
     assert eng.operand == "i8" and eng.assoc_operand == "i8"
     nb = eng.build_basis(0.5)
     assert nb == int(eng.alive.sum().item()) and nb > 17000 and nb == nb4
-    assert torch.equal(cnt_f4, eng.cnt[: eng.n, : eng.n]) and torch.equal(basis_f4, eng.basis_bits)
+    assert torch.equal(cnt_f4, eng.counts_full()) and torch.equal(basis_f4, eng.basis_bits)
     eng.score_all()
     g_pair = eng.gain_p.clone()
     assert torch.equal(g_f4, g_pair)                                # kind::mxf4 == kind::i8, bit for bit
