@@ -268,6 +268,28 @@ int bmf_confusion_triplets(const int32_t* rows, const int32_t* cols, const uint8
                            const uint64_t* u_words, int64_t kw, const uint64_t* v_words,
                            int64_t* counts, bmf_stream_t stream);
 
+/* ---- GreConDPlus._expansion, PyBMF/models/GreConDPlus.py:267-308 ------------------
+ * delta[i] = coverage_score(x_i, old_i | pattern) - coverage_score(x_i, old_i) in the reference's fp64 order for every row
+ * whose bit in exclude_bits (nullable; a bit vector over the rows) is clear, +0.0 for excluded rows; best[0] = bits of
+ * max(delta), best[1] = FIRST argmax (nullable).  Row-wise expansion (axis = 1): rows of X / X_old, pattern = v,
+ * exclude = u; column-wise (axis = 0): rows of X^T / X_old^T, pattern = u, exclude = v. */
+int bmf_expand_scores(const uint64_t* x_bits, const uint64_t* old_bits, int64_t rows, int64_t words,
+                      const uint64_t* pattern_bits, const uint64_t* exclude_bits, double w_fp, double w_fn,
+                      double* delta, int64_t* best, bmf_stream_t stream);
+/* ---- AssoOpt.set_optimal_row, PyBMF/models/AssoOpt.py:69-80 -------------------------
+ * best_trial[i] = FIRST argmax over j in [0, 2^k) of (-w_fp) FP + w_fn TP of the OR of the V^T rows selected by j
+ * (factor l = bit k-1-l of j, the MSB-first order of int2bin, AssoOpt.py:83-86) against data row i; best_score
+ * (nullable) receives the winning score.  k <= 20. */
+int bmf_optimal_rows(const uint64_t* x_bits, int64_t m, int64_t words, const uint64_t* vt_bits, int64_t k, double w_fp,
+                     double w_fn, int64_t* best_trial, double* best_score, bmf_stream_t stream);
+
+/* ---- measurement aid (bench.py): tensor-pipe ceiling measured on the box -----------------------------------
+ * One launch in which a CTA pair per TPC issues iters x 4 back-to-back tcgen05.mma instructions of the production shape
+ * (kind 0: kind::i8 256 x 256 x 32; kind 1: kind::mxf4 256 x 256 x 64, unit scales) on sparse small-integer operands
+ * resident in shared memory -- no TMA, no epilogue.  The caller times the launch with CUDA events; *ops_out_host (HOST
+ * pointer, nullable) receives the operations performed.  This is the roofline denominator of the scoring kernels. */
+int bmf_probe_mma_rate(int32_t kind, int32_t iters, double* ops_out_host, bmf_stream_t stream);
+
 /* ---- AssoIter.get_refined_column, PyBMF/models/AssoIter.py:80-100 -------------------------
  * One streaming pass over the rows: cover without factor `col`, get_vector with basis
  * V[:, col], overwrite bit `col` of u_words (AssoIter.py:60), and accumulate

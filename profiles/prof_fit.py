@@ -1,19 +1,17 @@
-import sys, time, cProfile, pstats, os
-sys.path.insert(0, os.getcwd())
-import torch
-from pybmf_b200 import models, synth
+"""Profiling target: ONE Asso(k).fit() at a BASELINE config through the public API (for ncu launch lists / --set full).
+    python profiles/prof_fit.py [c4|c2] [k] [rescore]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from pybmf_b200 import models, synth  # noqa: E402
+
+cfg = sys.argv[1] if len(sys.argv) > 1 else "c4"
+k = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+rescore = sys.argv[3] if len(sys.argv) > 3 else "auto"
 models.SILENT = True
-wl = sys.argv[1] if len(sys.argv) > 1 else "c4"
-X = synth.config_c4() if wl == "c4" else synth.config_c2()
-kw = dict(task="reconstruction", save_model=False, show_logs=False, show_result=False)
-models.Asso(tau=0.5, k=2, w_fp=0.5).fit(X, **kw)   # warm
-torch.cuda.synchronize()
-pr = cProfile.Profile()
-t0 = time.perf_counter()
-pr.enable()
-mdl = models.Asso(tau=0.5, k=int(sys.argv[2]) if len(sys.argv) > 2 else 5, w_fp=0.5)
-mdl.fit(X, **kw)
-torch.cuda.synchronize()
-pr.disable()
-print("fit seconds", time.perf_counter() - t0)
-pstats.Stats(pr).sort_stats("cumulative").print_stats(35)
+X = synth.config_c4() if cfg == "c4" else synth.config_c2()
+mdl = models.Asso(tau=0.5, k=k, w_fp=0.5, rescore=rescore)
+mdl.fit(X, task="reconstruction", save_model=False, show_logs=False, show_result=False)
+print("fit ok:", cfg, k, rescore, [s["winner"] for s in mdl.fit_steps_], "launches", mdl._dev_launches)

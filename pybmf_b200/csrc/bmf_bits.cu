@@ -1228,6 +1228,134 @@ refine_column_kernel(const uint64_t* __restrict__ xb, int64_t m, int64_t n, int6
   }
 }
 
+// =========================================================================================
+// GreConD+ expansion scores (PyBMF/models/GreConDPlus.py:267-308, `_expansion`): adding `pattern` to every row that is
+// not excluded, how much does each row's coverage score change?
+//   delta_i = [(-w_fp)(FP_i + N_i) + w_fn (TP_i + P_i)] - [(-w_fp) FP_i + w_fn TP_i]   (fp64, the reference's order)
+// with TP_i / FP_i of `old` against x and P_i / N_i the new true / false positives; excluded rows keep X_new = X_old,
+// so delta_i = +0.0.  Row-wise expansion passes (X, X_old, pattern = v, exclude = u); column-wise expansion passes
+// the transposed bit matrices with (pattern = u, exclude = v).  One warp per row, 128-bit row streams.
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+expand_delta_kernel(const uint64_t* __restrict__ xb, const uint64_t* __restrict__ ob, int64_t rows, int64_t words,
+                    const uint64_t* __restrict__ pattern, const uint64_t* __restrict__ exclude, double neg_w_fp,
+                    double w_fn, double* __restrict__ delta) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t pairs = words >> 1;
+  for (int64_t i = warp0; i < rows; i += nwarps) {
+    if (exclude != nullptr && ((exclude[i >> 6] >> (i & 63)) & 1ull)) {      // warp-uniform
+      if (lane == 0) delta[i] = 0.0;
+      continue;
+    }
+    int tp = 0, pd = 0, P = 0, A = 0;
+    for (int64_t p = lane; p < pairs; p += 32) {
+      const ulonglong2 x = ld_words2(xb + i * words + 2 * p);
+      const ulonglong2 o = ld_words2(ob + i * words + 2 * p);
+      const ulonglong2 v = ld_words2(pattern + 2 * p);
+      tp += __popcll(x.x & o.x) + __popcll(x.y & o.y);
+      pd += __popcll(o.x) + __popcll(o.y);
+      P += __popcll(x.x & ~o.x & v.x) + __popcll(x.y & ~o.y & v.y);
+      A += __popcll(~o.x & v.x) + __popcll(~o.y & v.y);                       // |v & ~old| = P + N
+    }
+    tp = warp_sum(tp); pd = warp_sum(pd); P = warp_sum(P); A = warp_sum(A);
+    if (lane == 0) {
+      const int fp = pd - tp, N = A - P;
+      const double s_old = cover_score_f64(neg_w_fp, w_fn, fp, tp);
+      const double s_new = cover_score_f64(neg_w_fp, w_fn, fp + N, tp + P);
+      delta[i] = __dsub_rn(s_new, s_old);
+    }
+  }
+}
+
+// max and FIRST argmax of a float64 vector (numpy's d_scores.max() / d_scores.argmax()); out[0] = bits, out[1] = index
+__global__ void __launch_bounds__(1024) argmax_first_f64_kernel(const double* __restrict__ v, int64_t n, long long* __restrict__ out) {
+  __shared__ double s_val[32];
+  __shared__ long long s_idx[32];
+  double best = 0.0;
+  long long idx = -1;
+  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+    const double x = v[j];
+    if (idx < 0 || x > best) { best = x; idx = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (oi >= 0 && (idx < 0 || ov > best || (ov == best && oi < idx))) { best = ov; idx = oi; }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_val[warp] = best; s_idx[warp] = idx; }
+  __syncthreads();
+  if (warp == 0) {
+    best = s_val[lane];
+    idx = s_idx[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (oi >= 0 && (idx < 0 || ov > best || (ov == best && oi < idx))) { best = ov; idx = oi; }
+    }
+    if (lane == 0) { out[0] = __double_as_longlong(best); out[1] = idx; }
+  }
+}
+
+// =========================================================================================
+// AssoOpt.set_optimal_row (PyBMF/models/AssoOpt.py:69-80): for data row i try all 2^k usage vectors, the score of trial
+// j is (-w_fp) FP + w_fn TP of  OR_{l in bits(j)} V^T_l  against x_i, and the FIRST maximum wins (np.argmax).
+// int2bin (AssoOpt.py:83-86) writes j MSB first, so factor l is bit (k - 1 - l) of j.
+// One CTA per data row, trials strided over the threads; V^T sits in shared memory when it fits.
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+optimal_row_kernel(const uint64_t* __restrict__ xb, int64_t m, int64_t words, const uint64_t* __restrict__ vt, int k,
+                   double neg_w_fp, double w_fn, int vt_in_smem, long long* __restrict__ best_trial,
+                   double* __restrict__ best_score) {
+  extern __shared__ uint64_t opt_smem[];
+  __shared__ double s_val[8];
+  __shared__ long long s_idx[8];
+  const uint64_t* V = vt;
+  if (vt_in_smem) {
+    for (int64_t e = threadIdx.x; e < (int64_t)k * words; e += blockDim.x) opt_smem[e] = vt[e];
+    __syncthreads();
+    V = opt_smem;
+  }
+  const long long trials = 1ll << k;
+  for (int64_t i = blockIdx.x; i < m; i += gridDim.x) {
+    const uint64_t* x = xb + i * words;
+    double best = 0.0;
+    long long idx = -1;
+    for (long long j = threadIdx.x; j < trials; j += blockDim.x) {
+      int tp = 0, pd = 0;
+      for (int64_t w = 0; w < words; ++w) {
+        uint64_t acc = 0;
+        for (int l = 0; l < k; ++l)
+          if ((j >> (k - 1 - l)) & 1ll) acc |= V[(int64_t)l * words + w];
+        tp += __popcll(acc & x[w]);
+        pd += __popcll(acc);
+      }
+      const double sc = cover_score_f64(neg_w_fp, w_fn, pd - tp, tp);
+      if (idx < 0 || sc > best) { best = sc; idx = j; }                    // ascending j per thread
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (oi >= 0 && (idx < 0 || ov > best || (ov == best && oi < idx))) { best = ov; idx = oi; }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) { s_val[warp] = best; s_idx[warp] = idx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int q = 1; q < (int)(blockDim.x >> 5); ++q)
+        if (s_idx[q] >= 0 && (idx < 0 || s_val[q] > best || (s_val[q] == best && s_idx[q] < idx))) { best = s_val[q]; idx = s_idx[q]; }
+      best_trial[i] = idx;
+      if (best_score != nullptr) best_score[i] = best;
+    }
+  }
+}
+
 static inline int row_stream_grid() { return num_sms() * 8; }
 
 }  // namespace bmf
@@ -1642,5 +1770,41 @@ extern "C" int bmf_refine_column(const uint64_t* x_bits, int64_t m, int64_t n, i
       x_bits, m, n, words, u_words, kw, vt_bits, col, wa, wb, -w_fp, w_fn,
       reinterpret_cast<unsigned long long*>(out));
   BMF_LAUNCH_CHECK("bmf_refine_column");
+  return 0;
+}
+
+
+extern "C" int bmf_expand_scores(const uint64_t* x_bits, const uint64_t* old_bits, int64_t rows, int64_t words,
+                                 const uint64_t* pattern_bits, const uint64_t* exclude_bits, double w_fp, double w_fn,
+                                 double* delta, int64_t* best, bmf_stream_t stream) {
+  BMF_REQUIRE(x_bits && old_bits && pattern_bits && delta, "bmf_expand_scores: null pointer");
+  BMF_REQUIRE(rows > 0 && words > 0 && words % 2 == 0, "bmf_expand_scores: bad shape");
+  int64_t blocks = ceil_div(rows, 8);
+  if (blocks > row_stream_grid()) blocks = row_stream_grid();
+  expand_delta_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x_bits, old_bits, rows, words, pattern_bits,
+                                                                     exclude_bits, -w_fp, w_fn, delta);
+  BMF_LAUNCH_CHECK("bmf_expand_scores");
+  if (best != nullptr) {
+    argmax_first_f64_kernel<<<1, 1024, 0, as_stream(stream)>>>(delta, rows, reinterpret_cast<long long*>(best));
+    BMF_LAUNCH_CHECK("bmf_expand_scores");
+  }
+  return 0;
+}
+
+extern "C" int bmf_optimal_rows(const uint64_t* x_bits, int64_t m, int64_t words, const uint64_t* vt_bits, int64_t k,
+                                double w_fp, double w_fn, int64_t* best_trial, double* best_score, bmf_stream_t stream) {
+  BMF_REQUIRE(x_bits && vt_bits && best_trial, "bmf_optimal_rows: null pointer");
+  BMF_REQUIRE(m > 0 && words > 0 && k >= 1 && k <= 20, "bmf_optimal_rows: 1 <= k <= 20 (2^k trials per row)");
+  const size_t vt_bytes = (size_t)k * (size_t)words * sizeof(uint64_t);
+  const int in_smem = vt_bytes <= 160 * 1024;
+  if (in_smem) {
+    int rc = check_cuda(cudaFuncSetAttribute(optimal_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vt_bytes),
+                        "bmf_optimal_rows");
+    if (rc) return rc;
+  }
+  int64_t blocks = m < (int64_t)num_sms() * 8 ? m : (int64_t)num_sms() * 8;
+  optimal_row_kernel<<<(unsigned)blocks, 256, in_smem ? vt_bytes : 0, as_stream(stream)>>>(
+      x_bits, m, words, vt_bits, (int)k, -w_fp, w_fn, in_smem, reinterpret_cast<long long*>(best_trial), best_score);
+  BMF_LAUNCH_CHECK("bmf_optimal_rows");
   return 0;
 }

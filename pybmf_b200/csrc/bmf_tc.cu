@@ -1252,6 +1252,99 @@ static int launch_gemm_f4s(const uint8_t* a, int64_t a_rows, const uint8_t* b, i
 }
 }  // namespace f4
 
+// =================================================================================================
+// Tensor-pipe ceiling probe (bench.py's roofline denominator, measured live on the box): a CTA pair per TPC issues
+// `iters` x 4 back-to-back tcgen05.mma instructions of the production shape -- kind::mxf4 M = 256, N = 256, K = 64
+// with unit scales, or kind::i8 M = 256, N = 256, K = 32 -- on operands that already sit in shared memory (sparse
+// small integers like the workload's; no TMA, no epilogue, one commit at the end).  What it measures is the issue rate
+// of the pipe itself at the clocks this kind of data sustains; the scoring kernels cannot be faster than this.
+// =================================================================================================
+namespace probe {
+using sm2::cluster_ctarank;
+using sm2::cluster_sync_all;
+using sm2::tcgen05_commit_2sm;
+using sm2::tcgen05_mma_i8_2sm;
+using f4::tcgen05_mma_f4_2sm;
+using f4::tmem_st_32x32_x8;
+constexpr int PROBE_THREADS = 128;
+constexpr int PROBE_SMEM = 2 * 16384 + 1024 + 64;
+
+template <int KIND>   // 0 = kind::i8, 1 = kind::mxf4
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PROBE_THREADS, 1)
+mma_rate_probe_kernel(int iters, uint32_t seed) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * 16384);
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5;
+  const bool leader = cluster_ctarank() == 0;
+  // operands: A = 128 rows x 128 B, B = 128 rows x 128 B per CTA; ~1/32 of the elements are a small integer
+  for (int i = threadIdx.x; i < 2 * 16384 / 4; i += PROBE_THREADS) {
+    uint32_t h = (uint32_t)i * 2654435761u + seed + blockIdx.x * 40503u;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    uint32_t w = 0;
+    if ((h & 7u) == 0u) w = (KIND == 1 ? 0x2u : 0x1u) << (((h >> 3) & 7u) * 4u) % 32u;
+    reinterpret_cast<uint32_t*>(smem)[i] = w;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(bars), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_base_slot);
+  if (KIND == 1) {                                        // unit UE8M0 scale factors in columns [496, 512)
+    const uint32_t sf_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + 496u;
+    tmem_st_32x32_x8(sf_addr, f4::SF_ONE);
+    tmem_st_32x32_x8(sf_addr + 8u, f4::SF_ONE);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  if (warp == 0 && leader) {
+    const uint32_t tb = warp_uniform(tmem_base), sb = warp_uniform(smem_u32(smem));
+    const uint64_t da = make_smem_desc(sb), db = make_smem_desc(sb + 16384u);
+    const uint32_t sfa = tb + 496u, sfb = tb + 504u;
+    constexpr uint32_t idesc_f4 = f4::idesc_f4(256);
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t d_tmem = tb + (uint32_t)((it & 1) ? 240 : 0);     // two accumulators, like the production kernels
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (KIND == 1)
+            tcgen05_mma_f4_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_f4, (uint32_t)(it > 1 || k),
+                               sfa, sfb);
+          else
+            tcgen05_mma_i8_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), sm2::IDESC_I8_2SM,
+                               (uint32_t)(it > 1 || k));
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one()) tcgen05_commit_2sm(smem_u32(bars));
+    __syncwarp();
+  }
+  mbar_wait(smem_u32(bars), 0);                          // the multicast commit arrives in both CTAs
+  tcgen05_fence_after();
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+}  // namespace probe
+
 // variant: 0 = auto (2-SM when the candidate rows are a multiple of 256), 1 = 1-SM, 2 = 2-SM
 template <int EPI>
 static int dispatch_gemm(int variant, const int8_t* a, int64_t a_rows, const int8_t* b, int64_t b_rows, int64_t ld,
@@ -1464,4 +1557,27 @@ extern "C" int bmf_cover_score_f4_general(const uint8_t* cand_plane, int64_t can
   ea.w_fp_fix = fix_ok ? llrint(w_fp * 1048576.0) : 0;
   ea.w_fn_fix = fix_ok ? llrint(w_fn * 1048576.0) : 0;
   return tc::f4::launch_gemm_f4<tc::EPI_GAIN2>(cand_plane, cand_pad, pq_plane, plane_rows, ld_bytes, ea, as_stream(stream));
+}
+
+
+// Tensor-pipe ceiling probe: see tc::probe.  kind 0 = kind::i8 (256 x 256 x 32 per instruction), 1 = kind::mxf4
+// (256 x 256 x 64).  Enqueues ONE launch of `iters` x 4 instructions per CTA pair on every TPC; the caller times it with
+// CUDA events.  *ops_out (host pointer) receives the operations the launch performs (2 * M * N * K per instruction).
+extern "C" int bmf_probe_mma_rate(int32_t kind, int32_t iters, double* ops_out_host, bmf_stream_t stream) {
+  BMF_REQUIRE((kind == 0 || kind == 1) && iters > 0 && iters <= (1 << 24), "bmf_probe_mma_rate: kind 0/1, 0 < iters <= 2^24");
+  const int pairs = num_sms() / 2;
+  int rc;
+  if (kind == 1) {
+    rc = check_cuda(cudaFuncSetAttribute(tc::probe::mma_rate_probe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         tc::probe::PROBE_SMEM), "bmf_probe_mma_rate");
+    if (rc) return rc;
+    tc::probe::mma_rate_probe_kernel<1><<<2 * pairs, tc::probe::PROBE_THREADS, tc::probe::PROBE_SMEM, as_stream(stream)>>>(iters, 12345u);
+  } else {
+    rc = check_cuda(cudaFuncSetAttribute(tc::probe::mma_rate_probe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         tc::probe::PROBE_SMEM), "bmf_probe_mma_rate");
+    if (rc) return rc;
+    tc::probe::mma_rate_probe_kernel<0><<<2 * pairs, tc::probe::PROBE_THREADS, tc::probe::PROBE_SMEM, as_stream(stream)>>>(iters, 12345u);
+  }
+  if (ops_out_host) *ops_out_host = 2.0 * 256.0 * 256.0 * (kind == 1 ? 64.0 : 32.0) * 4.0 * (double)iters * (double)pairs;
+  return check_cuda(cudaGetLastError(), "bmf_probe_mma_rate launch");
 }

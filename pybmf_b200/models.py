@@ -306,25 +306,28 @@ class BaseModel:
                 raise AttributeError(name) from None
             d["X_pd"] = U_.get_prediction(U=U, V=V, boolean=True)
             return d["X_pd"]
-        if name == "assoc" and "_dev_host_cnt" in d:            # Asso.py:207-212 from the device counts
-            cnt = d["_dev_host_cnt"].astype(np.float64)
-            s = np.diag(cnt).copy()
+        if name in ("assoc", "basis") and "_dev_keep" in d:
+            # `assoc` (Asso.py:207-212) and `basis` (Asso.py:231-234, minus the chosen rows Asso.py:106-107) stay on the
+            # device after a fit and come to the host the first time somebody reads them (55 MB of counts at the
+            # MovieLens shape: reading them eagerly cost more than the whole fit)
+            keep = d["_dev_keep"]
+            if name == "basis":
+                alive = keep["alive"].cpu().numpy().astype(bool)
+                idx = torch.from_numpy(np.flatnonzero(alive)).to(keep["basis_bits"].device)
+                rows = U_._bits_to_csr(keep["basis_bits"][idx], int(alive.sum()), keep["n"])
+                d["basis"] = _csr_to_lil_fast(rows)
+                return d["basis"]
+            if keep["cnt"] is None:
+                raise AttributeError("assoc: the n x n float64 association matrix is not kept for n > 8192 or when the "
+                                     "rows are sharded over several GPUs (%.1f GB at n = %d); use `basis`"
+                                     % (8e-9 * keep["n"] ** 2, keep["n"]))
+            cnt = keep["cnt"].cpu().numpy().astype(np.float64)
+            sdiag = np.diag(cnt).copy()
             out = np.zeros_like(cnt)
-            out[s > 0] = cnt[s > 0] / s[s > 0][:, None]
+            out[sdiag > 0] = cnt[sdiag > 0] / sdiag[sdiag > 0][:, None]
             d["assoc"] = lil_matrix(out)
+            keep["cnt"] = None
             return d["assoc"]
-        if name == "basis" and "_dev_host_basis" in d:          # candidates left after the fit (Asso.py:106-107)
-            d["basis"] = lil_matrix(d["_dev_host_basis"].astype(int))
-            return d["basis"]
-        if name == "basis" and "_dev_basis_bits" in d:          # wide matrices: unpacked from the device bit rows on demand
-            bits, alive, n = d.pop("_dev_basis_bits")
-            keep = alive.cpu().numpy().astype(bool)
-            rows = U_._bits_to_csr(bits[torch.from_numpy(np.flatnonzero(keep)).to(bits.device)], int(keep.sum()), n)
-            d["basis"] = rows.tolil()
-            return d["basis"]
-        if name == "assoc" and "_dev_basis_bits" in d:
-            raise AttributeError("assoc: the n x n float64 association matrix is not kept for n > 8192 (it would be "
-                                 "%.1f GB); use `basis`, or refit a column subset" % (8e-9 * d["_dev_basis_bits"][2] ** 2))
         raise AttributeError(name)
 
     def predict_X(self, U=None, V=None, u=None, v=None, us=None, vs=None, boolean=True):
@@ -344,6 +347,22 @@ class BaseModel:
         elif v is not None:
             Vm = U_.binarize(Vm, v)
         self.X_pd = U_.matmul(Um, Vm.T, boolean=boolean, sparse=True)
+
+
+def _csr_to_lil_fast(A: csr_matrix) -> lil_matrix:
+    """csr -> lil without scipy's Python loop over ALL rows (0.5 s for the 480189 x 20 usage matrix of the
+    Netflix-shaped config): the empty lil already holds one empty list per row, only non-empty rows are filled."""
+    A = A.tocsr()
+    out = lil_matrix(A.shape, dtype=A.dtype)
+    if A.nnz == 0:
+        return out
+    nz = np.flatnonzero(np.diff(A.indptr))
+    big_i, big_d = A.indices.tolist(), A.data.tolist()          # one conversion, then cheap list slices per row
+    rows, data = out.rows, out.data
+    for r, a, b in zip(nz.tolist(), A.indptr[nz].tolist(), A.indptr[nz + 1].tolist()):
+        rows[r] = big_i[a:b]
+        data[r] = big_d[a:b]
+    return out
 
 
 def _column(vec, n):
@@ -449,7 +468,7 @@ class Asso(BaseModel):
                 self._materialize_factors()
             if "_host_factors" in d:
                 Uc, Vc = self._unpack_host_factors()
-                d["U"], d["V"] = Uc.tolil(), Vc.tolil()
+                d["U"], d["V"] = _csr_to_lil_fast(Uc), _csr_to_lil_fast(Vc)
                 if "_dev_kept" not in d:
                     del d["_host_factors"]
                 return d[name]
@@ -458,6 +477,11 @@ class Asso(BaseModel):
     def _state_for_pickle(self):
         if "_host_factors" in self.__dict__:
             _ = self.U                                          # pickles carry the lil factors like the reference's
+        keep = self.__dict__.get("_dev_keep")
+        if keep is not None:                                    # ... and `basis` / `assoc` where they are small enough
+            _ = self.basis
+            if keep["cnt"] is not None:
+                _ = self.assoc
         return {k: v for k, v in self.__dict__.items() if not k.startswith("_dev") and k != "_host_factors"}
 
     # ---- init_model: association matrix and candidate basis (Asso.py:48-59, 191-235) -----------
@@ -466,6 +490,7 @@ class Asso(BaseModel):
         w_fn = 1 - self.w_fp if self.w_fn is None else self.w_fn
         self._dev = CoverEngine(self.X_train, self.w_fp, w_fn, scorer=self._scorer, assoc=self._assoc_kernel,
                                 rescore=self.__dict__.get("_rescore", "auto"))
+        self.rescore_ = self._dev.rescore                      # 'incremental' or 'full' (what this fit really runs)
         self._dev_nb = self._dev.build_basis(self.tau, prescore=True)
         self.__dict__.pop("assoc", None)
         self.__dict__.pop("basis", None)
@@ -475,11 +500,8 @@ class Asso(BaseModel):
         if dev is not None:
             # keep what the lazy `assoc` / `basis` attributes need, as host arrays
             self._dev_launches = dev.launches
-            if dev.n <= 8192 and dev.cnt is not None:
-                self._dev_host_cnt = dev.counts_full().cpu().numpy()
-                self._dev_host_basis = dev.basis_host()
-            else:                                              # wide matrices: keep the compact form (bit rows + alive mask)
-                self._dev_basis_bits = (dev.basis_bits, dev.alive, dev.n)
+            self._dev_keep = {"n": dev.n, "basis_bits": dev.basis_bits, "alive": dev.alive,
+                              "cnt": dev.counts_full() if (dev.n <= 8192 and dev.cnt is not None) else None}
         self.__dict__.pop("_dev_split_cache", None)
         self.__dict__.pop("_dev_nb", None)
 
@@ -722,3 +744,66 @@ class TransposedModel(Asso):
         X_test = X_test.T if X_test is not None else None
         self.model.fit(X_train, X_val, X_test, **kwargs)
         self.U, self.V = self.model.V, self.model.U
+
+
+class AssoOpt(Asso):
+    """Asso with an exhaustive search over each row of U -- PyBMF/models/AssoOpt.py:12-80 (SURVEY.md section 8f,
+    rank 4).  `set_optimal_row(i)` tries all 2^k usage vectors for data row i; here one kernel launch
+    (bmf_optimal_rows) does that for every row.  The reference's `_fit` ends in its defect D4
+    (`coverage_score(..., w=self.w)`, AssoOpt.py:65: there is no attribute `w`), which is reproduced: U is refined, then
+    the same AttributeError surfaces."""
+
+    def __init__(self, model, w_fp=1, w_fn=1):
+        self.check_params(model=model, w_fp=w_fp, w_fn=w_fn)
+
+    def check_params(self, **kwargs):
+        BaseModel.check_params(self, **kwargs)
+        if "model" in kwargs:
+            model = kwargs.get("model")
+            self.import_model(k=model.k, U=model.U, V=model.V, logs=model.logs)
+
+    def fit(self, X_train, X_val=None, X_test=None, **kwargs):
+        BaseModel.fit(self, X_train, X_val, X_test, **kwargs)
+        self._fit()
+        self.finish(show_logs=self.show_logs, save_model=self.save_model, show_result=self.show_result)
+
+    def init_model(self):
+        BaseModel.init_model(self)
+
+    def _init_factors(self):
+        BaseModel._init_factors(self)
+
+    def optimal_rows(self, rows=None):
+        """argmax trial of every data row (or of `rows`) and its score: int64 [m], float64 [m]."""
+        _native.require_gpu()
+        X = device.to_csr_pattern(self.X_train)
+        if rows is not None:
+            X = X[np.asarray(rows, dtype=np.int64)]
+        m = X.shape[0]
+        x_bits = U_._bits_on_device(X)
+        vt = U_._bits_on_device(U_._pattern(self.V).T.tocsr())
+        if vt.shape[0] != self.k:
+            raise ValueError("shapes (1,%d) and (%d,%d) not aligned" % (self.k, vt.shape[0], self.n))   # int2bin(j, k) @ V.T
+        best = device.zeros((max(m, 1),), torch.int64)
+        score = device.zeros((max(m, 1),), torch.float64)
+        if m > 0:
+            _native.call("bmf_optimal_rows", x_bits, m, x_bits.shape[1], vt, self.k, float(self.w_fp), float(self.w_fn),
+                         best, score)
+        return best.cpu().numpy()[:m], score.cpu().numpy()[:m]
+
+    def set_optimal_row(self, i):
+        """AssoOpt.py:69-80: index of the best of the 2^k usage vectors for row i (np.argmax: first maximum)."""
+        idx, _score = self.optimal_rows([i])
+        return int(idx[0])
+
+    def _fit(self):
+        tic = time.perf_counter()
+        results, _scores = self.optimal_rows()
+        _say("[I] Exhaustive search finished in {}s.".format(time.perf_counter() - tic))
+        k = self.k
+        bits = ((results[:, None] >> (k - 1 - np.arange(k))[None, :]) & 1).astype(np.int64)    # int2bin: MSB first
+        self.U[:, :] = lil_matrix(bits)
+        self.__dict__.pop("X_pd", None)
+        self.X_pd = U_.get_prediction(U=self.U, V=self.V, boolean=True)
+        score = U_.coverage_score(gt=self.X_train, pd=self.X_pd, w=self.w)         # AssoOpt.py:65 (D4)
+        self.evaluate(df_name="refinements", train_info={"score": score})
