@@ -957,11 +957,19 @@ __device__ __forceinline__ void panel_or_fast(const ulonglong2* Vs, int panel_pa
   }
 }
 
+// Row order (ROWMAP): 0 = every warp owns blocks of 32 CONSECUTIVE rows (one coalesced load of the usage words);
+// 1 = interleaved: a CTA owns super-blocks of 32 x (#warps) rows and at any moment its warps work on CONSECUTIVE rows
+// (warp w takes rows base + r * #warps + w), so the 2 KB segments the CTAs of one row range write (or read) at the same
+// time tile a contiguous stretch of memory the way a memset does, instead of 32 x #CTAs scattered rows.
+__device__ __forceinline__ int64_t panel_row(int rowmap, int64_t block, int r, int warp, int nw) {
+  return rowmap ? (block * nw * 32 + (int64_t)r * nw + warp) : (block * 32 + r);
+}
+
 template <bool COUNT_GT>
 __global__ void __launch_bounds__(PANEL_THREADS, 1)
 confusion_panel_kernel(const uint64_t* __restrict__ gt, int64_t m, int64_t words,
                        const uint64_t* __restrict__ u_words, const uint64_t* __restrict__ vt, int64_t k,
-                       int panel_chunks, int RING_DEPTH, unsigned long long* __restrict__ counts) {
+                       int panel_chunks, int RING_DEPTH, int rowmap, unsigned long long* __restrict__ counts) {
   extern __shared__ __align__(128) uint8_t panel_smem[];
   const int panel_pairs = panel_chunks * CH_PAIRS;
   const int row_bytes = panel_pairs * 16;
@@ -988,42 +996,53 @@ confusion_panel_kernel(const uint64_t* __restrict__ gt, int64_t m, int64_t words
   fence_proxy_async();
   load_vt_panel(Vs, vt, k, words, pair0, panel_pairs);     // ends with __syncthreads()
 
-  // this warp's rows: 32-row blocks gw, gw + nwarps, ...
-  const int64_t gw = (int64_t)blockIdx.y * PANEL_WARPS + warp;
-  const int64_t nwarps = (int64_t)gridDim.y * PANEL_WARPS;
-  const int64_t blocks_total = (m + 31) >> 5;
-  int my_blocks = 0, last_rows = 0;
-  if (gw < blocks_total) {
-    my_blocks = (int)((blocks_total - 1 - gw) / nwarps) + 1;
-    const int64_t last_block = gw + (int64_t)(my_blocks - 1) * nwarps;
-    last_rows = (int)((m - last_block * 32) < 32 ? (m - last_block * 32) : 32);
-  }
-  int to_issue = my_blocks > 0 ? (my_blocks - 1) * 32 + last_rows : 0;    // rows not yet requested
-  // issue side (meaningful in lane 0): next row segment to request, as an incrementally updated pointer
-  const uint64_t* iss_ptr = gt + 2 * pair0 + gw * 32 * words;
-  const int64_t step_block = (nwarps * 32 - 31) * words;
-  int iss_r = 0, iss_slot = 0;
+  // this warp's rows, in blocks of up to 32 (see panel_row): block ids blk0, blk0 + blk_step, ...
+  const int nw = PANEL_WARPS;
+  const int64_t blk0 = rowmap ? (int64_t)blockIdx.y : (int64_t)blockIdx.y * nw + warp;
+  const int64_t blk_step = rowmap ? (int64_t)gridDim.y : (int64_t)gridDim.y * nw;
+  const int64_t blk_rows = rowmap ? (int64_t)nw * 32 : 32;
+  const int64_t blocks_total = (m + blk_rows - 1) / blk_rows;
+  const int my_blocks = blk0 < blocks_total ? (int)((blocks_total - 1 - blk0) / blk_step) + 1 : 0;
+  auto rows_in = [&](int b) -> int {                       // valid rows of this warp in its b-th block
+    const int64_t first = panel_row(rowmap, blk0 + (int64_t)b * blk_step, 0, warp, nw);
+    if (first >= m) return 0;
+    const int64_t stride = rowmap ? nw : 1;
+    const int64_t cnt = (m - first + stride - 1) / stride;
+    return (int)(cnt < 32 ? cnt : 32);
+  };
+  // issue side (meaningful in lane 0): next row segment to request
+  int iss_b = 0, iss_r = 0, iss_slot = 0;
+  int iss_n = my_blocks > 0 ? rows_in(0) : 0;
+  while (iss_b < my_blocks && iss_n == 0) { ++iss_b; iss_n = iss_b < my_blocks ? rows_in(iss_b) : 0; }
+  const uint64_t* gt_panel = gt + 2 * pair0;
   auto issue = [&]() {
+    const int64_t row = panel_row(rowmap, blk0 + (int64_t)iss_b * blk_step, iss_r, warp, nw);
     mbar_expect_tx(bar0 + 8u * iss_slot, seg_bytes);
-    bulk_load(ring0 + (uint32_t)(iss_slot * row_bytes), iss_ptr, seg_bytes, bar0 + 8u * iss_slot);
+    bulk_load(ring0 + (uint32_t)(iss_slot * row_bytes), gt_panel + row * words, seg_bytes, bar0 + 8u * iss_slot);
     iss_slot = iss_slot == RING_DEPTH - 1 ? 0 : iss_slot + 1;
-    if (++iss_r == 32) { iss_r = 0; iss_ptr += step_block; } else { iss_ptr += words; }
-    --to_issue;
+    if (++iss_r == iss_n) {
+      iss_r = 0;
+      do { ++iss_b; iss_n = iss_b < my_blocks ? rows_in(iss_b) : 0; } while (iss_b < my_blocks && iss_n == 0);
+    }
   };
   if (lane == 0)
-    for (int d = 0; d < RING_DEPTH && to_issue > 0; ++d) issue();
+    for (int d = 0; d < RING_DEPTH && iss_b < my_blocks; ++d) issue();
 
-  HarleySeal8 hs_tp, hs_pd, hs_gt;
+  HarleySeal8 hs_tp, hs_gt;
+  long long n_pd = 0;
   int slot = 0;
   uint32_t phase = 0;
   bool second = false;
-  const uint64_t* u_ptr = u_words + gw * 32 + lane;
-  uint64_t u_next = (my_blocks > 0 && gw * 32 + lane < m) ? __ldg(u_ptr) : 0ull;
+  auto usage_of = [&](int b) -> uint64_t {                 // lane r holds the usage word of the block's r-th row
+    if (b >= my_blocks) return 0ull;
+    const int64_t row = panel_row(rowmap, blk0 + (int64_t)b * blk_step, lane, warp, nw);
+    return row < m ? __ldg(u_words + row) : 0ull;
+  };
+  uint64_t u_next = usage_of(0);
   for (int blk = 0; blk < my_blocks; ++blk) {
     const uint64_t u_cur = u_next;
-    u_ptr += nwarps * 32;
-    u_next = (blk + 1 < my_blocks && (gw + (int64_t)(blk + 1) * nwarps) * 32 + lane < m) ? __ldg(u_ptr) : 0ull;
-    const int nrows = blk + 1 < my_blocks ? 32 : last_rows;
+    u_next = usage_of(blk + 1);
+    const int nrows = rows_in(blk);
     for (int r = 0; r < nrows; ++r) {
       const uint64_t sel = __shfl_sync(0xffffffffu, u_cur, r);
       const ulonglong2* seg = reinterpret_cast<const ulonglong2*>(ring + (size_t)slot * row_bytes);
@@ -1038,9 +1057,11 @@ confusion_panel_kernel(const uint64_t* __restrict__ gt, int64_t m, int64_t words
 #pragma unroll
         for (int u = 0; u < 4; ++u) { w[2 * u] = g[u].x & d[u].x; w[2 * u + 1] = g[u].y & d[u].y; }
         if (!second) hs_tp.add8_first(w); else hs_tp.add8_second(w);
+        // |pd| goes through POPC (XU pipe) while |gt & pd| goes through the carry-save tree (LOP3 on the ALU pipe): ncu
+        // showed the ALU pipe 85 % busy with both counts on the tree (profiles/r01c), the XU pipe almost idle -- splitting
+        // the two counts over the two pipes takes ~30 LOP3 per row segment off the critical pipe
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { w[2 * u] = d[u].x; w[2 * u + 1] = d[u].y; }
-        if (!second) hs_pd.add8_first(w); else hs_pd.add8_second(w);
+        for (int u = 0; u < 4; ++u) n_pd += __popcll(d[u].x) + __popcll(d[u].y);
         if (COUNT_GT) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) { w[2 * u] = g[u].x; w[2 * u + 1] = g[u].y; }
@@ -1049,12 +1070,12 @@ confusion_panel_kernel(const uint64_t* __restrict__ gt, int64_t m, int64_t words
         second = !second;
       }
       __syncwarp();                                         // every lane has consumed the slot
-      if (lane == 0 && to_issue > 0) issue();               // refill it with the row RING_DEPTH ahead
+      if (lane == 0 && iss_b < my_blocks) issue();          // refill it with the row RING_DEPTH ahead
       if (++slot == RING_DEPTH) { slot = 0; phase ^= 1u; }
     }
   }
   const long long t_tp = warp_sum_ll(hs_tp.total());
-  const long long t_pd = warp_sum_ll(hs_pd.total());
+  const long long t_pd = warp_sum_ll(n_pd);
   const long long t_gt = COUNT_GT ? warp_sum_ll(hs_gt.total()) : 0;
   if (lane == 0 && (t_pd | t_gt)) {
     atomicAdd(counts + 0, (unsigned long long)t_tp);
@@ -1069,7 +1090,7 @@ confusion_panel_kernel(const uint64_t* __restrict__ gt, int64_t m, int64_t words
 constexpr int PRODUCT_THREADS = 1024;
 __global__ void __launch_bounds__(PRODUCT_THREADS, 1)
 bool_product_panel_kernel(const uint64_t* __restrict__ u_words, int64_t m, const uint64_t* __restrict__ vt,
-                          int64_t k, int64_t words, int panel_chunks, uint64_t* __restrict__ pd) {
+                          int64_t k, int64_t words, int panel_chunks, int rowmap, uint64_t* __restrict__ pd) {
   extern __shared__ __align__(128) uint8_t panel_smem[];
   ulonglong2* Vs = reinterpret_cast<ulonglong2*>(panel_smem);
   const int panel_pairs = panel_chunks * CH_PAIRS;
@@ -1077,18 +1098,24 @@ bool_product_panel_kernel(const uint64_t* __restrict__ u_words, int64_t m, const
   const int64_t pair0 = (int64_t)blockIdx.x * panel_pairs;
   load_vt_panel(Vs, vt, k, words, pair0, panel_pairs);
 
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (int64_t)blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.y * (blockDim.x >> 5);
-  uint64_t mine = warp0 * 32 + lane < m ? __ldg(u_words + warp0 * 32 + lane) : 0ull;
-  for (int64_t base = warp0 * 32; base < m; base += nwarps * 32) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // block index space: rowmap 0 -> 32-row blocks, one per warp and pass; rowmap 1 -> super-blocks, one per CTA and pass
+  const int64_t blk0 = rowmap ? (int64_t)blockIdx.y : (int64_t)blockIdx.y * nw + warp;
+  const int64_t blk_step = rowmap ? (int64_t)gridDim.y : (int64_t)gridDim.y * nw;
+  const int64_t blk_rows = rowmap ? (int64_t)nw * 32 : 32;
+  auto my_row = [&](int64_t blk) { return panel_row(rowmap, blk, lane, warp, nw); };
+  int64_t ri = my_row(blk0);
+  uint64_t mine = (blk0 * blk_rows < m && ri < m) ? __ldg(u_words + ri) : 0ull;
+  for (int64_t blk = blk0; blk * blk_rows < m; blk += blk_step) {
     const uint64_t cur = mine;
-    const int64_t nb = base + nwarps * 32 + lane;
-    mine = nb < m ? __ldg(u_words + nb) : 0ull;
-    const int nrows = (int)((m - base) < 32 ? (m - base) : 32);
-    for (int r = 0; r < nrows; ++r) {
+    const int64_t nxt = blk + blk_step;
+    ri = my_row(nxt);
+    mine = (nxt * blk_rows < m && ri < m) ? __ldg(u_words + ri) : 0ull;
+    for (int r = 0; r < 32; ++r) {
+      const int64_t row = panel_row(rowmap, blk, r, warp, nw);
+      if (row >= m) break;
       const uint64_t sel = __shfl_sync(0xffffffffu, cur, r);
-      uint64_t* out = pd + (base + r) * words;
+      uint64_t* out = pd + row * words;
       for (int c = 0; c < panel_chunks; ++c) {
         const int slot0 = c * CH_PAIRS + lane;
         if (pair0 + c * CH_PAIRS >= pairs) break;
@@ -1121,6 +1148,10 @@ static inline int confusion_ring_depth(int64_t k, int chunks) {
 }
 static inline size_t confusion_panel_smem(int64_t k, int chunks, int depth) {
   return (size_t)(k + PANEL_WARPS * depth) * chunks * CH_PAIRS * 16 + PANEL_WARPS * RING_DEPTH_MAX * 8;
+}
+static inline int panel_rowmap() {              // BMF_PANEL_ROWMAP=0 restores the blocked row order (A/B experiments)
+  const char* e = getenv("BMF_PANEL_ROWMAP");
+  return (e != nullptr && e[0] == '0') ? 0 : 1;
 }
 static inline bool panel_disabled() {
   const char* e = getenv("BMF_NO_PANEL");
@@ -1651,7 +1682,8 @@ extern "C" int bmf_bool_product(const uint64_t* u_words, int64_t m, int64_t kw, 
                                              (int)smem), "bmf_bool_product");
     if (rc) return rc;
     dim3 grid((unsigned)panels, (unsigned)splits);
-    bool_product_panel_kernel<<<grid, PRODUCT_THREADS, smem, as_stream(stream)>>>(u_words, m, vt_bits, k, words, chunks, pd_bits);
+    bool_product_panel_kernel<<<grid, PRODUCT_THREADS, smem, as_stream(stream)>>>(u_words, m, vt_bits, k, words, chunks,
+                                                                                panel_rowmap(), pd_bits);
     BMF_LAUNCH_CHECK("bmf_bool_product");
     return 0;
   }
@@ -1686,12 +1718,14 @@ static int launch_confusion(const uint64_t* gt_bits, const uint64_t* pd_bits, in
         rc = check_cuda(cudaFuncSetAttribute(confusion_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem), who);
         if (rc) return rc;
-        confusion_panel_kernel<false><<<grid, PANEL_THREADS, smem, st>>>(gt_bits, m, words, u_words, vt_bits, k, chunks, depth, c);
+        confusion_panel_kernel<false><<<grid, PANEL_THREADS, smem, st>>>(gt_bits, m, words, u_words, vt_bits, k, chunks, depth,
+                                                                         panel_rowmap(), c);
       } else {
         rc = check_cuda(cudaFuncSetAttribute(confusion_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem), who);
         if (rc) return rc;
-        confusion_panel_kernel<true><<<grid, PANEL_THREADS, smem, st>>>(gt_bits, m, words, u_words, vt_bits, k, chunks, depth, c);
+        confusion_panel_kernel<true><<<grid, PANEL_THREADS, smem, st>>>(gt_bits, m, words, u_words, vt_bits, k, chunks, depth,
+                                                                        panel_rowmap(), c);
       }
       rc = check_cuda(cudaGetLastError(), who);
       if (rc) return rc;

@@ -540,9 +540,9 @@ def test_model_is_picklable_and_lazy_attrs(M, tmp_path):
     assert not any(k.startswith("_dev") for k in back.__dict__)
     # the reference's pickle carries assoc and basis (Asso.py:54-55): so does this one (read from the device at save time)
     assert sp.isspmatrix_lil(back.__dict__["assoc"]) and sp.isspmatrix_lil(back.__dict__["basis"])
-    Bk, _ = O.build_basis(O.build_assoc(c["X"]), c["tau"])
-    chosen = [int(s["winner"]) for s in mdl.fit_steps_]
-    alive_rows = [i for i in range(Bk.shape[0]) if i not in chosen]       # no all-zero rows here: candidate index = row
+    Bk, src = O.build_basis(O.build_assoc(c["X"]), c["tau"])
+    chosen = [int(s["winner"]) for s in mdl.fit_steps_]                   # original column ids of the chosen rows
+    alive_rows = [r for r, j in enumerate(src) if int(j) not in chosen]
     assert np.array_equal(_dense(back.__dict__["basis"]), Bk[alive_rows])
     assoc = mdl.assoc
     assert sp.isspmatrix_lil(assoc) and np.array_equal(assoc.toarray(), O.build_assoc(c["X"]))

@@ -610,6 +610,56 @@ def test_c5_scale_panel_kernels_properties(nat, monkeypatch):
     assert int(cx[0].item()) == tp + fn and int(cp[0].item()) == tp + fp
 
 
+def test_c5_largest_point_blocks_against_cpu_restatement(nat):
+    """BASELINE configs[4] at its LARGEST point (1M x 100k, k = 64): the materialised product and the per-block TP / FP / FN
+    of the fused confusion kernel against the CPU restatement (oracle/asso_c.c: bmfo_bool_product + bmfo_confusion) on
+    four sampled 4096-row blocks (first, two interior, the ragged last one), plus the size-independent identities."""
+    import ctypes as C
+    from oracle import asso_oracle_c as OC
+    _native, device = nat
+    m, n, k = 1_000_000, 100_000, 64
+    words = device.words_for(n)
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+
+    def rnd(shape, ands):
+        w = torch.randint(-2 ** 63, 2 ** 63 - 1, shape, dtype=torch.int64, device="cuda", generator=g)
+        for _ in range(ands - 1):
+            w &= torch.randint(-2 ** 63, 2 ** 63 - 1, shape, dtype=torch.int64, device="cuda", generator=g)
+        return w
+    uw = rnd((m, 1), 5)
+    vt = rnd((k, words), 5)
+    vt[:, n // 64] &= (1 << (n % 64)) - 1
+    vt[:, (n + 63) // 64:] = 0
+    pd = device.zeros((m, words), torch.int64)
+    _native.call("bmf_bool_product", uw, m, 1, vt, k, words, pd)
+    x = pd.clone()
+    for c0 in range(0, m, 65536):                                   # ground truth = product with ~6 % of the bits flipped
+        blk = x[c0:c0 + 65536]
+        blk ^= rnd(blk.shape, 4)
+    x[:, n // 64] &= (1 << (n % 64)) - 1
+    x[:, (n + 63) // 64:] = 0
+    total = device.zeros((3,), torch.int64)
+    _native.call("bmf_confusion_factors", x, m, words, uw, 1, vt, k, -1, total, None, None)
+    vt_h = vt.cpu().numpy().view(np.uint64)
+    L = OC.lib()
+    for r0 in (0, 317 * 4096 + 17, 700_001, m - 3000):
+        r1 = min(m, r0 + 4096)
+        rows = r1 - r0
+        uw_h = np.ascontiguousarray(uw[r0:r1].cpu().numpy().view(np.uint64))
+        want_pd = np.zeros((rows, words), dtype=np.uint64)
+        L.bmfo_bool_product(OC._ptr(uw_h), rows, 1, OC._ptr(vt_h), k, words, -1, OC._ptr(want_pd))
+        assert np.array_equal(pd[r0:r1].cpu().numpy().view(np.uint64), want_pd), r0
+        x_h = np.ascontiguousarray(x[r0:r1].cpu().numpy().view(np.uint64))
+        want = np.zeros(3, dtype=np.int64)
+        L.bmfo_confusion(OC._ptr(x_h), OC._ptr(want_pd), rows, words, OC._ptr(want), None, None)
+        got = device.zeros((3,), torch.int64)
+        _native.call("bmf_confusion_factors", x[r0:r1], rows, words, uw[r0:r1], 1, vt, k, -1, got, None, None)
+        assert [int(v) for v in got.cpu().numpy()] == [int(v) for v in want], r0
+    cb = device.zeros((3,), torch.int64)
+    _native.call("bmf_confusion_bits", x, pd, m, words, -1, cb, None, None)
+    assert torch.equal(cb, total)                                   # fused == materialised at full size
+
+
 def test_confusion_triplets(nat):
     _native, device = nat
     rng = np.random.RandomState(8)
