@@ -96,3 +96,66 @@ def test_live_reference_small():
     r = O.asso_fit(X, 3, 0.3, 0.4)
     assert np.array_equal(r["U"], (mdl.U.toarray() != 0)) and np.array_equal(r["V"], (mdl.V.toarray() != 0))
     assert [l["score"] for l in r["logs"]] == [float(v) for v in mdl.logs["updates"][("train", 0, "score")]]
+
+
+# ---- the bit-packed C restatement (oracle/asso_c.c through oracle/asso_oracle_c.py) --------------------------
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_c_restatement_matches_reference_outputs(name):
+    """The C restatement that writes the full-size fixtures is pinned against the genuine reference's golden outputs:
+    U, V, TP / FP per step, scores (bit for bit for a/2^s weights, rtol 1e-12 otherwise), D1 truncation, D2 error."""
+    import scipy.sparse as sp
+    from oracle import asso_oracle_c as OC
+    c = load_golden(name)
+    g = c["g"]
+    r = OC.asso_fit(sp.csr_matrix(c["X"]), c["k"], c["tau"], c["w_fp"], c["w_fn"])
+    assert r["error"] == c["error"]
+    m, n = c["X"].shape
+    U = np.stack(r["U_cols"], 1) if r["U_cols"] else np.zeros((m, 0), np.uint8)
+    V = np.stack(r["V_cols"], 1) if r["V_cols"] else np.zeros((n, 0), np.uint8)
+    assert U.shape == g["U"].shape and np.array_equal(U, g["U"]) and np.array_equal(V, g["V"])
+    if "log_TP" in g:
+        assert [s["tp"] for s in r["steps"]] == list(g["log_TP"].astype(np.int64))
+        assert [s["fp"] for s in r["steps"]] == list(g["log_FP"].astype(np.int64))
+        sc = np.array([s["score"] for s in r["steps"]])
+        if O.integer_weights(c["w_fp"], c["w_fn"]) is not None:
+            assert np.array_equal(sc, g["log_score"])
+        else:
+            np.testing.assert_allclose(sc, g["log_score"], rtol=1e-12, atol=0)
+    if "iter_U" in g:
+        it = OC.asso_iter_fit(sp.csr_matrix(c["X"]), g["U"], g["V"], c["k"], c["w_fp"], c["w_fn"])
+        assert np.array_equal(it["U"], g["iter_U"])
+        assert np.array_equal(np.array([(a, int(b)) for a, b in it["trace"]]).reshape(-1, 2), g["iter_trace"])
+
+
+def test_c2_fixture_is_reproduced_and_agrees_with_numpy_restatement():
+    """tests/golden/c2_digest.json (BASELINE configs[1], full size, k = 20) is what the C restatement computes today, and
+    its first greedy steps equal the dense numpy restatement's (the two share no code; k = 20 was compared once when the
+    fixture was made: 82 s of numpy time)."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from oracle import asso_oracle_c as OC
+    from pybmf_b200 import synth
+    X = synth.config_c2()
+    want = json.load(open(os.path.join(GOLDEN, "c2_digest.json")))
+    r = OC.asso_fit(X, 20, 0.5, 0.5)
+    for key in ("winners", "score_bits", "used", "tp", "fp", "u_sha256", "v_sha256"):
+        assert r["digest"][key] == want[key], key
+    w = O.asso_fit(X, 2, 0.5, 0.5)
+    U = np.stack(r["U_cols"], 1)
+    assert np.array_equal(U[:, :2], w["U"]) and [l["score"] for l in w["logs"]] == [s["score"] for s in r["steps"][:2]]
+
+
+def test_c4_fixture_is_self_consistent():
+    """tests/golden/c4_digest.json (480189 x 17770, k = 20; 40 min of host time to regenerate): structural checks."""
+    import json
+    import os
+    from conftest import GOLDEN
+    d = json.load(open(os.path.join(GOLDEN, "c4_digest.json")))
+    assert d["m"] == 480189 and d["n"] == 17770 and d["k"] == 20 and len(d["winners"]) == 20 and d["error"] == ""
+    assert len(set(d["winners"])) == 20 and all(0 <= w < d["n"] for w in d["winners"])
+    tp, fp = np.array(d["tp"]), np.array(d["fp"])
+    assert (np.diff(tp) > 0).all() and (np.diff(fp) >= 0).all() and tp[-1] <= d["sum_x"] == d["nnz"]
+    score = np.array([np.frombuffer(bytes.fromhex(h), dtype=np.float64)[0] for h in d["score_bits"]])
+    assert np.array_equal(score, 0.5 * tp - 0.5 * fp)                # w = [0.5, 0.5]: score = coverage of the whole cover
+    assert (np.diff(score) > 0).all()
