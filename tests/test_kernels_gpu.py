@@ -642,7 +642,7 @@ def test_c5_largest_point_blocks_against_cpu_restatement(nat):
     _native.call("bmf_confusion_factors", x, m, words, uw, 1, vt, k, -1, total, None, None)
     vt_h = vt.cpu().numpy().view(np.uint64)
     L = OC.lib()
-    for r0 in (0, 317 * 4096 + 17, 700_001, m - 3000):
+    for r0 in (0, 117 * 4096 + 17, 700_001, m - 3000):
         r1 = min(m, r0 + 4096)
         rows = r1 - r0
         uw_h = np.ascontiguousarray(uw[r0:r1].cpu().numpy().view(np.uint64))
