@@ -55,7 +55,7 @@ def load_peaks():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
@@ -96,8 +96,15 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in rows)]
         busy = [v for v in sm if v > 0.5 * (max(mx) if mx else 1)] or sm
+        watts = []
+        for r in rows:
+            try:
+                watts.append(float(r[6]))
+            except (IndexError, ValueError):
+                pass
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "power_w_max": max(watts) if watts else None,
+                "power_w_median": statistics.median(watts) if watts else None}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -363,8 +370,11 @@ def measure_mma_peak(torch, kind, iters=4096, reps=5):
 def timed_fits(models, torch, dist, world, X, tau, w_fp, k, scorer, rescore, repeats):
     """`repeats` whole Asso(k).fit() calls through the public API from the host scipy matrix.  Returns the per-run
     seconds (max over ranks), seconds incl. the first read of U / V, the last model and what ended the fit."""
+    import gc
     secs, plus, err, mdl = [], [], None, None
     for _ in range(repeats):
+        mdl = None                                              # the previous model (a lil U of ~1e6 Python lists at c4) is
+        gc.collect()                                            # released BEFORE the timed region, not inside it
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

@@ -14,7 +14,7 @@ models.SILENT = True
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 X = synth.config_c4()
 kw = dict(task="reconstruction", save_model=False, show_logs=False, show_result=False)
-for trace in ("0", "1", "0"):
+for trace in ("0", "0", "1", "1", "0", "0"):
     os.environ["BMF_FIT_TRACE"] = trace
     if world > 1:
         dist.barrier()
@@ -23,6 +23,8 @@ for trace in ("0", "1", "0"):
     models.Asso(tau=0.5, k=k, w_fp=0.5).fit(X, **kw)
     torch.cuda.synchronize()
     if rank == 0:
-        print("fit(k=%d) world=%d trace=%s: %.3f s" % (k, world, trace, time.perf_counter() - t0), file=sys.stderr)
+        print("fit(k=%d) world=%d trace=%s: %.3f s  (torch reserved %.1f GB, allocated %.1f GB)" % (
+            k, world, trace, time.perf_counter() - t0, torch.cuda.memory_reserved() / 1e9, torch.cuda.memory_allocated() / 1e9),
+            file=sys.stderr)
 if world > 1:
     dist.destroy_process_group()

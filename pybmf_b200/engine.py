@@ -70,7 +70,7 @@ class _Trace:
 
     def __init__(self):
         self.on = os.environ.get("BMF_FIT_TRACE", "0") == "1"
-        self.t = time.perf_counter()
+        self.t = self.t0 = time.perf_counter()
         self.rows = []
 
     def mark(self, name):

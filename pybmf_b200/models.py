@@ -401,6 +401,7 @@ class Asso(BaseModel):
     def fit(self, X_train, X_val=None, X_test=None, **kwargs):
         self.__dict__.pop("U", None)                           # a fit always starts from empty factors
         self.__dict__.pop("V", None)
+        self._dev_t0 = time.perf_counter()
         super().fit(X_train, X_val, X_test, **kwargs)
         self._dev_log_batch = []
         try:
@@ -502,6 +503,7 @@ class Asso(BaseModel):
         w_fn = 1 - self.w_fp if self.w_fn is None else self.w_fn
         self._dev = CoverEngine(self.X_train, self.w_fp, w_fn, scorer=self._scorer, assoc=self._assoc_kernel,
                                 rescore=self.__dict__.get("_rescore", "auto"))
+        self._dev.trace.rows.insert(0, ("before_engine", self._dev.trace.t0 - self.__dict__.get("_dev_t0", self._dev.trace.t0)))
         self.rescore_ = self._dev.rescore                      # 'incremental' or 'full' (what this fit really runs)
         self._dev_nb = self._dev.build_basis(self.tau, prescore=True)
         self.__dict__.pop("assoc", None)
@@ -528,7 +530,8 @@ class Asso(BaseModel):
         m, n = self.m, self.n
         size = m * n
         n_basis = self._dev_nb
-        stepwise = self.X_val is not None or self.X_test is not None or dev.trace.on
+        stepwise = (self.X_val is not None or self.X_test is not None
+                    or os.environ.get("BMF_FIT_TRACE_STEPS", "0") == "1")
         chunk = 1 if stepwise else (self.k if self.k is not None else 16)
         k = 0                                                 # next greedy step to book (the reference's `k`)
         enq = 0                                               # steps enqueued so far
