@@ -1246,11 +1246,11 @@ static int launch_gemm_f4s(const uint8_t* a, int64_t a_rows, const uint8_t* b, i
   const int pairs_max = num_sms() / 2;
   const int pairs = (int)(tiles < pairs_max ? tiles : pairs_max);
   // Raster: candidate tiles cycle fastest inside a group of group_m, data-row tiles advance per group pass.  Measured at c4
-  // (profiles/r02_group_sweep.log; time is the same 34.6 ms for every setting that avoids the cliff): one group holding ALL
-  // candidate tiles -- a wave of 74 pairs then reads ~1 row super tile and every candidate tile -- draws the least power
-  // (427 W median vs 484 W at 16) at 27.8 GB of DRAM reads per launch; groups of 16 read 28.3 GB; a group of 35 (an 80 MB
-  // panel) falls off the L2 cliff: 134 GB, hit rate 66 %, sw_power_cap at 1.82 GHz -- the 126 MB L2 is two 63 MB halves.
-  int group_m = mt <= pairs_max ? mt : 16;
+  // (profiles/r02_group_sweep.log, profiles/r02g_shard_kernel_probe.log): groups of 8 / 16 / 24 candidate tiles (18-55 MB
+  // candidate panels) all run at the pipe's issue rate (34.6 ms; 28 GB of DRAM reads per launch at 16); a group of 35 (an
+  // 80 MB panel) falls off the L2 cliff -- 134 GB, hit rate 66 %, sw_power_cap -- because the 126 MB L2 is two 63 MB halves;
+  // one group over ALL 70 candidate tiles (160 MB panel) is 30 % slower (43 ms).  Keep 16.
+  int group_m = 16;
   if (const char* e = getenv("BMF_GROUP_M2")) { int v = atoi(e); if (v >= 1 && v <= 1024) group_m = v; }
   gemm_f4s_2sm_kernel<EPI><<<2 * pairs, NUM_THREADS, SMEM_BYTES_S, stream>>>(ma, mb0, mb1, mt, st, kb, group_m, ea);
   return check_cuda(cudaGetLastError(), "gemm_f4s_2sm_kernel launch");
