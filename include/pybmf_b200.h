@@ -283,6 +283,21 @@ int bmf_expand_scores(const uint64_t* x_bits, const uint64_t* old_bits, int64_t 
 int bmf_optimal_rows(const uint64_t* x_bits, int64_t m, int64_t words, const uint64_t* vt_bits, int64_t k, double w_fp,
                      double w_fn, int64_t* best_trial, double* best_score, bmf_stream_t stream);
 
+/* ---- on-device synthetic inputs -----------------------------------------------------
+ * The generators' recipe (PyBMF/generators/BaseGenerator.py:202-221, PyBMF/utils/generator_utils.py:30-49) on bit rows,
+ * with a counter-based generator: bit (i, j) of a stream depends only on (seed, stream_id, i, j), so every rank can
+ * generate its own row range [row0, row0 + rows) of the same logical matrix.
+ * bmf_random_bits: bits[r][.] = Bernoulli(p) for logical row row0 + r (pad bits 0).
+ * bmf_noise_bits : add_noise -- ones dropped with probability p_pos, then entries set with probability p_neg.
+ * bmf_transpose_bits: bits [rows][words] -> bits_t [ncols][words_t] (caller zero-fills bits_t's pad words), the X^T the
+ * association needs when X never existed as a csr. */
+int bmf_random_bits(uint64_t* bits, int64_t rows, int64_t ncols, int64_t words, int64_t row0, uint64_t seed,
+                    uint64_t stream_id, double p, bmf_stream_t stream);
+int bmf_noise_bits(uint64_t* bits, int64_t rows, int64_t ncols, int64_t words, int64_t row0, uint64_t seed, double p_pos,
+                   double p_neg, bmf_stream_t stream);
+int bmf_transpose_bits(const uint64_t* bits, int64_t rows, int64_t ncols, int64_t words, uint64_t* bits_t,
+                       int64_t words_t, bmf_stream_t stream);
+
 /* ---- measurement aid (bench.py): tensor-pipe ceiling measured on the box -----------------------------------
  * One launch in which a CTA pair per TPC issues iters x 4 back-to-back tcgen05.mma instructions of the production shape
  * (kind 0: kind::i8 256 x 256 x 32; kind 1: kind::mxf4 256 x 256 x 64, unit scales) on sparse small-integer operands

@@ -56,6 +56,9 @@ SIGNATURES = {
     "bmf_basis_threshold_rows": [_p, _i64, _i64, _i64, _i64, _i32, _f64, _p, _i64, _p, _p, _p],
     "bmf_expand_scores": [_p, _p, _i64, _i64, _p, _p, _f64, _f64, _p, _p, _p],
     "bmf_optimal_rows": [_p, _i64, _i64, _p, _i64, _f64, _f64, _p, _p, _p],
+    "bmf_random_bits": [_p, _i64, _i64, _i64, _i64, C.c_uint64, C.c_uint64, _f64, _p],
+    "bmf_noise_bits": [_p, _i64, _i64, _i64, _i64, C.c_uint64, _f64, _f64, _p],
+    "bmf_transpose_bits": [_p, _i64, _i64, _i64, _p, _i64, _p],
     "bmf_probe_mma_rate": [_i32, _i32, _p, _p],
     "bmf_refine_column": [_p, _i64, _i64, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _f64, _f64, _p, _p],
 }

@@ -1387,6 +1387,83 @@ optimal_row_kernel(const uint64_t* __restrict__ xb, int64_t m, int64_t words, co
   }
 }
 
+// =========================================================================================
+// On-device synthetic inputs: the generators' recipe -- Boolean product of two random
+// factors (PyBMF/generators/BaseGenerator.py:202-221 boolean_matmul) followed by add_noise
+// (PyBMF/utils/generator_utils.py:30-49: ones dropped with probability p_pos, then every entry set with probability
+// p_neg) -- with a COUNTER-BASED generator: bit (i, j) of stream s is a pure function of (seed, s, i, j), so a rank that
+// generates only its own row range produces exactly the rows a single GPU would.  Not bit-identical to numpy's
+// Mersenne twister (validated by density / shard-independence / a fit against the CPU restatement on the same bits).
+// =========================================================================================
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// 64 Bernoulli(p) bits for global bit indices [base, base + 64): two draws per 64-bit hash (threshold = p * 2^32)
+__device__ __forceinline__ uint64_t bernoulli_word(uint64_t seed, uint64_t stream, uint64_t base, uint32_t thr) {
+  uint64_t w = 0;
+  const uint64_t key = seed * 0x9E3779B97F4A7C15ull + stream * 0xD1B54A32D192ED03ull;
+#pragma unroll 4
+  for (int q = 0; q < 32; ++q) {
+    const uint64_t h = splitmix64(key + (base >> 1) + (uint64_t)q);
+    w |= (uint64_t)((uint32_t)h < thr) << (2 * q);
+    w |= (uint64_t)((uint32_t)(h >> 32) < thr) << (2 * q + 1);
+  }
+  return w;
+}
+// out[r][w] = Bernoulli(p) bits of logical row (row0 + r), columns [64 w, 64 w + 64) of a (rows x ncols) matrix
+__global__ void random_bits_kernel(uint64_t* __restrict__ out, int64_t rows, int64_t ncols, int64_t words, int64_t row0,
+                                   uint64_t seed, uint64_t stream, uint32_t thr) {
+  const int64_t total = rows * words;
+  const int64_t cw = (ncols + 63) >> 6;                   // words that hold real columns
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / words, w = t - r * words;
+    uint64_t v = 0;
+    if (w < cw) {
+      v = bernoulli_word(seed, stream, (uint64_t)((row0 + r) * cw + w) * 64ull, thr);
+      const int64_t left = ncols - w * 64;
+      if (left < 64) v &= (1ull << left) - 1ull;
+    }
+    out[t] = v;
+  }
+}
+// add_noise on bit rows: x = (x & ~drop) | flip with drop ~ Bernoulli(p_pos), flip ~ Bernoulli(p_neg) per entry
+__global__ void noise_bits_kernel(uint64_t* __restrict__ x, int64_t rows, int64_t ncols, int64_t words, int64_t row0,
+                                  uint64_t seed, uint32_t thr_pos, uint32_t thr_neg) {
+  const int64_t total = rows * words;
+  const int64_t cw = (ncols + 63) >> 6;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / words, w = t - r * words;
+    if (w >= cw) continue;
+    const uint64_t base = (uint64_t)((row0 + r) * cw + w) * 64ull;
+    uint64_t v = x[t];
+    if (thr_pos) v &= ~bernoulli_word(seed, 3, base, thr_pos);
+    if (thr_neg) v |= bernoulli_word(seed, 4, base, thr_neg);
+    const int64_t left = ncols - w * 64;
+    if (left < 64) v &= (1ull << left) - 1ull;
+    x[t] = v;
+  }
+}
+// bit-matrix transpose: x [rows][words] -> xt [ncols][words_t] (bit r of xt row c = bit c of x row r); one CTA of 64
+// threads per 64 x 64 bit tile: thread t holds row t's word, ballots give the 64 column words
+__global__ void __launch_bounds__(64) transpose_bits_kernel(const uint64_t* __restrict__ x, int64_t rows, int64_t ncols,
+                                                            int64_t words, uint64_t* __restrict__ xt, int64_t words_t) {
+  __shared__ uint32_t half[64][2];
+  const int t = threadIdx.x, lane = t & 31, wp = t >> 5;
+  const int64_t cb = blockIdx.x, rb = blockIdx.y;
+  const int64_t r = rb * 64 + t;
+  const uint64_t w = (r < rows) ? x[r * words + cb] : 0ull;
+#pragma unroll 8
+  for (int c = 0; c < 64; ++c) {
+    const uint32_t b = __ballot_sync(0xffffffffu, (w >> c) & 1ull);
+    if (lane == 0) half[c][wp] = b;
+  }
+  __syncthreads();
+  const int64_t col = cb * 64 + t;
+  if (col < ncols) xt[col * words_t + rb] = (uint64_t)half[t][0] | ((uint64_t)half[t][1] << 32);
+}
+
 static inline int row_stream_grid() { return num_sms() * 8; }
 
 }  // namespace bmf
@@ -1840,5 +1917,49 @@ extern "C" int bmf_optimal_rows(const uint64_t* x_bits, int64_t m, int64_t words
   optimal_row_kernel<<<(unsigned)blocks, 256, in_smem ? vt_bytes : 0, as_stream(stream)>>>(
       x_bits, m, words, vt_bits, (int)k, -w_fp, w_fn, in_smem, reinterpret_cast<long long*>(best_trial), best_score);
   BMF_LAUNCH_CHECK("bmf_optimal_rows");
+  return 0;
+}
+
+
+static inline uint32_t bernoulli_threshold(double p) {
+  if (!(p > 0.0)) return 0u;
+  if (p >= 1.0) return 0xFFFFFFFFu;
+  return (uint32_t)(p * 4294967296.0);
+}
+
+extern "C" int bmf_random_bits(uint64_t* bits, int64_t rows, int64_t ncols, int64_t words, int64_t row0, uint64_t seed,
+                               uint64_t stream_id, double p, bmf_stream_t stream) {
+  BMF_REQUIRE(bits && rows >= 0 && ncols > 0 && words * 64 >= ncols && row0 >= 0, "bmf_random_bits: bad arguments");
+  BMF_REQUIRE(p >= 0.0 && p <= 1.0, "bmf_random_bits: p must be in [0, 1]");
+  if (rows == 0) return 0;
+  int64_t blocks = ceil_div(rows * words, 256);
+  if (blocks > (int64_t)num_sms() * 32) blocks = (int64_t)num_sms() * 32;
+  random_bits_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(bits, rows, ncols, words, row0, seed, stream_id,
+                                                                    bernoulli_threshold(p));
+  BMF_LAUNCH_CHECK("bmf_random_bits");
+  return 0;
+}
+
+extern "C" int bmf_noise_bits(uint64_t* bits, int64_t rows, int64_t ncols, int64_t words, int64_t row0, uint64_t seed,
+                              double p_pos, double p_neg, bmf_stream_t stream) {
+  BMF_REQUIRE(bits && rows >= 0 && ncols > 0 && words * 64 >= ncols && row0 >= 0, "bmf_noise_bits: bad arguments");
+  BMF_REQUIRE(p_pos >= 0.0 && p_pos <= 1.0 && p_neg >= 0.0 && p_neg <= 1.0, "bmf_noise_bits: probabilities must be in [0, 1]");
+  if (rows == 0) return 0;
+  int64_t blocks = ceil_div(rows * words, 256);
+  if (blocks > (int64_t)num_sms() * 32) blocks = (int64_t)num_sms() * 32;
+  noise_bits_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(bits, rows, ncols, words, row0, seed,
+                                                                   bernoulli_threshold(p_pos), bernoulli_threshold(p_neg));
+  BMF_LAUNCH_CHECK("bmf_noise_bits");
+  return 0;
+}
+
+extern "C" int bmf_transpose_bits(const uint64_t* bits, int64_t rows, int64_t ncols, int64_t words, uint64_t* bits_t,
+                                  int64_t words_t, bmf_stream_t stream) {
+  BMF_REQUIRE(bits && bits_t && rows > 0 && ncols > 0, "bmf_transpose_bits: bad arguments");
+  BMF_REQUIRE(words * 64 >= ncols && words_t * 64 >= rows, "bmf_transpose_bits: word counts must cover the matrix");
+  dim3 grid((unsigned)ceil_div(ncols, 64), (unsigned)ceil_div(rows, 64));
+  BMF_REQUIRE(grid.y <= 65535u, "bmf_transpose_bits: more than 4.19M rows per call; transpose in row chunks");
+  transpose_bits_kernel<<<grid, 64, 0, as_stream(stream)>>>(bits, rows, ncols, words, bits_t, words_t);
+  BMF_LAUNCH_CHECK("bmf_transpose_bits");
   return 0;
 }

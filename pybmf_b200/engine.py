@@ -107,7 +107,12 @@ class CoverEngine:
         # takes the host ~0.1 s, so the scan runs in build_basis() WHILE the GPU packs and computes X^T X, and only
         # a matrix that really stores zeros (rare) is cleaned and rebuilt.  |X| is counted on the device.
         self._ctor_args = (w_fp, w_fn, scorer, assoc, rescore)
-        Xl = device.csr_rows_view(X, r0, r1)
+        on_device = hasattr(X, "bits") and hasattr(X, "r0")     # generate.DeviceBits: this rank's rows are already bit rows
+        if on_device:
+            assert (X.r0, X.r1) == (r0, r1), "DeviceBits rows must follow ShardPlan(m, world).rows(rank)"
+            Xl = None
+        else:
+            Xl = device.csr_rows_view(X, r0, r1)
         self._host_rows = Xl
         self.trace.mark("host_csr")
         self.w_fp, self.w_fn = float(w_fp), float(w_fn)
@@ -179,7 +184,9 @@ class CoverEngine:
         self.cnt = None
         self.launches = 0
         self._ip = self._ix = None
-        if self.assoc_kind == "tcgen05" and self.assoc_operand == "f4" and self.m_loc > 0:
+        if on_device:
+            self.x_bits = X.bits
+        elif self.assoc_kind == "tcgen05" and self.assoc_operand == "f4" and self.m_loc > 0:
             self._upload_pack_associate(Xl)                     # chunked: H2D of chunk c+1 overlaps X^T X of chunk c
         else:
             self._ip, self._ix = device.upload_csr(Xl)
@@ -324,7 +331,11 @@ class CoverEngine:
         n_pad, ldc = self._cnt_shape()
         cnt = self.cnt if self.cnt is not None else device.zeros((self._cnt_rows(n_pad), ldc), torch.int32)
         if m_loc > 0 and self.cnt is None:
-            xt_bits = device.pack_csr(self._ip, self._ix, m_loc, n, transposed=True)
+            if self._ip is None:                                # the input never was a csr (generate.DeviceBits)
+                from .generate import transpose_bits
+                xt_bits = transpose_bits(self.x_bits, m_loc, n)
+            else:
+                xt_bits = device.pack_csr(self._ip, self._ix, m_loc, n, transposed=True)
             if self.assoc_kind == "tcgen05" and self.assoc_operand == "f4":
                 # X^T as packed E2M1 0/1; A operand = rows padded to 256, B operand = the same plane padded to 496
                 ldk = device.round_up(m_loc, 256) // 2

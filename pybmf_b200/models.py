@@ -95,7 +95,8 @@ class BaseModel:
             _say("[I] Missing validation data.")
         if X_test is None:
             _say("[W] Missing testing data.")
-        self.X_train = U_.to_sparse(X_train, "csr")
+        # generate.DeviceBits (rows already bit-packed on the device) is passed through: Asso packs nothing and uploads nothing
+        self.X_train = X_train if hasattr(X_train, "bits") else U_.to_sparse(X_train, "csr")
         self.X_val = None if X_val is None else U_.to_sparse(X_val, "csr")
         self.X_test = None if X_test is None else U_.to_sparse(X_test, "csr")
         self.m, self.n = self.X_train.shape

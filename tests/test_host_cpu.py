@@ -229,3 +229,14 @@ def test_row_sharded_greedy_world2_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert "rank %d ok" % r in o
+
+
+def test_install_as_pybmf_aliases_the_reference_module_paths():
+    """same module paths as the reference -- `from PyBMF.models import Asso` resolves to this package."""
+    import subprocess
+    code = ("import sys; sys.path.insert(0, %r); import pybmf_b200; pybmf_b200.install_as_pybmf();"
+            "from PyBMF.models import Asso, AssoIter, AssoOpt, TransposedModel;"
+            "from PyBMF.utils import matmul, add, multiply, get_prediction, TP, FP, TN, FN, coverage_score, description_length;"
+            "import pybmf_b200.models as m; assert Asso is m.Asso and AssoIter is m.AssoIter; print('ok')" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout[-2000:]

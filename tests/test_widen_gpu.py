@@ -149,3 +149,72 @@ def test_grecond_call_sites_through_routed_utils(M):
         assert [float(v) for v in got] == [float(g["log_" + c][t]) for c in ("Recall", "Precision", "Accuracy", "F1")]
     assert np.array_equal((U_.get_prediction(U=U, V=V, boolean=True).toarray() != 0).astype(np.uint8), g["X_pd"])
     assert np.array_equal((U_.get_residual(X=X, U=U, V=V).toarray() != 0).astype(np.uint8), g["X_rs"])
+
+
+# ---- on-device input generation -------------------------------------------------------
+def test_random_bits_density_padding_and_shard_independence(M):
+    from pybmf_b200 import device, generate
+    m, n, p = 3000, 1237, 0.3
+    full = generate.random_bits(m, n, p, seed=11, rank=0, world=1)
+    A = device.bits_to_host(full.bits, n)
+    assert A.shape == (m, n)
+    dens = A.mean()
+    assert abs(dens - p) < 4 * np.sqrt(p * (1 - p) / (m * n)), dens
+    raw = full.bits.cpu().numpy().view(np.uint64)
+    assert (raw[:, (n + 63) // 64:] == 0).all() and (raw[:, n // 64] >> np.uint64(n % 64) == 0).all()   # pad bits are 0
+    parts = [generate.random_bits(m, n, p, seed=11, rank=r, world=4) for r in range(4)]
+    cat = np.concatenate([device.bits_to_host(q.bits[: q.r1 - q.r0], n) for q in parts if q.r1 > q.r0])
+    assert np.array_equal(cat, A)                                   # a rank's rows do not depend on the world size
+    other = device.bits_to_host(generate.random_bits(m, n, p, seed=12, rank=0, world=1).bits, n)
+    assert 0.35 < (other != A).mean() < 0.5                         # another seed is another matrix (2 p (1 - p) = 0.42)
+    # columns are not correlated with rows (a counter bug would show as identical rows / columns)
+    assert len({r.tobytes() for r in A[:200]}) == 200
+
+
+def test_noise_bits_follow_add_noise_semantics(M):
+    """generator_utils.add_noise: X = max(X - Bern(p_pos), 0) then X = min(X + Bern(p_neg), 1)."""
+    from pybmf_b200 import device, generate
+    m, n = 2000, 900
+    X = generate.random_bits(m, n, 0.5, seed=1, rank=0, world=1)
+    before = device.bits_to_host(X.bits, n).astype(np.int64)
+    generate.add_noise_bits(X, noise=(0.25, 0.1), seed=5)
+    after = device.bits_to_host(X.bits, n).astype(np.int64)
+    ones, zeros = before == 1, before == 0
+    kept = after[ones].mean()                                       # P(stays 1) = (1 - p_pos) + p_pos * p_neg
+    made = after[zeros].mean()                                      # P(0 -> 1) = p_neg
+    assert abs(kept - (0.75 + 0.25 * 0.1)) < 0.004 and abs(made - 0.1) < 0.003, (kept, made)
+    Y = generate.random_bits(m, n, 0.5, seed=1, rank=0, world=1)
+    generate.add_noise_bits(Y, noise=(1.0, 0.0), seed=5)
+    assert int(device.bits_to_host(Y.bits, n).sum()) == 0
+
+
+@pytest.mark.parametrize("rows,ncols", [(1, 1), (64, 64), (70, 130), (1000, 37), (129, 4100)])
+def test_transpose_bits(M, rows, ncols):
+    from pybmf_b200 import device, generate
+    rng = np.random.RandomState(rows + ncols)
+    A = (rng.rand(rows, ncols) < 0.3).astype(np.uint8)
+    bits = torch.from_numpy(device.dense_to_words(A)).cuda()
+    t = generate.transpose_bits(bits, rows, ncols)
+    assert np.array_equal(device.bits_to_host(t, rows), A.T)
+
+
+def test_fit_from_device_bits_equals_fit_from_host_csr_and_cpu_restatement(M):
+    """Asso.fit() on a matrix that was GENERATED on the device (never a csr, nothing uploaded) equals the fit on the same
+    matrix downloaded to a host csr, and the CPU restatement's fit on that csr."""
+    from oracle import asso_oracle_c as OC
+    from pybmf_b200 import generate
+    from pybmf_b200.digest import DIGEST_KEYS, result_digest
+    m, n = 5000, 1500
+    Xd = generate.planted_bits(m, n, 12, 0.08, 0.08, 0.1, 0.01, seed=77)
+    Xh = Xd.to_csr()
+    dens = Xh.nnz / (m * n)
+    assert 0.03 < dens < 0.2, dens
+    a = M.Asso(tau=0.45, k=8, w_fp=0.5)
+    a.fit(Xd, **FIT_KW)
+    b = M.Asso(tau=0.45, k=8, w_fp=0.5)
+    b.fit(Xh, **FIT_KW)
+    da, db = result_digest(a), result_digest(b)
+    want = OC.asso_fit(Xh, 8, 0.45, 0.5)["digest"]
+    for key in DIGEST_KEYS:
+        assert da[key] == db[key] == want[key], key
+    assert len(da["winners"]) == 8
