@@ -300,14 +300,30 @@ cover_score_popc_kernel(const uint64_t* __restrict__ xb, const uint64_t* __restr
   if (!any_alive) return;
 
   long long gp[4] = {0, 0, 0, 0}, gn[4] = {0, 0, 0, 0};
+  // A row whose cover is still empty has N = |b_j| - P: its second contraction is redundant, |b_j| is counted once per
+  // candidate instead (4 popcounts per word instead of 16).  cov_rows[r] says whether row r of the tile has any cover.
+  __shared__ int cov_rows[PT];
   const int64_t row_tiles = (m + PT - 1) / PT;
   for (int64_t rt = blockIdx.y; rt < row_tiles; rt += gridDim.y) {
     const int64_t i0 = rt * PT;
-    int accp[4][4], accn[4][4];
+    int accp[4][4], accn[4][4], accb[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
       for (int c = 0; c < 4; ++c) { accp[r][c] = 0; accn[r][c] = 0; }
+    if (threadIdx.x < PT) cov_rows[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t w0 = 0; w0 < words; w0 += PW)                      // pass 1 over the tile's cover words: which rows are covered?
+      for (int e = threadIdx.x; e < PT * PW; e += blockDim.x) {
+        const int r = e / PW, w = e % PW;
+        const int64_t gr = i0 + r, gw = w0 + w;
+        if (gr < m && gw < words && __ldg(cb + gr * words + gw) != 0ull) cov_rows[r] = 1;
+      }
+    __syncthreads();
+    bool need_n[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) need_n[r] = cov_rows[ty * 4 + r] != 0;
+    const bool any_need = need_n[0] | need_n[1] | need_n[2] | need_n[3];
     for (int64_t w0 = 0; w0 < words; w0 += PW) {
       for (int e = threadIdx.x; e < PT * PW; e += blockDim.x) {
         const int r = e / PW, w = e % PW;
@@ -331,14 +347,19 @@ cover_score_popc_kernel(const uint64_t* __restrict__ xb, const uint64_t* __restr
 #pragma unroll
         for (int r = 0; r < 4; ++r) { p[r] = Ps[ty * 4 + r][w]; q[r] = Ns[ty * 4 + r][w]; }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) b[c] = Bs[c * 16 + tx][w];
+        for (int c = 0; c < 4; ++c) { b[c] = Bs[c * 16 + tx][w]; accb[c] += __popcll(b[c]); }
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            accp[r][c] += __popcll(p[r] & b[c]);
-            accn[r][c] += __popcll(q[r] & b[c]);
-          }
+          for (int c = 0; c < 4; ++c) accp[r][c] += __popcll(p[r] & b[c]);
+        if (any_need) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            if (need_n[r]) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) accn[r][c] += __popcll(q[r] & b[c]);
+            }
+        }
       }
       __syncthreads();
     }
@@ -350,7 +371,7 @@ cover_score_popc_kernel(const uint64_t* __restrict__ xb, const uint64_t* __restr
       if (!(wa | wb)) { tpo = tp_old[i]; fpo = fp_old[i]; }
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const int P = accp[r][c], N = accn[r][c];
+        const int P = accp[r][c], N = need_n[r] ? accn[r][c] : accb[c] - accp[r][c];
         if (wa | wb) {
           const int d = wb * P - wa * N;
           gp[c] += d > 0 ? d : 0;
@@ -965,11 +986,13 @@ __device__ __forceinline__ int64_t panel_row(int rowmap, int64_t block, int r, i
   return rowmap ? (block * nw * 32 + (int64_t)r * nw + warp) : (block * 32 + r);
 }
 
-template <bool COUNT_GT>
+// MODE: how the two counts |gt & pd| and |pd| are taken -- 0: both through the carry-save tree (ALU pipe, LOP3),
+// 1: |gt & pd| through the tree and |pd| through POPC (XU pipe), 2: both through POPC.
+template <bool COUNT_GT, int MODE>
 __global__ void __launch_bounds__(PANEL_THREADS, 1)
 confusion_panel_kernel(const uint64_t* __restrict__ gt, int64_t m, int64_t words,
                        const uint64_t* __restrict__ u_words, const uint64_t* __restrict__ vt, int64_t k,
-                       int panel_chunks, int RING_DEPTH, int rowmap, unsigned long long* __restrict__ counts) {
+                       int panel_chunks, int RING_DEPTH, unsigned long long* __restrict__ counts) {
   extern __shared__ __align__(128) uint8_t panel_smem[];
   const int panel_pairs = panel_chunks * CH_PAIRS;
   const int row_bytes = panel_pairs * 16;
@@ -996,53 +1019,43 @@ confusion_panel_kernel(const uint64_t* __restrict__ gt, int64_t m, int64_t words
   fence_proxy_async();
   load_vt_panel(Vs, vt, k, words, pair0, panel_pairs);     // ends with __syncthreads()
 
-  // this warp's rows, in blocks of up to 32 (see panel_row): block ids blk0, blk0 + blk_step, ...
-  const int nw = PANEL_WARPS;
-  const int64_t blk0 = rowmap ? (int64_t)blockIdx.y : (int64_t)blockIdx.y * nw + warp;
-  const int64_t blk_step = rowmap ? (int64_t)gridDim.y : (int64_t)gridDim.y * nw;
-  const int64_t blk_rows = rowmap ? (int64_t)nw * 32 : 32;
-  const int64_t blocks_total = (m + blk_rows - 1) / blk_rows;
-  const int my_blocks = blk0 < blocks_total ? (int)((blocks_total - 1 - blk0) / blk_step) + 1 : 0;
-  auto rows_in = [&](int b) -> int {                       // valid rows of this warp in its b-th block
-    const int64_t first = panel_row(rowmap, blk0 + (int64_t)b * blk_step, 0, warp, nw);
-    if (first >= m) return 0;
-    const int64_t stride = rowmap ? nw : 1;
-    const int64_t cnt = (m - first + stride - 1) / stride;
-    return (int)(cnt < 32 ? cnt : 32);
-  };
-  // issue side (meaningful in lane 0): next row segment to request
-  int iss_b = 0, iss_r = 0, iss_slot = 0;
-  int iss_n = my_blocks > 0 ? rows_in(0) : 0;
-  while (iss_b < my_blocks && iss_n == 0) { ++iss_b; iss_n = iss_b < my_blocks ? rows_in(iss_b) : 0; }
-  const uint64_t* gt_panel = gt + 2 * pair0;
+  // this warp's rows: 32-row blocks gw, gw + nwarps, ...
+  const int64_t gw = (int64_t)blockIdx.y * PANEL_WARPS + warp;
+  const int64_t nwarps = (int64_t)gridDim.y * PANEL_WARPS;
+  const int64_t blocks_total = (m + 31) >> 5;
+  int my_blocks = 0, last_rows = 0;
+  if (gw < blocks_total) {
+    my_blocks = (int)((blocks_total - 1 - gw) / nwarps) + 1;
+    const int64_t last_block = gw + (int64_t)(my_blocks - 1) * nwarps;
+    last_rows = (int)((m - last_block * 32) < 32 ? (m - last_block * 32) : 32);
+  }
+  int to_issue = my_blocks > 0 ? (my_blocks - 1) * 32 + last_rows : 0;    // rows not yet requested
+  // issue side (meaningful in lane 0): next row segment to request, as an incrementally updated pointer
+  const uint64_t* iss_ptr = gt + 2 * pair0 + gw * 32 * words;
+  const int64_t step_block = (nwarps * 32 - 31) * words;
+  int iss_r = 0, iss_slot = 0;
   auto issue = [&]() {
-    const int64_t row = panel_row(rowmap, blk0 + (int64_t)iss_b * blk_step, iss_r, warp, nw);
     mbar_expect_tx(bar0 + 8u * iss_slot, seg_bytes);
-    bulk_load(ring0 + (uint32_t)(iss_slot * row_bytes), gt_panel + row * words, seg_bytes, bar0 + 8u * iss_slot);
+    bulk_load(ring0 + (uint32_t)(iss_slot * row_bytes), iss_ptr, seg_bytes, bar0 + 8u * iss_slot);
     iss_slot = iss_slot == RING_DEPTH - 1 ? 0 : iss_slot + 1;
-    if (++iss_r == iss_n) {
-      iss_r = 0;
-      do { ++iss_b; iss_n = iss_b < my_blocks ? rows_in(iss_b) : 0; } while (iss_b < my_blocks && iss_n == 0);
-    }
+    if (++iss_r == 32) { iss_r = 0; iss_ptr += step_block; } else { iss_ptr += words; }
+    --to_issue;
   };
   if (lane == 0)
-    for (int d = 0; d < RING_DEPTH && iss_b < my_blocks; ++d) issue();
+    for (int d = 0; d < RING_DEPTH && to_issue > 0; ++d) issue();
 
-  HarleySeal8 hs_tp, hs_gt;
-  long long n_pd = 0;
+  HarleySeal8 hs_tp, hs_pd, hs_gt;
+  long long n_pd = 0, n_tp = 0;
   int slot = 0;
   uint32_t phase = 0;
   bool second = false;
-  auto usage_of = [&](int b) -> uint64_t {                 // lane r holds the usage word of the block's r-th row
-    if (b >= my_blocks) return 0ull;
-    const int64_t row = panel_row(rowmap, blk0 + (int64_t)b * blk_step, lane, warp, nw);
-    return row < m ? __ldg(u_words + row) : 0ull;
-  };
-  uint64_t u_next = usage_of(0);
+  const uint64_t* u_ptr = u_words + gw * 32 + lane;
+  uint64_t u_next = (my_blocks > 0 && gw * 32 + lane < m) ? __ldg(u_ptr) : 0ull;
   for (int blk = 0; blk < my_blocks; ++blk) {
     const uint64_t u_cur = u_next;
-    u_next = usage_of(blk + 1);
-    const int nrows = rows_in(blk);
+    u_ptr += nwarps * 32;
+    u_next = (blk + 1 < my_blocks && (gw + (int64_t)(blk + 1) * nwarps) * 32 + lane < m) ? __ldg(u_ptr) : 0ull;
+    const int nrows = blk + 1 < my_blocks ? 32 : last_rows;
     for (int r = 0; r < nrows; ++r) {
       const uint64_t sel = __shfl_sync(0xffffffffu, u_cur, r);
       const ulonglong2* seg = reinterpret_cast<const ulonglong2*>(ring + (size_t)slot * row_bytes);
@@ -1056,12 +1069,20 @@ confusion_panel_kernel(const uint64_t* __restrict__ gt, int64_t m, int64_t words
         uint64_t w[8];
 #pragma unroll
         for (int u = 0; u < 4; ++u) { w[2 * u] = g[u].x & d[u].x; w[2 * u + 1] = g[u].y & d[u].y; }
-        if (!second) hs_tp.add8_first(w); else hs_tp.add8_second(w);
-        // |pd| goes through POPC (XU pipe) while |gt & pd| goes through the carry-save tree (LOP3 on the ALU pipe): ncu
-        // showed the ALU pipe 85 % busy with both counts on the tree (profiles/r01c), the XU pipe almost idle -- splitting
-        // the two counts over the two pipes takes ~30 LOP3 per row segment off the critical pipe
+        if (MODE == 2) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) n_pd += __popcll(d[u].x) + __popcll(d[u].y);
+          for (int u = 0; u < 8; ++u) n_tp += __popcll(w[u]);
+        } else {
+          if (!second) hs_tp.add8_first(w); else hs_tp.add8_second(w);
+        }
+        if (MODE == 0) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { w[2 * u] = d[u].x; w[2 * u + 1] = d[u].y; }
+          if (!second) hs_pd.add8_first(w); else hs_pd.add8_second(w);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) n_pd += __popcll(d[u].x) + __popcll(d[u].y);
+        }
         if (COUNT_GT) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) { w[2 * u] = g[u].x; w[2 * u + 1] = g[u].y; }
@@ -1070,12 +1091,12 @@ confusion_panel_kernel(const uint64_t* __restrict__ gt, int64_t m, int64_t words
         second = !second;
       }
       __syncwarp();                                         // every lane has consumed the slot
-      if (lane == 0 && iss_b < my_blocks) issue();          // refill it with the row RING_DEPTH ahead
+      if (lane == 0 && to_issue > 0) issue();               // refill it with the row RING_DEPTH ahead
       if (++slot == RING_DEPTH) { slot = 0; phase ^= 1u; }
     }
   }
-  const long long t_tp = warp_sum_ll(hs_tp.total());
-  const long long t_pd = warp_sum_ll(n_pd);
+  const long long t_tp = warp_sum_ll(MODE == 2 ? n_tp : hs_tp.total());
+  const long long t_pd = warp_sum_ll(MODE == 0 ? hs_pd.total() : n_pd);
   const long long t_gt = COUNT_GT ? warp_sum_ll(hs_gt.total()) : 0;
   if (lane == 0 && (t_pd | t_gt)) {
     atomicAdd(counts + 0, (unsigned long long)t_tp);
@@ -1090,7 +1111,8 @@ confusion_panel_kernel(const uint64_t* __restrict__ gt, int64_t m, int64_t words
 constexpr int PRODUCT_THREADS = 1024;
 __global__ void __launch_bounds__(PRODUCT_THREADS, 1)
 bool_product_panel_kernel(const uint64_t* __restrict__ u_words, int64_t m, const uint64_t* __restrict__ vt,
-                          int64_t k, int64_t words, int panel_chunks, int rowmap, uint64_t* __restrict__ pd) {
+                          int64_t k, int64_t words, int panel_chunks, int rowmap, int store_mode,
+                          uint64_t* __restrict__ pd) {
   extern __shared__ __align__(128) uint8_t panel_smem[];
   ulonglong2* Vs = reinterpret_cast<ulonglong2*>(panel_smem);
   const int panel_pairs = panel_chunks * CH_PAIRS;
@@ -1124,7 +1146,12 @@ bool_product_panel_kernel(const uint64_t* __restrict__ u_words, int64_t m, const
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int64_t gp = pair0 + slot0 + 32 * u;
-          if (gp < pairs) __stcs(reinterpret_cast<ulonglong2*>(out) + gp, d[u]);
+          if (gp < pairs) {
+            ulonglong2* dst = reinterpret_cast<ulonglong2*>(out) + gp;
+            if (store_mode == 0) __stcs(dst, d[u]);
+            else if (store_mode == 1) *dst = d[u];
+            else __stwt(dst, d[u]);
+          }
         }
       }
     }
@@ -1149,9 +1176,19 @@ static inline int confusion_ring_depth(int64_t k, int chunks) {
 static inline size_t confusion_panel_smem(int64_t k, int chunks, int depth) {
   return (size_t)(k + PANEL_WARPS * depth) * chunks * CH_PAIRS * 16 + PANEL_WARPS * RING_DEPTH_MAX * 8;
 }
-static inline int panel_rowmap() {              // BMF_PANEL_ROWMAP=0 restores the blocked row order (A/B experiments)
+static inline int panel_rowmap() {              // BMF_PANEL_ROWMAP=1 selects the interleaved row order (A/B experiments)
   const char* e = getenv("BMF_PANEL_ROWMAP");
-  return (e != nullptr && e[0] == '0') ? 0 : 1;
+  return (e != nullptr && e[0] == '1') ? 1 : 0;
+}
+static inline int confusion_count_mode() {      // BMF_CONFUSION_COUNT = 0 (tree / tree), 1 (tree / POPC), 2 (POPC / POPC)
+  const char* e = getenv("BMF_CONFUSION_COUNT");
+  if (e != nullptr && e[0] >= '0' && e[0] <= '2') return e[0] - '0';
+  return 1;                                     // measured best (profiles/r02_c5_knob_sweep.log)
+}
+static inline int product_store_mode() {        // BMF_PRODUCT_STORE = 0 (st.cs, evict first), 1 (plain st), 2 (st.wt)
+  const char* e = getenv("BMF_PRODUCT_STORE");
+  if (e != nullptr && e[0] >= '0' && e[0] <= '2') return e[0] - '0';
+  return 0;
 }
 static inline bool panel_disabled() {
   const char* e = getenv("BMF_NO_PANEL");
@@ -1760,7 +1797,8 @@ extern "C" int bmf_bool_product(const uint64_t* u_words, int64_t m, int64_t kw, 
     if (rc) return rc;
     dim3 grid((unsigned)panels, (unsigned)splits);
     bool_product_panel_kernel<<<grid, PRODUCT_THREADS, smem, as_stream(stream)>>>(u_words, m, vt_bits, k, words, chunks,
-                                                                                panel_rowmap(), pd_bits);
+                                                                                panel_rowmap(), product_store_mode(),
+                                                                                pd_bits);
     BMF_LAUNCH_CHECK("bmf_bool_product");
     return 0;
   }
@@ -1791,19 +1829,21 @@ static int launch_confusion(const uint64_t* gt_bits, const uint64_t* pd_bits, in
       if (splits < 1) splits = 1;
       if (splits > 65535) splits = 65535;
       dim3 grid((unsigned)panels, (unsigned)splits);
+      const int mode = confusion_count_mode();
+#define BMF_CONF_LAUNCH(CG, MD)                                                                                      \
+  do {                                                                                                               \
+    rc = check_cuda(cudaFuncSetAttribute(confusion_panel_kernel<CG, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem), who);                                                           \
+    if (rc) return rc;                                                                                               \
+    confusion_panel_kernel<CG, MD><<<grid, PANEL_THREADS, smem, st>>>(gt_bits, m, words, u_words, vt_bits, k, chunks,  \
+                                                                      depth, c);                                     \
+  } while (0)
       if (gt_ones >= 0) {
-        rc = check_cuda(cudaFuncSetAttribute(confusion_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem), who);
-        if (rc) return rc;
-        confusion_panel_kernel<false><<<grid, PANEL_THREADS, smem, st>>>(gt_bits, m, words, u_words, vt_bits, k, chunks, depth,
-                                                                         panel_rowmap(), c);
+        if (mode == 0) BMF_CONF_LAUNCH(false, 0); else if (mode == 1) BMF_CONF_LAUNCH(false, 1); else BMF_CONF_LAUNCH(false, 2);
       } else {
-        rc = check_cuda(cudaFuncSetAttribute(confusion_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem), who);
-        if (rc) return rc;
-        confusion_panel_kernel<true><<<grid, PANEL_THREADS, smem, st>>>(gt_bits, m, words, u_words, vt_bits, k, chunks, depth,
-                                                                        panel_rowmap(), c);
+        if (mode == 0) BMF_CONF_LAUNCH(true, 0); else if (mode == 1) BMF_CONF_LAUNCH(true, 1); else BMF_CONF_LAUNCH(true, 2);
       }
+#undef BMF_CONF_LAUNCH
       rc = check_cuda(cudaGetLastError(), who);
       if (rc) return rc;
       confusion_finalize_kernel<<<1, 1, 0, st>>>(reinterpret_cast<long long*>(counts), (long long)gt_ones);

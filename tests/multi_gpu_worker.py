@@ -51,6 +51,23 @@ for name in ("ex01_6", "c1_noisy", "c1_clean", "planted_w02", "d2_no_pattern"):
         if O.integer_weights(c["w_fp"], c["w_fn"]) is not None:
             assert np.array_equal(np.array([float(v) for v in df[("train", 0, "score")]]), g["log_score"]), name
 
+# D1 in the middle of a fit (rollback of speculative steps + cover rebuild on every rank), then D2
+c = load_golden("c1_noisy")
+try:
+    O.asso_fit(c["X"], 5, 0.5, 0.5, tol=0.12)
+    raise SystemExit("the oracle should have raised")
+except O.NoCandidateError as e:
+    want_state = e.args[1]
+for rescore in ("auto", "full"):
+    mdl = models.Asso(tau=0.5, k=5, tol=0.12, w_fp=0.5, rescore=rescore)
+    try:
+        mdl.fit(sp.csr_matrix(c["X"]), **KW)
+        raise SystemExit("fit should have raised TypeError")
+    except TypeError:
+        pass
+    assert np.array_equal(dense(mdl.U), want_state["U"]) and np.array_equal(dense(mdl.V), want_state["V"]), (rescore, rank)
+    assert [float(v) for v in mdl.logs["updates"][("train", 0, "score")]] == [l["score"] for l in want_state["logs"]]
+
 # BASELINE configs[1] at full size and rank against the CPU restatement's fixture
 from pybmf_b200.digest import DIGEST_KEYS, result_digest
 with open(os.path.join(ROOT, "tests", "golden", "c2_digest.json")) as fh:

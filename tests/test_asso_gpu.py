@@ -552,3 +552,26 @@ def test_model_is_picklable_and_lazy_attrs(M, tmp_path):
     with open(tmp_path / "m.pickle", "rb") as fh:
         d = pickle.load(fh)
     assert "U" in d and "X_pd" in d
+
+
+@pytest.mark.parametrize("scorer,rescore", [("tcgen05", "auto"), ("tcgen05", "full"), ("tcgen05_i8", "auto"), ("popc", "full")])
+@pytest.mark.parametrize("k,tol", [(5, 0.12), (None, 0)])
+def test_truncation_mid_fit_and_unbounded_k_match_oracle(M, scorer, rescore, k, tol):
+    """The device-resident loop enqueues steps speculatively; what the reference would NOT have run must leave no trace.
+    (k=5, tol=0.12): quirk D1 truncates the factor of step 3 (error <= tol), the cover is rebuilt from the three kept factors
+    (rollback) and the next step finds no candidate above the inherited threshold -> the reference's TypeError (D2).
+    (k=None): the loop runs in chunks until no candidate improves -> TypeError.  U, V and every log row equal the numpy
+    restatement's state at the moment it would have raised."""
+    c = load_golden("c1_noisy")
+    X = sp.csr_matrix(c["X"])
+    with pytest.raises(O.NoCandidateError) as ei:
+        O.asso_fit(c["X"], k, 0.5, 0.5, tol=tol)
+    want = ei.value.args[1]
+    mdl = M.Asso(tau=0.5, k=k, tol=tol, w_fp=0.5, scorer=scorer, rescore=rescore)
+    with pytest.raises(TypeError):
+        mdl.fit(X, **FIT_KW)
+    assert np.array_equal(_dense(mdl.U), want["U"]) and np.array_equal(_dense(mdl.V), want["V"])
+    df = mdl.logs["updates"]
+    assert len(df) == len(want["logs"])
+    for col in LOG_COLS:
+        assert [float(v) for v in df[("train", 0, col)]] == [float(l[col]) for l in want["logs"]], col
