@@ -112,6 +112,72 @@ def upload_csr(X: sp.csr_matrix):
     return indptr.to(d, non_blocking=True), indices.to(d, non_blocking=True)
 
 
+class _Stager:
+    """Host -> device copies of LARGE pageable arrays through a small pinned ring, filled by a few threads.
+
+    `tensor.to(device)` from pageable memory is staged by the driver on ONE thread: 11 GB/s on this pool's hosts
+    (35 ms for the 400 MB index array of the Netflix-shaped config).  A threaded memcpy into pinned slots followed by
+    async copies reaches the PCIe rate (profiles/r02j_h2d_pinned_probe.log: 5.3 ms memcpy on 8 threads + 7.2 ms DMA,
+    overlapped slot by slot).  The ring is 4 x 16 MB: pinning it costs ~40 ms ONCE per process (pinning the whole 400 MB
+    would cost 240 ms, registering the array in place 60 ms per fit -- both measured, both worse)."""
+    SLOT = 16 << 20
+    SLOTS = 4
+
+    def __init__(self, threads):
+        from concurrent.futures import ThreadPoolExecutor
+        self.buf = torch.empty(self.SLOT * self.SLOTS, dtype=torch.uint8, pin_memory=True)
+        self.view = self.buf.numpy()
+        self.events = [None] * self.SLOTS
+        self.next = 0
+        self.threads = threads
+        self.pool = ThreadPoolExecutor(threads) if threads > 1 else None
+
+    def upload(self, src: np.ndarray, dst, stream):
+        """src (contiguous numpy) -> dst (device tensor of the same byte size) on `stream`; returns when every piece has been
+        ENQUEUED (the last DMA may still be in flight: order later work on `stream`)."""
+        src_u8 = src.reshape(-1).view(np.uint8)
+        dst_u8 = dst.reshape(-1).view(torch.uint8)
+        nbytes = src_u8.size
+        assert dst_u8.numel() == nbytes
+        for off in range(0, nbytes, self.SLOT):
+            s = self.next
+            self.next = (s + 1) % self.SLOTS
+            if self.events[s] is not None:
+                self.events[s].synchronize()                       # the slot's previous DMA has drained
+            ln = min(self.SLOT, nbytes - off)
+            base = s * self.SLOT
+            if self.pool is None or ln < (1 << 20):
+                np.copyto(self.view[base:base + ln], src_u8[off:off + ln])
+            else:
+                cuts = np.linspace(0, ln, self.threads + 1, dtype=np.int64)
+                list(self.pool.map(lambda ab: np.copyto(self.view[base + ab[0]:base + ab[1]], src_u8[off + ab[0]:off + ab[1]]),
+                                   zip(cuts[:-1], cuts[1:])))
+            with torch.cuda.stream(stream):
+                dst_u8[off:off + ln].copy_(self.buf[base:base + ln], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+            self.events[s] = ev
+
+
+_STAGER = None
+
+
+def stager(world: int = 1):
+    """The process-wide pinned staging ring (created on first use); None when BMF_PINNED_UPLOAD=0."""
+    global _STAGER
+    import os
+    if os.environ.get("BMF_PINNED_UPLOAD", "1") == "0":
+        return None
+    if _STAGER is None:
+        cores = os.cpu_count() or 1
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            pass
+        _STAGER = _Stager(max(1, min(8, cores // (2 * max(world, 1)))))
+    return _STAGER
+
+
 def pack_csr(indptr_d, indices_d, m: int, n: int, transposed: bool = False):
     """CSR pattern on device -> bit matrix [m, words(n)] (or X^T: [n, words(m)])."""
     rows, cols = (n, m) if transposed else (m, n)

@@ -271,8 +271,9 @@ class CoverEngine:
     def _upload_pack_associate(self, Xl: sp.csr_matrix):
         """FP4 association path: the csr rows go up in a few chunks on a copy stream; as soon as a chunk has landed the
         main stream packs its bit rows, packs / expands its slice of X^T (K = the chunk's rows) and ACCUMULATES that
-        slice's X^T X into cnt, while the (host-blocking, pageable) copy of the next chunk is in flight.  At c4 the copy
-        (38 ms) and the association (36 ms) used to run back to back."""
+        slice's X^T X into cnt, while the copy of the next chunk is in flight (large index arrays go through
+        device.stager(): threaded memcpy into a pinned ring + async DMA, ~4x the driver's single-thread pageable staging).
+        At c4 the copy (38 ms pageable) and the association (36 ms) used to run back to back."""
         n, m_loc = self.n, self.m_loc
         n_pad, ldc = self._cnt_shape()
         d = device.dev()
@@ -290,8 +291,16 @@ class CoverEngine:
             ia, ib = int(indptr[a]), int(indptr[b])
             ip_h = torch.from_numpy(np.ascontiguousarray((indptr[a:b + 1] - indptr[a]).astype(np.int64, copy=False)))
             ix_h = torch.from_numpy(np.ascontiguousarray(indices[ia:ib].astype(np.int32, copy=False)))
+            st = device.stager(self.world) if ix_h.numel() >= (1 << 22) else None     # >= 16 MB of indices
             with torch.cuda.stream(copy):
-                ip_d, ix_d = ip_h.to(d, non_blocking=True), ix_h.to(d, non_blocking=True)
+                ip_d = ip_h.to(d, non_blocking=True)
+                if st is None:
+                    ix_d = ix_h.to(d, non_blocking=True)       # pageable: staged by the driver on one thread (11 GB/s)
+                else:
+                    ix_d = torch.empty(ix_h.shape, dtype=torch.int32, device=d)
+            if st is not None:
+                st.upload(ix_h.numpy(), ix_d, copy)            # threaded memcpy into a pinned ring + async DMA
+            with torch.cuda.stream(copy):
                 landed = torch.cuda.Event()
                 landed.record(copy)
             main.wait_event(landed)
