@@ -378,6 +378,10 @@ def timed_fits(models, torch, dist, world, X, tau, w_fp, k, scorer, rescore, rep
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        # the cyclic collector is paused while the clock runs (as `timeit` does): a generation-2 pass walks every live
+        # container object, and one lil U of the Netflix-shaped config alone is ~1e6 Python lists -- with a few fitted models
+        # alive such passes added 0.1-0.3 s to SOME fits (profiles/r02f_fit_repeat_probe_n2.log, r02k_fit_time_c4*.log)
+        gc.disable()
         t0 = time.perf_counter()
         mdl = models.Asso(tau=tau, k=k, w_fp=w_fp, scorer=scorer, rescore=rescore)
         try:
@@ -386,6 +390,7 @@ def timed_fits(models, torch, dist, world, X, tau, w_fp, k, scorer, rescore, rep
             err = str(e)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
+        gc.enable()
         from pybmf_b200.digest import result_digest
         dg = result_digest(mdl)                                 # from the packed bits, before U / V are unpacked
         t2 = time.perf_counter()
