@@ -695,6 +695,14 @@ cover_apply_kernel(const uint64_t* __restrict__ xb, uint64_t* __restrict__ cb, i
       c.y |= v.y;
       *cp = c;
     }
+    if (slot >= 0) {                                                    // K padding of the compact rows (never written above)
+      const int64_t used_bytes = words * (ex.comp_kind == 1 ? 32 : 64);
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      for (int64_t q = lane; q < ((ex.comp_ld - used_bytes) >> 4); q += 32) {
+        reinterpret_cast<uint4*>(ex.comp_old + slot * ex.comp_ld + used_bytes)[q] = z;
+        reinterpret_cast<uint4*>(ex.comp_new + slot * ex.comp_ld + used_bytes)[q] = z;
+      }
+    }
     if (lane == 0) {
       tp_old[i] = tpo + P;
       fp_old[i] = fpo + N;

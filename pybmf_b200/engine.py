@@ -540,8 +540,8 @@ class CoverEngine:
         if self.rescore == "incremental" and self.comp_old is None and self.m_loc > 0:
             rows, ld = self.rows_plane.shape
             dt = self.rows_plane.dtype
-            self.comp_old = device.zeros((rows, ld), dt)           # capacity = every row: a winner can use them all
-            self.comp_new = device.zeros((rows, ld), dt)
+            self.comp_old = device.empty((rows, ld), dt)           # capacity = every row: a winner can use them all;
+            self.comp_new = device.empty((rows, ld), dt)           # bmf_cover_apply_compact writes whole rows incl. K padding
 
     def _score_into_gains(self):
         """One FULL scoring pass of the current cover into the local gain vector(s) (kernel only, no exchange)."""
