@@ -160,6 +160,16 @@ class _Stager:
 
 
 _STAGER = None
+_COPY_STREAM = {}
+
+
+def copy_stream():
+    """The process-wide side stream for host -> device copies (one per device)."""
+    idx = torch.cuda.current_device()
+    if idx not in _COPY_STREAM:
+        _COPY_STREAM[idx] = torch.cuda.Stream(device=idx)
+    return _COPY_STREAM[idx]
+
 
 
 def stager(world: int = 1):

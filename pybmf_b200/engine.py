@@ -283,9 +283,10 @@ class CoverEngine:
         nchunks = 3 if Xl.nnz >= (1 << 24) else 1
         step = device.round_up(-(-m_loc // nchunks), 256)      # chunk boundaries: multiples of 256 rows (K tiles, bit words)
         main = torch.cuda.current_stream()
-        copy = torch.cuda.Stream() if nchunks > 1 else main
-        indptr, indices = Xl.indptr, Xl.indices
+        copy = device.copy_stream() if nchunks > 1 else main   # ONE copy stream per process: the caching allocator keeps a
+        indptr, indices = Xl.indptr, Xl.indices                # block pool per stream, a new stream per fit strands ~0.4 GB each
         first = True
+        self.trace.mark("upload_alloc")
         for a in range(0, m_loc, step):
             b = min(a + step, m_loc)
             ia, ib = int(indptr[a]), int(indptr[b])
@@ -300,6 +301,7 @@ class CoverEngine:
                     ix_d = torch.empty(ix_h.shape, dtype=torch.int32, device=d)
             if st is not None:
                 st.upload(ix_h.numpy(), ix_d, copy)            # threaded memcpy into a pinned ring + async DMA
+            self.trace.mark("upload_stage")
             with torch.cuda.stream(copy):
                 landed = torch.cuda.Event()
                 landed.record(copy)
