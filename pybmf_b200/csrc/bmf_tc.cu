@@ -748,7 +748,8 @@ __device__ __forceinline__ void epilogue_tile_f4(uint32_t taddr, int64_t row, in
     // B200's vector FP64 pipe is narrow: evaluating the fp64 row test for all 8.5e9 elements of a step bounds the kernel
     // (math-pipe throttle = 66 % of the stall samples).  So each element is first decided in fixed point:
     //   d = round(w_fn 2^20) P - round(w_fp 2^20) N  differs from 2^20 (w_fn P - w_fp N) by at most (P + N) / 2, and the fp64
-    //   evaluation of s_new - s_old is off by < 2^-35, hence |d| > P + N + 2 fixes the outcome of the fp64 comparison;
+    //   evaluation of s_new vs s_old is off by < 2^-51 |w| n, i.e. < 0.5 units of d under the host gate |w| n < 2^30 (see
+    //   bmf_cover_score_f4_general), hence |d| > P + N + 2 fixes the outcome of the fp64 comparison;
     // only the undecided elements (exact or near ties such as 0.8 P = 0.2 N) go through the literal fp64 expression, one
     // per lane and pass, so the number of fp64 passes per chunk is the LARGEST per-lane count, not the number of
     // elements that are undecided in some lane.  The result is identical to evaluating fp64 everywhere.
@@ -1411,6 +1412,8 @@ extern "C" int bmf_cover_score_i8(const int8_t* cand_plane, int64_t cand_pad, co
   BMF_REQUIRE(cand_pad > 0 && cand_pad % tc::BM == 0, "bmf_cover_score_i8: cand_pad must be a positive multiple of 128");
   BMF_REQUIRE(rows_pad > 0 && rows_pad % tc::BN == 0, "bmf_cover_score_i8: rows_pad must be a positive multiple of 256");
   BMF_REQUIRE(ld > 0 && ld % tc::BK == 0, "bmf_cover_score_i8: ld must be a positive multiple of 128");
+  BMF_REQUIRE(ld <= 524288, "bmf_cover_score_i8: more than 524288 columns would overflow the epilogue's int32 partial sums "
+                            "(32 elements x 127 x ld)");
   int rc = check_cuda(cudaMemsetAsync(gain, 0, sizeof(int64_t) * cand_pad, as_stream(stream)), "bmf_cover_score_i8");
   if (rc) return rc;
   tc::EpiArgs ea = {};
@@ -1431,7 +1434,7 @@ extern "C" int bmf_cover_rescore_i8(const int8_t* cand_plane, int64_t cand_pad, 
   BMF_REQUIRE(cand_plane && compact_plane && gain && dyn_rows, "bmf_cover_rescore_i8: null pointer");
   BMF_REQUIRE(cand_pad > 0 && cand_pad % tc::BM == 0, "bmf_cover_rescore_i8: cand_pad must be a positive multiple of 128");
   BMF_REQUIRE(rows_cap > 0 && rows_cap % tc::BN == 0, "bmf_cover_rescore_i8: rows_cap must be a positive multiple of 256");
-  BMF_REQUIRE(ld > 0 && ld % tc::BK == 0, "bmf_cover_rescore_i8: ld must be a positive multiple of 128");
+  BMF_REQUIRE(ld > 0 && ld % tc::BK == 0 && ld <= 524288, "bmf_cover_rescore_i8: ld must be a multiple of 128, at most 524288");
   tc::EpiArgs ea = {};
   ea.sign = sign;
   ea.cand_pop = cand_pop;
@@ -1556,7 +1559,12 @@ extern "C" int bmf_cover_score_f4_general(const uint8_t* cand_plane, int64_t can
   ea.m_rows = m;
   ea.neg_w_fp = -w_fp;
   ea.w_fn = w_fn;
-  const bool fix_ok = (w_fp == w_fp) && (w_fn == w_fn) && w_fp > -1024.0 && w_fp < 1024.0 && w_fn > -1024.0 && w_fn < 1024.0;
+  // The fixed-point pre-decision may only settle an element when the literal fp64 comparison cannot disagree with it.  The
+  // fp64 evaluation of s_new and s_old carries ~4 roundings of terms up to |w| * count (count <= number of columns), i.e.
+  // an error below 2^-51 |w| n, which is 2^-31 |w| n in units of d = 2^20 (w_fn P - w_fp N).  The margin P + N + 2 leaves a
+  // slack of (P + N) / 2 + 2 >= 2 such units beyond the weight rounding, so the gate is |w| n < 2^30 (error < 0.5 units).
+  const double wmax = fmax(fabs(w_fp), fabs(w_fn));
+  const bool fix_ok = (w_fp == w_fp) && (w_fn == w_fn) && wmax < 1024.0 && wmax * (double)(ld_bytes * 2) < 1073741824.0;
   const char* no_fix = getenv("BMF_NO_FIXED_PREDECISION");
   ea.fix_ok = (fix_ok && !(no_fix && no_fix[0] == '1')) ? 1 : 0;
   ea.w_fp_fix = fix_ok ? llrint(w_fp * 1048576.0) : 0;

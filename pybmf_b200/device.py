@@ -83,8 +83,8 @@ def csr_rows_view(X, r0: int, r1: int) -> sp.csr_matrix:
 def has_stored_zeros(X: sp.csr_matrix) -> bool:
     """O(nnz) host scan of the value array (the pattern kernels treat every STORED entry as a one).  Memory bound:
     large arrays are scanned by a few threads (numpy releases the GIL inside count_nonzero)."""
-    if not X.nnz or X.data.dtype == np.bool_:
-        return False
+    if not X.nnz:
+        return False                                            # (a bool matrix can store explicit False entries too)
     data = X.data
     if data.size < (1 << 22):
         return np.count_nonzero(data) != data.size

@@ -240,3 +240,13 @@ def test_install_as_pybmf_aliases_the_reference_module_paths():
             "import pybmf_b200.models as m; assert Asso is m.Asso and AssoIter is m.AssoIter; print('ok')" % ROOT)
     out = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout[-2000:]
+
+
+def test_stored_zero_scan_sees_explicit_false_in_bool_matrices():
+    """A bool csr can STORE False entries; the pattern kernels would treat them as ones (advisor finding, round 1)."""
+    from pybmf_b200 import device
+    X = sp.csr_matrix((np.array([True, False, True]), (np.array([0, 0, 1]), np.array([0, 2, 1]))), shape=(2, 3))
+    assert X.nnz == 3 and device.has_stored_zeros(X)
+    clean = device.drop_stored_zeros(X)
+    assert clean.nnz == 2 and not device.has_stored_zeros(clean)
+    assert not device.has_stored_zeros(sp.csr_matrix(np.eye(3, dtype=bool)))
