@@ -244,6 +244,7 @@ def test_install_as_pybmf_aliases_the_reference_module_paths():
 
 def test_stored_zero_scan_sees_explicit_false_in_bool_matrices():
     """A bool csr can STORE False entries; the pattern kernels would treat them as ones (advisor finding, round 1)."""
+    import scipy.sparse as sp
     from pybmf_b200 import device
     X = sp.csr_matrix((np.array([True, False, True]), (np.array([0, 0, 1]), np.array([0, 2, 1]))), shape=(2, 3))
     assert X.nnz == 3 and device.has_stored_zeros(X)
