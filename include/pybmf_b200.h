@@ -232,6 +232,25 @@ int bmf_cover_rescore_f4(const uint8_t* cand_plane, int64_t cand_pad, const uint
 int bmf_cover_rescore_i8(const int8_t* cand_plane, int64_t cand_pad, const int8_t* compact_plane, int64_t rows_cap,
                          int64_t ld, int32_t sign, const int32_t* cand_pop, int32_t bias_scale, const int32_t* dyn_rows,
                          int32_t gain_sign, int64_t* gain, bmf_stream_t stream);
+/* The same for GENERAL (non-dyadic) weights: sum_use P and sum_use N update by the same identity.  The compacted operand
+ * is the interleaved P/Q plane (kind 3: packed E2M1 in blocks of 120 rows, kind 4: int8 in blocks of 128 rows) and the used
+ * rows' per-row TP / FP before and after the update travel with it (comp_tp_* / comp_fp_*, indexed by slot), because the
+ * fp64 row test needs them.  bmf_cover_rescore_*_general = bmf_cover_score_*_general on the compacted rows, row count from
+ * *dyn_rows, gain_p / gain_n accumulated with gain_sign instead of overwritten. */
+int bmf_cover_apply_compact_general(const uint64_t* x_bits, uint64_t* c_bits, int64_t m, int64_t n, int64_t words,
+                                    const uint64_t* basis_bits, uint8_t* alive, const int64_t* winner, int32_t* tp_old,
+                                    int32_t* fp_old, double w_fp, double w_fn, int32_t kind, uint8_t* comp_old,
+                                    uint8_t* comp_new, int64_t comp_ld, int64_t comp_cap, int32_t* nused,
+                                    int32_t* comp_tp_old, int32_t* comp_fp_old, int32_t* comp_tp_new,
+                                    int32_t* comp_fp_new, uint64_t* u_bits, int64_t* totals, bmf_stream_t stream);
+int bmf_cover_rescore_f4_general(const uint8_t* cand_plane, int64_t cand_pad, const uint8_t* compact_pq_plane,
+                                 int64_t rows_cap, int64_t ld_bytes, const int32_t* cand_pop, const int32_t* comp_tp,
+                                 const int32_t* comp_fp, double w_fp, double w_fn, const int32_t* dyn_rows,
+                                 int32_t gain_sign, int64_t* gain_p, int64_t* gain_n, bmf_stream_t stream);
+int bmf_cover_rescore_i8_general(const int8_t* cand_plane, int64_t cand_pad, const int8_t* compact_pq_plane,
+                                 int64_t rows_cap, int64_t ld, const int32_t* cand_pop, const int32_t* comp_tp,
+                                 const int32_t* comp_fp, double w_fp, double w_fn, const int32_t* dyn_rows,
+                                 int32_t gain_sign, int64_t* gain_p, int64_t* gain_n, bmf_stream_t stream);
 /* bmf_basis_threshold on a row window [row0, row0 + nrows) (all pointers at row row0): with the rows of X sharded, every
  * rank thresholds the block of X^T X it received from the reduce-scatter and the bit rows are all-gathered.
  * symmetric != 0 (row0 = 0): entries below the diagonal were skipped by bmf_gemm_f4_nt(accumulate bit 1) and are read

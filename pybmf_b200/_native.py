@@ -53,6 +53,10 @@ SIGNATURES = {
                                 _i64, _i64, _i32, _p, _p, _p, _i64, _i32, _p, _p, _p],
     "bmf_cover_rescore_f4": [_p, _i64, _p, _i64, _i64, _p, _i32, _p, _i32, _p, _p],
     "bmf_cover_rescore_i8": [_p, _i64, _p, _i64, _i64, _i32, _p, _i32, _p, _i32, _p, _p],
+    "bmf_cover_apply_compact_general": [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _f64, _f64, _i32, _p, _p, _i64, _i64, _p,
+                                        _p, _p, _p, _p, _p, _p, _p],
+    "bmf_cover_rescore_f4_general": [_p, _i64, _p, _i64, _i64, _p, _p, _p, _f64, _f64, _p, _i32, _p, _p, _p],
+    "bmf_cover_rescore_i8_general": [_p, _i64, _p, _i64, _i64, _p, _p, _p, _f64, _f64, _p, _i32, _p, _p, _p],
     "bmf_basis_threshold_rows": [_p, _i64, _i64, _i64, _i64, _i32, _f64, _p, _i64, _p, _p, _p],
     "bmf_expand_scores": [_p, _p, _i64, _i64, _p, _p, _f64, _f64, _p, _p, _p],
     "bmf_optimal_rows": [_p, _i64, _i64, _p, _i64, _f64, _f64, _p, _p, _p],

@@ -555,6 +555,27 @@ __global__ void compact_tail_zero_kernel(uint8_t* __restrict__ a, uint8_t* __res
   }
 }
 
+// the same for the interleaved P/Q layouts (blocks of `blk` data rows: blk P rows then blk Q rows): slots
+// [*nused, round_up(*nused, blk)) of the last block.  The FP4 general-weights epilogue settles most elements in fixed point
+// WITHOUT looking at the row state, so padding rows must really be zero (P = N = 0 leaves them undecided -> fp64 -> +inf).
+__global__ void compact_tail_zero_pq_kernel(uint8_t* __restrict__ a, uint8_t* __restrict__ b, int64_t ld, int64_t cap,
+                                            const int* __restrict__ nused, int blk) {
+  const int64_t used = *nused < cap ? *nused : cap;
+  int64_t end = (used + blk - 1) / blk * blk;
+  if (end > cap) end = (cap + blk - 1) / blk * blk;
+  const int64_t chunks = ld >> 4;
+  const int64_t total = (end - used) * chunks;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t slot = used + t / chunks, ch = t % chunks;
+    const int64_t prow = (slot / blk) * (2 * blk) + slot % blk;
+    reinterpret_cast<uint4*>(a + prow * ld)[ch] = z;
+    reinterpret_cast<uint4*>(b + prow * ld)[ch] = z;
+    reinterpret_cast<uint4*>(a + (prow + blk) * ld)[ch] = z;
+    reinterpret_cast<uint4*>(b + (prow + blk) * ld)[ch] = z;
+  }
+}
+
 // =========================================================================================
 // apply the chosen candidate: one warp per data row, 128-bit row streams
 // =========================================================================================
@@ -577,6 +598,12 @@ struct ApplyExtra {
   int64_t kw;
   int factor_bit;
   uint64_t* vt_row;
+  // general weights (kinds 3 = packed E2M1 P/Q blocks of 120 rows, 4 = int8 P/Q blocks of 128 rows): the used rows' per-row
+  // TP / FP before and after the update travel with the compacted planes (the fp64 row test needs them)
+  int32_t* comp_tp_old;
+  int32_t* comp_fp_old;
+  int32_t* comp_tp_new;
+  int32_t* comp_fp_new;
 };
 
 __global__ void __launch_bounds__(256)
@@ -624,28 +651,48 @@ cover_apply_kernel(const uint64_t* __restrict__ xb, uint64_t* __restrict__ cb, i
       if (slot >= 0) {                                                  // this row before / after the update
         const ulonglong2 x = ld_words2(xb + i * words + 2 * p);
         const uint64_t xw[2] = {x.x, x.y}, cw[2] = {c.x, c.y}, nw[2] = {c.x | v.x, c.y | v.y};
+        const int kind = ex.comp_kind;
+        // plane row of this slot (P row for the P/Q layouts; the Q row sits q_off rows further)
+        const int64_t prow = kind == 3 ? (slot / 120) * 240 + slot % 120 : (kind == 4 ? (slot >> 7) * 256 + (slot & 127) : slot);
+        const int64_t q_off = (kind == 3 ? 120 : 128) * ex.comp_ld;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int64_t col0 = (2 * p + h) * 64;
           const int64_t left = n - col0;
           const uint64_t valid = left >= 64 ? ~0ull : (left <= 0 ? 0ull : ((1ull << left) - 1ull));
-          if (ex.comp_kind == 1) {                                      // 64 bits -> 32 bytes of packed E2M1
-            uint4* o = reinterpret_cast<uint4*>(ex.comp_old + slot * ex.comp_ld + (2 * p + h) * 32);
-            uint4* q = reinterpret_cast<uint4*>(ex.comp_new + slot * ex.comp_ld + (2 * p + h) * 32);
+          if (kind == 1 || kind == 3) {                                 // 64 bits -> 32 bytes of packed E2M1
+            uint4* o = reinterpret_cast<uint4*>(ex.comp_old + prow * ex.comp_ld + (2 * p + h) * 32);
+            uint4* q = reinterpret_cast<uint4*>(ex.comp_new + prow * ex.comp_ld + (2 * p + h) * 32);
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               const uint32_t x32 = (uint32_t)(xw[h] >> (32 * g)), vd = (uint32_t)(valid >> (32 * g));
-              o[g] = f4_codes32(x32, (uint32_t)(cw[h] >> (32 * g)), vd, ex.v_one, ex.v_zero, ex.v_cov);
-              q[g] = f4_codes32(x32, (uint32_t)(nw[h] >> (32 * g)), vd, ex.v_one, ex.v_zero, ex.v_cov);
+              const uint32_t c32 = (uint32_t)(cw[h] >> (32 * g)), n32 = (uint32_t)(nw[h] >> (32 * g));
+              if (kind == 1) {
+                o[g] = f4_codes32(x32, c32, vd, ex.v_one, ex.v_zero, ex.v_cov);
+                q[g] = f4_codes32(x32, n32, vd, ex.v_one, ex.v_zero, ex.v_cov);
+              } else {                                                  // P = x & ~c and Q = c as E2M1 1.0 (code 2)
+                o[g] = f4_codes32(x32 & ~c32, 0u, vd, 2u, 0u, 0u);
+                q[g] = f4_codes32(x32 & ~n32, 0u, vd, 2u, 0u, 0u);
+                reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(o) + q_off)[g] = f4_codes32(c32, 0u, vd, 2u, 0u, 0u);
+                reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(q) + q_off)[g] = f4_codes32(n32, 0u, vd, 2u, 0u, 0u);
+              }
             }
           } else {                                                      // 64 bits -> 64 int8
-            uint4* o = reinterpret_cast<uint4*>(ex.comp_old + slot * ex.comp_ld + (2 * p + h) * 64);
-            uint4* q = reinterpret_cast<uint4*>(ex.comp_new + slot * ex.comp_ld + (2 * p + h) * 64);
+            uint4* o = reinterpret_cast<uint4*>(ex.comp_old + prow * ex.comp_ld + (2 * p + h) * 64);
+            uint4* q = reinterpret_cast<uint4*>(ex.comp_new + prow * ex.comp_ld + (2 * p + h) * 64);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const uint32_t x16 = (uint32_t)(xw[h] >> (16 * g)) & 0xffffu, vd = (uint32_t)(valid >> (16 * g)) & 0xffffu;
-              o[g] = i8_bytes16(x16, (uint32_t)(cw[h] >> (16 * g)) & 0xffffu, vd, ex.v_one, ex.v_zero, ex.v_cov);
-              q[g] = i8_bytes16(x16, (uint32_t)(nw[h] >> (16 * g)) & 0xffffu, vd, ex.v_one, ex.v_zero, ex.v_cov);
+              const uint32_t c16 = (uint32_t)(cw[h] >> (16 * g)) & 0xffffu, n16 = (uint32_t)(nw[h] >> (16 * g)) & 0xffffu;
+              if (kind == 2) {
+                o[g] = i8_bytes16(x16, c16, vd, ex.v_one, ex.v_zero, ex.v_cov);
+                q[g] = i8_bytes16(x16, n16, vd, ex.v_one, ex.v_zero, ex.v_cov);
+              } else {
+                o[g] = i8_bytes16(x16 & ~c16, 0u, vd, 1, 0, 0);
+                q[g] = i8_bytes16(x16 & ~n16, 0u, vd, 1, 0, 0);
+                reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(o) + q_off)[g] = i8_bytes16(c16, 0u, vd, 1, 0, 0);
+                reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(q) + q_off)[g] = i8_bytes16(n16, 0u, vd, 1, 0, 0);
+              }
             }
           }
         }
@@ -696,11 +743,24 @@ cover_apply_kernel(const uint64_t* __restrict__ xb, uint64_t* __restrict__ cb, i
       *cp = c;
     }
     if (slot >= 0) {                                                    // K padding of the compact rows (never written above)
-      const int64_t used_bytes = words * (ex.comp_kind == 1 ? 32 : 64);
+      const int kind = ex.comp_kind;
+      const int64_t used_bytes = words * ((kind == 1 || kind == 3) ? 32 : 64);
+      const int64_t prow = kind == 3 ? (slot / 120) * 240 + slot % 120 : (kind == 4 ? (slot >> 7) * 256 + (slot & 127) : slot);
+      const int64_t q_off = (kind == 3 ? 120 : 128) * ex.comp_ld;
       const uint4 z = make_uint4(0u, 0u, 0u, 0u);
       for (int64_t q = lane; q < ((ex.comp_ld - used_bytes) >> 4); q += 32) {
-        reinterpret_cast<uint4*>(ex.comp_old + slot * ex.comp_ld + used_bytes)[q] = z;
-        reinterpret_cast<uint4*>(ex.comp_new + slot * ex.comp_ld + used_bytes)[q] = z;
+        uint4* o = reinterpret_cast<uint4*>(ex.comp_old + prow * ex.comp_ld + used_bytes) + q;
+        uint4* w = reinterpret_cast<uint4*>(ex.comp_new + prow * ex.comp_ld + used_bytes) + q;
+        *o = z;
+        *w = z;
+        if (kind >= 3) {
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(o) + q_off) = z;
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(w) + q_off) = z;
+        }
+      }
+      if (lane == 0 && kind >= 3) {
+        ex.comp_tp_old[slot] = tpo; ex.comp_fp_old[slot] = fpo;
+        ex.comp_tp_new[slot] = tpo + P; ex.comp_fp_new[slot] = fpo + N;
       }
     }
     if (lane == 0) {
@@ -1689,6 +1749,31 @@ extern "C" int bmf_cover_apply_compact(const uint64_t* x_bits, uint64_t* c_bits,
   if (rc || kind == 0) return rc;
   compact_tail_zero_kernel<<<64, 256, 0, as_stream(stream)>>>(comp_old, comp_new, comp_ld, comp_cap, nused, tile_rows);
   BMF_LAUNCH_CHECK("bmf_cover_apply_compact");
+  return 0;
+}
+
+extern "C" int bmf_cover_apply_compact_general(const uint64_t* x_bits, uint64_t* c_bits, int64_t m, int64_t n, int64_t words,
+                                               const uint64_t* basis_bits, uint8_t* alive, const int64_t* winner,
+                                               int32_t* tp_old, int32_t* fp_old, double w_fp, double w_fn, int32_t kind,
+                                               uint8_t* comp_old, uint8_t* comp_new, int64_t comp_ld, int64_t comp_cap,
+                                               int32_t* nused, int32_t* comp_tp_old, int32_t* comp_fp_old,
+                                               int32_t* comp_tp_new, int32_t* comp_fp_new, uint64_t* u_bits,
+                                               int64_t* totals, bmf_stream_t stream) {
+  BMF_REQUIRE(kind == 0 || ((kind == 3 || kind == 4) && comp_old && comp_new && nused && comp_cap > 0 && comp_tp_old &&
+                            comp_fp_old && comp_tp_new && comp_fp_new),
+              "bmf_cover_apply_compact_general: kind 3 (E2M1 P/Q) / 4 (int8 P/Q) needs the compact planes, counters and counter");
+  BMF_REQUIRE(kind == 0 || (comp_ld % 128 == 0 && comp_ld * (kind == 3 ? 2 : 1) >= words * 64),
+              "bmf_cover_apply_compact_general: comp_ld must cover words*64 columns");
+  ApplyExtra ex = {};
+  ex.comp_old = comp_old; ex.comp_new = comp_new; ex.comp_ld = comp_ld; ex.comp_cap = comp_cap; ex.nused = nused;
+  ex.comp_kind = kind;
+  ex.comp_tp_old = comp_tp_old; ex.comp_fp_old = comp_fp_old; ex.comp_tp_new = comp_tp_new; ex.comp_fp_new = comp_fp_new;
+  int rc = launch_cover_apply(x_bits, c_bits, m, n, words, basis_bits, alive, winner, tp_old, fp_old, 0, 0, w_fp, w_fn,
+                              nullptr, 0, 0, 0, u_bits, totals, stream, ex);
+  if (rc || kind == 0) return rc;
+  compact_tail_zero_pq_kernel<<<64, 256, 0, as_stream(stream)>>>(comp_old, comp_new, comp_ld, comp_cap, nused,
+                                                               kind == 3 ? 120 : 128);
+  BMF_LAUNCH_CHECK("bmf_cover_apply_compact_general");
   return 0;
 }
 

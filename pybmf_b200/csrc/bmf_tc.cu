@@ -163,13 +163,18 @@ __device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// EPI_GAIN2 on compacted rows (incremental re-scoring): the number of valid data rows comes from the device counter
+__device__ __forceinline__ int64_t dyn_m_rows(const EpiArgs& ea) {
+  return ea.dyn_rows != nullptr ? (int64_t)*reinterpret_cast<const volatile int32_t*>(ea.dyn_rows) : ea.m_rows;
+}
+
 // EPI_GAIN2, before the accumulator is waited for: the 128 epilogue threads of a CTA stage the state of the
 // tile's 128 data rows (et = 0..127) into buffer `acc` and meet on named barrier 1.  With two buffers one
 // barrier per tile is enough: a thread that passes the barrier of tile t+1 has finished reading tile t.
 __device__ __forceinline__ void stage_row_state(RowState* rs, int acc, int et, int nt, const EpiArgs& ea) {
   const int64_t i = (int64_t)nt * 128 + et;
   RowState r;
-  if (i < ea.m_rows) {
+  if (i < dyn_m_rows(ea)) {
     r.tpo = ea.tp_old[i];
     r.fpo = ea.fp_old[i];
     r.s_old = cover_score_f64(ea.neg_w_fp, ea.w_fn, r.fpo, r.tpo);
@@ -208,8 +213,8 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int64_t row, int n
       sum_n += part_n;
     }
     if (sum_p | sum_n) {
-      atomicAdd(ea.gain + row, (unsigned long long)sum_p);
-      atomicAdd(ea.gain_n + row, (unsigned long long)sum_n);
+      atomicAdd(ea.gain + row, (unsigned long long)(ea.gain_sign < 0 ? -sum_p : sum_p));
+      atomicAdd(ea.gain_n + row, (unsigned long long)(ea.gain_sign < 0 ? -sum_n : sum_n));
     }
   } else {
     const int bias = (EPI == EPI_GAIN && ea.cand_pop != nullptr) ? ea.bias_scale * ea.cand_pop[row] : 0;
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                int mt_total, int nt_total_in, int kb_total, int group_m, const EpiArgs ea) {
   extern __shared__ uint8_t smem_raw[];
-  const int nt_total = dyn_row_tiles(ea, nt_total_in, BN);
+  const int nt_total = dyn_row_tiles(ea, nt_total_in, EPI == EPI_GAIN2 ? 128 : BN);   // GAIN2: a tile = 128 P + 128 Q rows
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then tmem base
@@ -498,7 +503,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_i8_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    int mt_total, int nt_total_in, int kb_total, int group_m, const EpiArgs ea) {
   extern __shared__ uint8_t smem_raw[];
-  const int nt_total = dyn_row_tiles(ea, nt_total_in, BN);
+  const int nt_total = dyn_row_tiles(ea, nt_total_in, EPI == EPI_GAIN2 ? 128 : BN);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE_BYTES2);
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES2 + 4);
@@ -723,7 +728,7 @@ __device__ __forceinline__ void stage_row_state_f4(RowState* rs, int acc, int et
   if (et < HALFN) {
     const int64_t i = (int64_t)nt * HALFN + et;
     RowState r;
-    if (i < ea.m_rows) {
+    if (i < dyn_m_rows(ea)) {
       r.tpo = ea.tp_old[i];
       r.fpo = ea.fp_old[i];
       r.s_old = cover_score_f64(ea.neg_w_fp, ea.w_fn, r.fpo, r.tpo);
@@ -789,8 +794,8 @@ __device__ __forceinline__ void epilogue_tile_f4(uint32_t taddr, int64_t row, in
       sum_n += part_n;
     }
     if (sum_p | sum_n) {
-      atomicAdd(ea.gain + row, (unsigned long long)sum_p);
-      atomicAdd(ea.gain_n + row, (unsigned long long)sum_n);
+      atomicAdd(ea.gain + row, (unsigned long long)(ea.gain_sign < 0 ? -sum_p : sum_p));
+      atomicAdd(ea.gain_n + row, (unsigned long long)(ea.gain_sign < 0 ? -sum_n : sum_n));
     }
     return;
   }
@@ -822,8 +827,9 @@ __device__ __forceinline__ void epilogue_tile_f4(uint32_t taddr, int64_t row, in
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F4Threads<EPI>::value, 1)
 gemm_f4_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   int mt_total, int nt_total, int kb_total, int group_m, const EpiArgs ea) {
+                   int mt_total, int nt_total_in, int kb_total, int group_m, const EpiArgs ea) {
   extern __shared__ uint8_t smem_raw[];
+  const int nt_total = dyn_row_tiles(ea, nt_total_in, EPI == EPI_GAIN2 ? HALFN : BN4);   // GAIN2: a tile = 120 P + 120 Q rows
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES4 * STAGE_BYTES4);
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES4 + 4);
@@ -1445,20 +1451,22 @@ extern "C" int bmf_cover_rescore_i8(const int8_t* cand_plane, int64_t cand_pad, 
   return tc::dispatch_gemm<tc::EPI_GAIN>(0, cand_plane, cand_pad, compact_plane, rows_cap, ld, ea, as_stream(stream));
 }
 
-extern "C" int bmf_cover_score_i8_general(const int8_t* cand_plane, int64_t cand_pad, const int8_t* pq_plane,
-                                          int64_t m, int64_t ld, const int32_t* cand_pop, const int32_t* tp_old,
-                                          const int32_t* fp_old, double w_fp, double w_fn, int64_t* gain_p,
-                                          int64_t* gain_n, bmf_stream_t stream) {
+static int cover_score_i8_general_impl(const int8_t* cand_plane, int64_t cand_pad, const int8_t* pq_plane, int64_t m,
+                                       int64_t ld, const int32_t* cand_pop, const int32_t* tp_old, const int32_t* fp_old,
+                                       double w_fp, double w_fn, int64_t* gain_p, int64_t* gain_n, const int32_t* dyn_rows,
+                                       int gain_sign, bmf_stream_t stream) {
   BMF_REQUIRE(cand_plane && pq_plane && cand_pop && tp_old && fp_old && gain_p && gain_n,
               "bmf_cover_score_i8_general: null pointer");
   BMF_REQUIRE(cand_pad > 0 && cand_pad % tc::BM == 0, "bmf_cover_score_i8_general: cand_pad must be a positive multiple of 128");
   BMF_REQUIRE(m > 0, "bmf_cover_score_i8_general: no data rows");
   BMF_REQUIRE(ld > 0 && ld % tc::BK == 0, "bmf_cover_score_i8_general: ld must be a positive multiple of 128");
   const int64_t plane_rows = 2 * ceil_div(m, 128) * 128;   // [ceil(m/128)][P|Q][128] rows of ld bytes
-  int rc = check_cuda(cudaMemsetAsync(gain_p, 0, sizeof(int64_t) * cand_pad, as_stream(stream)), "bmf_cover_score_i8_general");
-  if (rc) return rc;
-  rc = check_cuda(cudaMemsetAsync(gain_n, 0, sizeof(int64_t) * cand_pad, as_stream(stream)), "bmf_cover_score_i8_general");
-  if (rc) return rc;
+  if (dyn_rows == nullptr) {                               // a full pass overwrites; a re-score accumulates
+    int rc = check_cuda(cudaMemsetAsync(gain_p, 0, sizeof(int64_t) * cand_pad, as_stream(stream)), "bmf_cover_score_i8_general");
+    if (rc) return rc;
+    rc = check_cuda(cudaMemsetAsync(gain_n, 0, sizeof(int64_t) * cand_pad, as_stream(stream)), "bmf_cover_score_i8_general");
+    if (rc) return rc;
+  }
   tc::EpiArgs ea = {};
   ea.cand_pop = cand_pop;
   ea.gain = reinterpret_cast<unsigned long long*>(gain_p);
@@ -1468,7 +1476,26 @@ extern "C" int bmf_cover_score_i8_general(const int8_t* cand_plane, int64_t cand
   ea.m_rows = m;
   ea.neg_w_fp = -w_fp;
   ea.w_fn = w_fn;
+  ea.dyn_rows = dyn_rows;
+  ea.gain_sign = gain_sign;
   return tc::dispatch_gemm<tc::EPI_GAIN2>(0, cand_plane, cand_pad, pq_plane, plane_rows, ld, ea, as_stream(stream));
+}
+
+extern "C" int bmf_cover_score_i8_general(const int8_t* cand_plane, int64_t cand_pad, const int8_t* pq_plane,
+                                          int64_t m, int64_t ld, const int32_t* cand_pop, const int32_t* tp_old,
+                                          const int32_t* fp_old, double w_fp, double w_fn, int64_t* gain_p,
+                                          int64_t* gain_n, bmf_stream_t stream) {
+  return cover_score_i8_general_impl(cand_plane, cand_pad, pq_plane, m, ld, cand_pop, tp_old, fp_old, w_fp, w_fn, gain_p,
+                                     gain_n, nullptr, 1, stream);
+}
+
+extern "C" int bmf_cover_rescore_i8_general(const int8_t* cand_plane, int64_t cand_pad, const int8_t* compact_pq_plane,
+                                            int64_t rows_cap, int64_t ld, const int32_t* cand_pop, const int32_t* comp_tp,
+                                            const int32_t* comp_fp, double w_fp, double w_fn, const int32_t* dyn_rows,
+                                            int32_t gain_sign, int64_t* gain_p, int64_t* gain_n, bmf_stream_t stream) {
+  BMF_REQUIRE(dyn_rows != nullptr && (gain_sign == 1 || gain_sign == -1), "bmf_cover_rescore_i8_general: dyn_rows / gain_sign");
+  return cover_score_i8_general_impl(cand_plane, cand_pad, compact_pq_plane, rows_cap, ld, cand_pop, comp_tp, comp_fp, w_fp,
+                                     w_fn, gain_p, gain_n, dyn_rows, gain_sign, stream);
 }
 
 // ---- FP4 (kind::mxf4) entry points -------------------------------------------------------------------
@@ -1536,20 +1563,22 @@ extern "C" int bmf_cover_rescore_f4(const uint8_t* cand_plane, int64_t cand_pad,
   return tc::f4::launch_gemm_f4s<tc::EPI_GAIN>(cand_plane, cand_pad, compact_plane, rows_cap, ld_bytes, ea, as_stream(stream));
 }
 
-extern "C" int bmf_cover_score_f4_general(const uint8_t* cand_plane, int64_t cand_pad, const uint8_t* pq_plane, int64_t m,
-                                          int64_t ld_bytes, const int32_t* cand_pop, const int32_t* tp_old,
-                                          const int32_t* fp_old, double w_fp, double w_fn, int64_t* gain_p,
-                                          int64_t* gain_n, bmf_stream_t stream) {
+static int cover_score_f4_general_impl(const uint8_t* cand_plane, int64_t cand_pad, const uint8_t* pq_plane, int64_t m,
+                                       int64_t ld_bytes, const int32_t* cand_pop, const int32_t* tp_old,
+                                       const int32_t* fp_old, double w_fp, double w_fn, int64_t* gain_p, int64_t* gain_n,
+                                       const int32_t* dyn_rows, int gain_sign, bmf_stream_t stream) {
   BMF_REQUIRE(cand_plane && pq_plane && cand_pop && tp_old && fp_old && gain_p && gain_n,
               "bmf_cover_score_f4_general: null pointer");
   BMF_REQUIRE(cand_pad > 0 && cand_pad % tc::f4::BM4 == 0, "bmf_cover_score_f4_general: cand_pad must be a positive multiple of 256");
   BMF_REQUIRE(m > 0, "bmf_cover_score_f4_general: no data rows");
   BMF_REQUIRE(ld_bytes > 0 && ld_bytes % tc::BK == 0, "bmf_cover_score_f4_general: ld_bytes must be a positive multiple of 128");
   const int64_t plane_rows = 2 * ceil_div(m, tc::f4::HALFN) * tc::f4::HALFN;   // [ceil(m/120)][P|Q][120] rows
-  int rc = check_cuda(cudaMemsetAsync(gain_p, 0, sizeof(int64_t) * cand_pad, as_stream(stream)), "bmf_cover_score_f4_general");
-  if (rc) return rc;
-  rc = check_cuda(cudaMemsetAsync(gain_n, 0, sizeof(int64_t) * cand_pad, as_stream(stream)), "bmf_cover_score_f4_general");
-  if (rc) return rc;
+  if (dyn_rows == nullptr) {                               // a full pass overwrites; a re-score accumulates
+    int rc = check_cuda(cudaMemsetAsync(gain_p, 0, sizeof(int64_t) * cand_pad, as_stream(stream)), "bmf_cover_score_f4_general");
+    if (rc) return rc;
+    rc = check_cuda(cudaMemsetAsync(gain_n, 0, sizeof(int64_t) * cand_pad, as_stream(stream)), "bmf_cover_score_f4_general");
+    if (rc) return rc;
+  }
   tc::EpiArgs ea = {};
   ea.cand_pop = cand_pop;
   ea.gain = reinterpret_cast<unsigned long long*>(gain_p);
@@ -1559,6 +1588,8 @@ extern "C" int bmf_cover_score_f4_general(const uint8_t* cand_plane, int64_t can
   ea.m_rows = m;
   ea.neg_w_fp = -w_fp;
   ea.w_fn = w_fn;
+  ea.dyn_rows = dyn_rows;
+  ea.gain_sign = gain_sign;
   // The fixed-point pre-decision may only settle an element when the literal fp64 comparison cannot disagree with it.  The
   // fp64 evaluation of s_new and s_old carries ~4 roundings of terms up to |w| * count (count <= number of columns), i.e.
   // an error below 2^-51 |w| n, which is 2^-31 |w| n in units of d = 2^20 (w_fn P - w_fp N).  The margin P + N + 2 leaves a
@@ -1570,6 +1601,24 @@ extern "C" int bmf_cover_score_f4_general(const uint8_t* cand_plane, int64_t can
   ea.w_fp_fix = fix_ok ? llrint(w_fp * 1048576.0) : 0;
   ea.w_fn_fix = fix_ok ? llrint(w_fn * 1048576.0) : 0;
   return tc::f4::launch_gemm_f4<tc::EPI_GAIN2>(cand_plane, cand_pad, pq_plane, plane_rows, ld_bytes, ea, as_stream(stream));
+}
+
+extern "C" int bmf_cover_score_f4_general(const uint8_t* cand_plane, int64_t cand_pad, const uint8_t* pq_plane, int64_t m,
+                                          int64_t ld_bytes, const int32_t* cand_pop, const int32_t* tp_old,
+                                          const int32_t* fp_old, double w_fp, double w_fn, int64_t* gain_p,
+                                          int64_t* gain_n, bmf_stream_t stream) {
+  return cover_score_f4_general_impl(cand_plane, cand_pad, pq_plane, m, ld_bytes, cand_pop, tp_old, fp_old, w_fp, w_fn,
+                                     gain_p, gain_n, nullptr, 1, stream);
+}
+
+extern "C" int bmf_cover_rescore_f4_general(const uint8_t* cand_plane, int64_t cand_pad, const uint8_t* compact_pq_plane,
+                                            int64_t rows_cap, int64_t ld_bytes, const int32_t* cand_pop,
+                                            const int32_t* comp_tp, const int32_t* comp_fp, double w_fp, double w_fn,
+                                            const int32_t* dyn_rows, int32_t gain_sign, int64_t* gain_p, int64_t* gain_n,
+                                            bmf_stream_t stream) {
+  BMF_REQUIRE(dyn_rows != nullptr && (gain_sign == 1 || gain_sign == -1), "bmf_cover_rescore_f4_general: dyn_rows / gain_sign");
+  return cover_score_f4_general_impl(cand_plane, cand_pad, compact_pq_plane, rows_cap, ld_bytes, cand_pop, comp_tp, comp_fp,
+                                     w_fp, w_fn, gain_p, gain_n, dyn_rows, gain_sign, stream);
 }
 
 

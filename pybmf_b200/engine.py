@@ -167,9 +167,9 @@ class CoverEngine:
         # changed state) -- integer weights on the tensor-core scorers; 'auto' picks incremental where it exists.
         rescore = os.environ.get("BMF_RESCORE", rescore)
         assert rescore in ("auto", "full", "incremental")
-        can_inc = self.integer_mode and scorer == "tcgen05" and enc in ("zero", "signed")
+        can_inc = scorer == "tcgen05"                          # integer weights and general weights (P/Q planes) alike
         if rescore == "incremental" and not can_inc:
-            raise ValueError("incremental rescoring needs integer weights (a/2^s) and a tensor-core scorer")
+            raise ValueError("incremental rescoring needs a tensor-core scorer")
         self.rescore = "incremental" if (can_inc and rescore != "full") else "full"
         # X^T X is symmetric: on one GPU the FP4 association skips the tiles below the diagonal (with sharded rows every
         # rank needs complete row blocks for the reduce-scatter, and its share of the GEMM is 1/world anyway)
@@ -222,7 +222,7 @@ class CoverEngine:
         self.nused = device.zeros((2,), torch.int32)
         self.table = None                                       # [kcap + 1, 8] per-step results
         self.u_all = None                                       # [kcap, words_m] usage bit columns
-        self.comp_old = self.comp_new = None
+        self.comp_old = self.comp_new = self.comp_counts = None
         self.plane_stale = False
         self.score_events = None                                # bench: list of (start, end) CUDA events per scoring pass
         self.u_cols = []                                        # device bit vectors, one per chosen factor
@@ -544,6 +544,8 @@ class CoverEngine:
             dt = self.rows_plane.dtype
             self.comp_old = device.empty((rows, ld), dt)           # capacity = every row: a winner can use them all;
             self.comp_new = device.empty((rows, ld), dt)           # bmf_cover_apply_compact writes whole rows incl. K padding
+            if self.encoding == "pq":                              # general weights: the used rows' TP / FP before / after
+                self.comp_counts = device.zeros((4, self.m_loc), torch.int32)
 
     def _score_into_gains(self):
         """One FULL scoring pass of the current cover into the local gain vector(s) (kernel only, no exchange)."""
@@ -628,6 +630,16 @@ class CoverEngine:
             return
         u_bits = self.u_all[t]
         lib = _native.load()
+        if self.rescore == "incremental" and self.encoding == "pq":
+            kind = 3 if self.operand == "f4" else 4
+            cc = self.comp_counts
+            _native.call("bmf_cover_apply_compact_general", self.x_bits, self.c_bits, self.m_loc, self.n, self.words,
+                         self.basis_bits, self.alive, self.record, self.tp_old, self.fp_old, self.w_fp, self.w_fn,
+                         kind if compact else 0, self.comp_old, self.comp_new, self.comp_old.shape[1], self.m_loc,
+                         self.nused, cc[0], cc[1], cc[2], cc[3], u_bits, self.tail)
+            self.plane_stale = True
+            self.launches += 2 if compact else 1
+            return
         if self.rescore == "incremental":
             if self.operand == "f4":
                 kind, (one, zero, cov) = 1, [lib.bmf_e2m1_code(v) for v in self._plane_values()]
@@ -667,6 +679,15 @@ class CoverEngine:
         if self.m_loc == 0:
             return
         cap = self.comp_old.shape[0]
+        if self.encoding == "pq":
+            cc = self.comp_counts
+            fn = "bmf_cover_rescore_f4_general" if self.operand == "f4" else "bmf_cover_rescore_i8_general"
+            ld = self.ld4 if self.operand == "f4" else self.ld
+            for plane, tp, fp, sign in ((self.comp_old, cc[0], cc[1], -1), (self.comp_new, cc[2], cc[3], 1)):
+                _native.call(fn, self.cand_plane, self.cand_pad, plane, self.m_loc, ld, self.cand_pop, tp, fp, self.w_fp,
+                             self.w_fn, self.nused, sign, self.gain_p, self.gain_n)
+            self.launches += 2
+            return
         for plane, sign in ((self.comp_old, -1), (self.comp_new, 1)):
             if self.operand == "f4":
                 _native.call("bmf_cover_rescore_f4", self.cand_plane, self.cand_pad, plane, cap, self.ld4, self.cand_pop,

@@ -64,6 +64,18 @@ def test_asso_matches_reference_bit_exact(M, name, scorer, assoc):
 
 
 @pytest.mark.parametrize("name", GENERAL_CASES)
+@pytest.mark.parametrize("scorer", ["tcgen05_f4", "tcgen05_i8"])
+def test_asso_general_weights_full_rescoring(M, name, scorer):
+    """the same golden vectors with a full scoring pass per step (the default re-scores incrementally)"""
+    c = load_golden(name)
+    g = c["g"]
+    mdl = _fit(M, c, scorer=scorer, rescore="full")
+    assert mdl.rescore_ == "full"
+    assert np.array_equal(_dense(mdl.U), g["U"]) and np.array_equal(_dense(mdl.V), g["V"])
+    _check_logs(mdl.logs["updates"], g, exact_score=False)
+
+
+@pytest.mark.parametrize("name", GENERAL_CASES)
 @pytest.mark.parametrize("scorer", ["tcgen05", "tcgen05_f4", "tcgen05_i8", "popc"])
 def test_asso_general_weights(M, name, scorer):
     """non-dyadic weights: tensor cores (interleaved P/Q operand, fp64 row test in the epilogue) and popcount"""
@@ -362,14 +374,17 @@ def test_c4_k20_matches_oracle_digest(M, rescore):
 
 
 def test_device_loop_incremental_equals_full_rescoring(M):
-    """The device-resident loop: after every stretch of steps the incrementally maintained gain vector equals a fresh
-    full scoring pass of the same cover (all live candidates), for the FP4 and the int8 operand planes."""
+    """The device-resident loop: after every stretch of steps the incrementally maintained gain vector(s) equal a fresh
+    full scoring pass of the same cover (all live candidates) -- FP4 and int8 operand planes, integer weights (one signed
+    contraction) and general fp64 weights (sum_use P / sum_use N on the compacted P/Q planes)."""
     from pybmf_b200 import synth
     from pybmf_b200.engine import CoverEngine
     X = synth.planted(2100, 900, 10, 0.12, 0.12, 0.15, 0.02, seed=3)
-    for scorer, w_fp in (("tcgen05_f4", 0.5), ("tcgen05_i8", 0.5), ("tcgen05_i8", 0.25), ("tcgen05_f4", 0.75)):
-        inc = CoverEngine(X, w_fp, 1 - w_fp, scorer=scorer, rescore="incremental")
-        full = CoverEngine(X, w_fp, 1 - w_fp, scorer=scorer, rescore="full")
+    cases = (("tcgen05_f4", 0.5, 0.5), ("tcgen05_i8", 0.5, 0.5), ("tcgen05_i8", 0.25, 0.75), ("tcgen05_f4", 0.75, 0.25),
+             ("tcgen05_f4", 0.2, 0.8), ("tcgen05_i8", 0.2, 0.8), ("tcgen05_f4", 0.3, 0.6), ("tcgen05_i8", 0.37, 0.41))
+    for scorer, w_fp, w_fn in cases:
+        inc = CoverEngine(X, w_fp, w_fn, scorer=scorer, rescore="incremental")
+        full = CoverEngine(X, w_fp, w_fn, scorer=scorer, rescore="full")
         assert inc.rescore == "incremental" and full.rescore == "full"
         for e in (inc, full):
             e.build_basis(0.4)
@@ -380,10 +395,12 @@ def test_device_loop_incremental_equals_full_rescoring(M):
             full.enqueue_steps(done, count)
             done += count
             ti, tf = inc.read_table(0, done), full.read_table(0, done)
-            assert np.array_equal(ti, tf), (scorer, done)
+            assert np.array_equal(ti, tf), (scorer, w_fp, done)
             live = full.alive.bool()
             assert torch.equal(inc.alive, full.alive)
-            assert torch.equal(inc.gain_p[: inc.n][live], full.gain_p[: full.n][live]), (scorer, done)
+            assert torch.equal(inc.gain_p[: inc.n][live], full.gain_p[: full.n][live]), (scorer, w_fp, done)
+            if not inc.integer_mode:
+                assert torch.equal(inc.gain_n[: inc.n][live], full.gain_n[: full.n][live]), (scorer, w_fp, done)
             assert torch.equal(inc.c_bits, full.c_bits) and torch.equal(inc.tp_old, full.tp_old)
         assert (ti[:, 7] == 2).all() and (ti[:, 0] >= 0).all()
         st = inc.state.cpu().numpy()
