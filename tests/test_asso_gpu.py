@@ -407,6 +407,32 @@ def test_device_loop_incremental_equals_full_rescoring(M):
         assert st[1] == ti[-1, 5] and st[2] == ti[-1, 6] and st[4] == done
 
 
+@pytest.mark.parametrize("m,n", [(70, 50), (129, 257), (497, 130), (1000, 64)])
+def test_device_loop_ragged_shapes_match_oracle(M, m, n):
+    """Shapes that do not fill a tile, a 64-bit word or a 120 / 128 / 496-row block: whole fits (incremental and full
+    rescoring, integer and general weights) against the numpy restatement."""
+    from pybmf_b200 import synth
+    X = synth.planted(m, n, 4, 0.25, 0.25, 0.1, 0.03, seed=m + n)
+    for w_fp in (0.5, 0.2):
+        try:
+            want, err = O.asso_fit(X, 4, 0.3, w_fp), ""
+        except O.NoCandidateError as e:
+            want, err = e.args[1], "TypeError"
+        for scorer, rescore in (("tcgen05_f4", "auto"), ("tcgen05_i8", "auto"), ("tcgen05", "full")):
+            mdl = M.Asso(tau=0.3, k=4, w_fp=w_fp, scorer=scorer, rescore=rescore)
+            got_err = ""
+            try:
+                mdl.fit(X, **FIT_KW)
+            except TypeError:
+                got_err = "TypeError"
+            assert got_err == err, (scorer, rescore, w_fp)
+            assert np.array_equal(_dense(mdl.U), want["U"]) and np.array_equal(_dense(mdl.V), want["V"]), (scorer, rescore, w_fp)
+            if want["logs"]:
+                df = mdl.logs["updates"]
+                assert [int(v) for v in df[("train", 0, "TP")]] == [l["TP"] for l in want["logs"]]
+                assert [int(v) for v in df[("train", 0, "FP")]] == [l["FP"] for l in want["logs"]]
+
+
 def test_symmetric_association_equals_full(M, monkeypatch):
     """X^T X with the tiles below the diagonal skipped + the mirrored read gives the basis of the full product."""
     from pybmf_b200 import synth
