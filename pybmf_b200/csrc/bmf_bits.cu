@@ -1046,6 +1046,21 @@ __device__ __forceinline__ void panel_or_fast(const ulonglong2* Vs, int panel_pa
   }
 }
 
+// CTA -> (column panel, row split) for the panel kernels.  A row is ceil(pairs / panel_pairs) panels wide and the LAST
+// panel is usually narrower (n = 100 000 bits: six 2 KB panels and one of 224 bytes).  With a panels x splits grid the CTAs
+// of that last panel did 11 % of the others' work and then idled -- 21 of 147 SMs, which is why these kernels sat at 0.8 of
+// the copy peak whatever else was tuned.  The 1-D grid gives every panel a number of row splits proportional to its width.
+struct PanelGrid {
+  int full_panels;      // panels of full width
+  int splits_full;      // row splits (CTAs) per full panel
+  int splits_last;      // row splits of the narrower last panel (0 = there is none)
+};
+__device__ __forceinline__ void panel_coords(const PanelGrid& g, int& panel, int& split, int& nsplit) {
+  const int b = (int)blockIdx.x, nfull = g.full_panels * g.splits_full;
+  if (b < nfull) { panel = b / g.splits_full; split = b - panel * g.splits_full; nsplit = g.splits_full; }
+  else { panel = g.full_panels; split = b - nfull; nsplit = g.splits_last; }
+}
+
 // Row order (ROWMAP): 0 = every warp owns blocks of 32 CONSECUTIVE rows (one coalesced load of the usage words);
 // 1 = interleaved: a CTA owns super-blocks of 32 x (#warps) rows and at any moment its warps work on CONSECUTIVE rows
 // (warp w takes rows base + r * #warps + w), so the 2 KB segments the CTAs of one row range write (or read) at the same
@@ -1060,10 +1075,12 @@ template <bool COUNT_GT, int MODE>
 __global__ void __launch_bounds__(PANEL_THREADS, 1)
 confusion_panel_kernel(const uint64_t* __restrict__ gt, int64_t m, int64_t words,
                        const uint64_t* __restrict__ u_words, const uint64_t* __restrict__ vt, int64_t k,
-                       int panel_chunks, int RING_DEPTH, unsigned long long* __restrict__ counts) {
+                       int panel_chunks, int RING_DEPTH, const PanelGrid pg, unsigned long long* __restrict__ counts) {
   extern __shared__ __align__(128) uint8_t panel_smem[];
   const int panel_pairs = panel_chunks * CH_PAIRS;
   const int row_bytes = panel_pairs * 16;
+  int pg_panel, pg_split, pg_nsplit;
+  panel_coords(pg, pg_panel, pg_split, pg_nsplit);
   ulonglong2* Vs = reinterpret_cast<ulonglong2*>(panel_smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint8_t* ring = panel_smem + (size_t)k * row_bytes + (size_t)warp * RING_DEPTH * row_bytes;
@@ -1072,7 +1089,7 @@ confusion_panel_kernel(const uint64_t* __restrict__ gt, int64_t m, int64_t words
   const uint32_t ring0 = smem_u32(ring);
 
   const int64_t pairs = words >> 1;
-  const int64_t pair0 = (int64_t)blockIdx.x * panel_pairs;
+  const int64_t pair0 = (int64_t)pg_panel * panel_pairs;
   const int valid_pairs = (int)((pairs - pair0) < panel_pairs ? (pairs - pair0) : panel_pairs);
   const uint32_t seg_bytes = (uint32_t)valid_pairs * 16u;
   const int nch = (valid_pairs + CH_PAIRS - 1) / CH_PAIRS;  // chunks this panel really has
@@ -1088,8 +1105,8 @@ confusion_panel_kernel(const uint64_t* __restrict__ gt, int64_t m, int64_t words
   load_vt_panel(Vs, vt, k, words, pair0, panel_pairs);     // ends with __syncthreads()
 
   // this warp's rows: 32-row blocks gw, gw + nwarps, ...
-  const int64_t gw = (int64_t)blockIdx.y * PANEL_WARPS + warp;
-  const int64_t nwarps = (int64_t)gridDim.y * PANEL_WARPS;
+  const int64_t gw = (int64_t)pg_split * PANEL_WARPS + warp;
+  const int64_t nwarps = (int64_t)pg_nsplit * PANEL_WARPS;
   const int64_t blocks_total = (m + 31) >> 5;
   int my_blocks = 0, last_rows = 0;
   if (gw < blocks_total) {
@@ -1179,19 +1196,21 @@ confusion_panel_kernel(const uint64_t* __restrict__ gt, int64_t m, int64_t words
 constexpr int PRODUCT_THREADS = 1024;
 __global__ void __launch_bounds__(PRODUCT_THREADS, 1)
 bool_product_panel_kernel(const uint64_t* __restrict__ u_words, int64_t m, const uint64_t* __restrict__ vt,
-                          int64_t k, int64_t words, int panel_chunks, int rowmap, int store_mode,
+                          int64_t k, int64_t words, int panel_chunks, int rowmap, int store_mode, const PanelGrid pg,
                           uint64_t* __restrict__ pd) {
   extern __shared__ __align__(128) uint8_t panel_smem[];
   ulonglong2* Vs = reinterpret_cast<ulonglong2*>(panel_smem);
   const int panel_pairs = panel_chunks * CH_PAIRS;
   const int64_t pairs = words >> 1;
-  const int64_t pair0 = (int64_t)blockIdx.x * panel_pairs;
+  int pg_panel, pg_split, pg_nsplit;
+  panel_coords(pg, pg_panel, pg_split, pg_nsplit);
+  const int64_t pair0 = (int64_t)pg_panel * panel_pairs;
   load_vt_panel(Vs, vt, k, words, pair0, panel_pairs);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   // block index space: rowmap 0 -> 32-row blocks, one per warp and pass; rowmap 1 -> super-blocks, one per CTA and pass
-  const int64_t blk0 = rowmap ? (int64_t)blockIdx.y : (int64_t)blockIdx.y * nw + warp;
-  const int64_t blk_step = rowmap ? (int64_t)gridDim.y : (int64_t)gridDim.y * nw;
+  const int64_t blk0 = rowmap ? (int64_t)pg_split : (int64_t)pg_split * nw + warp;
+  const int64_t blk_step = rowmap ? (int64_t)pg_nsplit : (int64_t)pg_nsplit * nw;
   const int64_t blk_rows = rowmap ? (int64_t)nw * 32 : 32;
   auto my_row = [&](int64_t blk) { return panel_row(rowmap, blk, lane, warp, nw); };
   int64_t ri = my_row(blk0);
@@ -1243,6 +1262,31 @@ static inline int confusion_ring_depth(int64_t k, int chunks) {
 }
 static inline size_t confusion_panel_smem(int64_t k, int chunks, int depth) {
   return (size_t)(k + PANEL_WARPS * depth) * chunks * CH_PAIRS * 16 + PANEL_WARPS * RING_DEPTH_MAX * 8;
+}
+// every panel gets row splits in proportion to its width; the whole grid is ONE wave (<= #SM CTAs)
+static inline PanelGrid make_panel_grid(int64_t pairs, int panel_pairs, int64_t max_splits, int* total_ctas) {
+  const int64_t panels = ceil_div(pairs, panel_pairs);
+  const int64_t last_pairs = pairs - (panels - 1) * panel_pairs;
+  PanelGrid g;
+  const char* e = getenv("BMF_PANEL_BALANCE");
+  const bool balance = !(e != nullptr && e[0] == '0');
+  if (last_pairs == panel_pairs || !balance) {                       // all panels equally wide (or the round-1 grid)
+    int64_t splits = (int64_t)num_sms() / panels;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    g.full_panels = (int)panels; g.splits_full = (int)splits; g.splits_last = 0;
+  } else {
+    const double frac = (double)last_pairs / (double)panel_pairs;
+    int64_t sf = (int64_t)((double)num_sms() / ((double)(panels - 1) + frac));
+    if (sf > max_splits) sf = max_splits;
+    if (sf < 1) sf = 1;
+    int64_t sl = (int64_t)(frac * (double)sf + 0.5);
+    if (sl < 1) sl = 1;
+    while ((panels - 1) * sf + sl > (int64_t)num_sms() && sf > 1) { --sf; sl = (int64_t)(frac * (double)sf + 0.5); if (sl < 1) sl = 1; }
+    g.full_panels = (int)(panels - 1); g.splits_full = (int)sf; g.splits_last = (int)sl;
+  }
+  *total_ctas = g.full_panels * g.splits_full + g.splits_last;
+  return g;
 }
 static inline int panel_rowmap() {              // BMF_PANEL_ROWMAP=1 selects the interleaved row order (A/B experiments)
   const char* e = getenv("BMF_PANEL_ROWMAP");
@@ -1879,18 +1923,14 @@ extern "C" int bmf_bool_product(const uint64_t* u_words, int64_t m, int64_t kw, 
   if (chunks > 0) {
     const int panel_pairs = chunks * CH_PAIRS;
     const size_t smem = (size_t)k * panel_pairs * 16;
-    const int64_t panels = ceil_div(words >> 1, panel_pairs);
-    int64_t splits = (int64_t)num_sms() / panels;              // one CTA per SM, ONE wave
     const int64_t max_splits = ceil_div(m, 32 * (PRODUCT_THREADS / 32));
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-    if (splits > 65535) splits = 65535;
+    int ctas = 0;
+    const PanelGrid pg = make_panel_grid(words >> 1, panel_pairs, max_splits, &ctas);
     int rc = check_cuda(cudaFuncSetAttribute(bool_product_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem), "bmf_bool_product");
     if (rc) return rc;
-    dim3 grid((unsigned)panels, (unsigned)splits);
-    bool_product_panel_kernel<<<grid, PRODUCT_THREADS, smem, as_stream(stream)>>>(u_words, m, vt_bits, k, words, chunks,
-                                                                                panel_rowmap(), product_store_mode(),
+    bool_product_panel_kernel<<<ctas, PRODUCT_THREADS, smem, as_stream(stream)>>>(u_words, m, vt_bits, k, words, chunks,
+                                                                                panel_rowmap(), product_store_mode(), pg,
                                                                                 pd_bits);
     BMF_LAUNCH_CHECK("bmf_bool_product");
     return 0;
@@ -1915,21 +1955,17 @@ static int launch_confusion(const uint64_t* gt_bits, const uint64_t* pd_bits, in
       const int panel_pairs = chunks * CH_PAIRS;
       const int depth = confusion_ring_depth(k, chunks);
       const size_t smem = confusion_panel_smem(k, chunks, depth);
-      const int64_t panels = ceil_div(words >> 1, panel_pairs);
-      int64_t splits = (int64_t)num_sms() / panels;              // one CTA per SM, ONE wave
       const int64_t max_splits = ceil_div(ceil_div(m, 32), PANEL_WARPS);
-      if (splits > max_splits) splits = max_splits;
-      if (splits < 1) splits = 1;
-      if (splits > 65535) splits = 65535;
-      dim3 grid((unsigned)panels, (unsigned)splits);
+      int ctas = 0;
+      const PanelGrid pg = make_panel_grid(words >> 1, panel_pairs, max_splits, &ctas);
       const int mode = confusion_count_mode();
 #define BMF_CONF_LAUNCH(CG, MD)                                                                                      \
   do {                                                                                                               \
     rc = check_cuda(cudaFuncSetAttribute(confusion_panel_kernel<CG, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem), who);                                                           \
     if (rc) return rc;                                                                                               \
-    confusion_panel_kernel<CG, MD><<<grid, PANEL_THREADS, smem, st>>>(gt_bits, m, words, u_words, vt_bits, k, chunks,  \
-                                                                      depth, c);                                     \
+    confusion_panel_kernel<CG, MD><<<ctas, PANEL_THREADS, smem, st>>>(gt_bits, m, words, u_words, vt_bits, k, chunks,  \
+                                                                      depth, pg, c);                                 \
   } while (0)
       if (gt_ones >= 0) {
         if (mode == 0) BMF_CONF_LAUNCH(false, 0); else if (mode == 1) BMF_CONF_LAUNCH(false, 1); else BMF_CONF_LAUNCH(false, 2);
