@@ -952,13 +952,11 @@ __device__ __forceinline__ void csa64(uint64_t& h, uint64_t& l, uint64_t a, uint
 }
 // V^T panel -> shared memory: Vs[l][p] (pairs), zero beyond the matrix
 __device__ __forceinline__ void load_vt_panel(ulonglong2* Vs, const uint64_t* __restrict__ vt, int64_t k,
-                                              int64_t words, int64_t pair0, int panel_pairs) {
-  const int64_t pairs = words >> 1;
+                                              int64_t words, int64_t pair0, int panel_pairs, int valid_pairs) {
   const int total = (int)k * panel_pairs;
   for (int e = threadIdx.x; e < total; e += blockDim.x) {
     const int l = e / panel_pairs, p = e - l * panel_pairs;
-    const int64_t gp = pair0 + p;
-    Vs[e] = gp < pairs ? ld_words2(vt + (int64_t)l * words + 2 * gp) : make_ulonglong2(0ull, 0ull);
+    Vs[e] = p < valid_pairs ? ld_words2(vt + (int64_t)l * words + 2 * (pair0 + p)) : make_ulonglong2(0ull, 0ull);
   }
   __syncthreads();
 }
@@ -1046,19 +1044,20 @@ __device__ __forceinline__ void panel_or_fast(const ulonglong2* Vs, int panel_pa
   }
 }
 
-// CTA -> (column panel, row split) for the panel kernels.  A row is ceil(pairs / panel_pairs) panels wide and the LAST
-// panel is usually narrower (n = 100 000 bits: six 2 KB panels and one of 224 bytes).  With a panels x splits grid the CTAs
-// of that last panel did 11 % of the others' work and then idled -- 21 of 147 SMs, which is why these kernels sat at 0.8 of
-// the copy peak whatever else was tuned.  The 1-D grid gives every panel a number of row splits proportional to its width.
+// CTA -> (column panel, row split) for the panel kernels.  A row is ceil(pairs / panel_pairs) panels wide; cutting it into
+// panels of the FULL width leaves a narrow last one (n = 100 000 bits: six 2 KB panels and one of 224 bytes) whose CTAs
+// spend the same per-row instruction overhead on a ninth of the bytes -- 21 of 147 SMs moved 1.8 % of the data.  The row
+// is therefore cut into panels of EQUAL width (782 pairs -> 7 x 112): every CTA carries the same useful bytes per row.
 struct PanelGrid {
-  int full_panels;      // panels of full width
-  int splits_full;      // row splits (CTAs) per full panel
-  int splits_last;      // row splits of the narrower last panel (0 = there is none)
+  int panels;           // column panels per row
+  int splits;           // row splits (CTAs) per panel
+  int width_pairs;      // pairs per panel (<= the shared-memory panel width)
 };
 __device__ __forceinline__ void panel_coords(const PanelGrid& g, int& panel, int& split, int& nsplit) {
-  const int b = (int)blockIdx.x, nfull = g.full_panels * g.splits_full;
-  if (b < nfull) { panel = b / g.splits_full; split = b - panel * g.splits_full; nsplit = g.splits_full; }
-  else { panel = g.full_panels; split = b - nfull; nsplit = g.splits_last; }
+  const int b = (int)blockIdx.x;
+  split = b / g.panels;                                    // panel fastest: neighbouring CTAs write neighbouring columns
+  panel = b - split * g.panels;
+  nsplit = g.splits;
 }
 
 // Row order (ROWMAP): 0 = every warp owns blocks of 32 CONSECUTIVE rows (one coalesced load of the usage words);
@@ -1089,8 +1088,8 @@ confusion_panel_kernel(const uint64_t* __restrict__ gt, int64_t m, int64_t words
   const uint32_t ring0 = smem_u32(ring);
 
   const int64_t pairs = words >> 1;
-  const int64_t pair0 = (int64_t)pg_panel * panel_pairs;
-  const int valid_pairs = (int)((pairs - pair0) < panel_pairs ? (pairs - pair0) : panel_pairs);
+  const int64_t pair0 = (int64_t)pg_panel * pg.width_pairs;
+  const int valid_pairs = (int)((pairs - pair0) < pg.width_pairs ? (pairs - pair0) : pg.width_pairs);
   const uint32_t seg_bytes = (uint32_t)valid_pairs * 16u;
   const int nch = (valid_pairs + CH_PAIRS - 1) / CH_PAIRS;  // chunks this panel really has
   if (lane == 0) {
@@ -1102,7 +1101,7 @@ confusion_panel_kernel(const uint64_t* __restrict__ gt, int64_t m, int64_t words
   for (int e = lane; e < RING_DEPTH * panel_pairs; e += 32)
     reinterpret_cast<ulonglong2*>(ring)[e] = make_ulonglong2(0ull, 0ull);
   fence_proxy_async();
-  load_vt_panel(Vs, vt, k, words, pair0, panel_pairs);     // ends with __syncthreads()
+  load_vt_panel(Vs, vt, k, words, pair0, panel_pairs, valid_pairs);     // ends with __syncthreads()
 
   // this warp's rows: 32-row blocks gw, gw + nwarps, ...
   const int64_t gw = (int64_t)pg_split * PANEL_WARPS + warp;
@@ -1204,8 +1203,9 @@ bool_product_panel_kernel(const uint64_t* __restrict__ u_words, int64_t m, const
   const int64_t pairs = words >> 1;
   int pg_panel, pg_split, pg_nsplit;
   panel_coords(pg, pg_panel, pg_split, pg_nsplit);
-  const int64_t pair0 = (int64_t)pg_panel * panel_pairs;
-  load_vt_panel(Vs, vt, k, words, pair0, panel_pairs);
+  const int64_t pair0 = (int64_t)pg_panel * pg.width_pairs;
+  const int valid_pairs = (int)((pairs - pair0) < pg.width_pairs ? (pairs - pair0) : pg.width_pairs);
+  load_vt_panel(Vs, vt, k, words, pair0, panel_pairs, valid_pairs);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   // block index space: rowmap 0 -> 32-row blocks, one per warp and pass; rowmap 1 -> super-blocks, one per CTA and pass
@@ -1227,13 +1227,13 @@ bool_product_panel_kernel(const uint64_t* __restrict__ u_words, int64_t m, const
       uint64_t* out = pd + row * words;
       for (int c = 0; c < panel_chunks; ++c) {
         const int slot0 = c * CH_PAIRS + lane;
-        if (pair0 + c * CH_PAIRS >= pairs) break;
+        if (c * CH_PAIRS >= valid_pairs) break;
         ulonglong2 d[4];
         panel_or1(Vs, panel_pairs, sel, slot0, d);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int64_t gp = pair0 + slot0 + 32 * u;
-          if (gp < pairs) {
+          if (slot0 + 32 * u < valid_pairs) {
             ulonglong2* dst = reinterpret_cast<ulonglong2*>(out) + gp;
             if (store_mode == 0) __stcs(dst, d[u]);
             else if (store_mode == 1) *dst = d[u];
@@ -1263,29 +1263,19 @@ static inline int confusion_ring_depth(int64_t k, int chunks) {
 static inline size_t confusion_panel_smem(int64_t k, int chunks, int depth) {
   return (size_t)(k + PANEL_WARPS * depth) * chunks * CH_PAIRS * 16 + PANEL_WARPS * RING_DEPTH_MAX * 8;
 }
-// every panel gets row splits in proportion to its width; the whole grid is ONE wave (<= #SM CTAs)
+// equal-width panels, one wave of CTAs (<= #SM); BMF_PANEL_BALANCE=0 restores full-width panels + a narrow last one
 static inline PanelGrid make_panel_grid(int64_t pairs, int panel_pairs, int64_t max_splits, int* total_ctas) {
   const int64_t panels = ceil_div(pairs, panel_pairs);
-  const int64_t last_pairs = pairs - (panels - 1) * panel_pairs;
-  PanelGrid g;
   const char* e = getenv("BMF_PANEL_BALANCE");
   const bool balance = !(e != nullptr && e[0] == '0');
-  if (last_pairs == panel_pairs || !balance) {                       // all panels equally wide (or the round-1 grid)
-    int64_t splits = (int64_t)num_sms() / panels;
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-    g.full_panels = (int)panels; g.splits_full = (int)splits; g.splits_last = 0;
-  } else {
-    const double frac = (double)last_pairs / (double)panel_pairs;
-    int64_t sf = (int64_t)((double)num_sms() / ((double)(panels - 1) + frac));
-    if (sf > max_splits) sf = max_splits;
-    if (sf < 1) sf = 1;
-    int64_t sl = (int64_t)(frac * (double)sf + 0.5);
-    if (sl < 1) sl = 1;
-    while ((panels - 1) * sf + sl > (int64_t)num_sms() && sf > 1) { --sf; sl = (int64_t)(frac * (double)sf + 0.5); if (sl < 1) sl = 1; }
-    g.full_panels = (int)(panels - 1); g.splits_full = (int)sf; g.splits_last = (int)sl;
-  }
-  *total_ctas = g.full_panels * g.splits_full + g.splits_last;
+  int64_t splits = (int64_t)num_sms() / panels;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  PanelGrid g;
+  g.panels = (int)panels;
+  g.splits = (int)splits;
+  g.width_pairs = balance ? (int)ceil_div(pairs, panels) : panel_pairs;
+  *total_ctas = g.panels * g.splits;
   return g;
 }
 static inline int panel_rowmap() {              // BMF_PANEL_ROWMAP=1 selects the interleaved row order (A/B experiments)
