@@ -1,10 +1,14 @@
-"""Device-resident state of one Asso fit: bit-packed X and cover, candidate basis, int8 operand
-planes, and the per-step launch sequence  score-all -> (all-reduce) -> argmax -> apply.
+"""Device-resident state of one Asso fit: bit-packed X and cover, candidate basis, packed-E2M1 / int8 operand
+planes, and the greedy loop as ONE enqueued sequence  select -> apply (+ compaction) -> re-score -> all-reduce  per step
+(`enqueue_steps`; the step-wise `score_all` / `select_and_apply` pair remains for callers that want every step).
+
+After the first full scoring pass only the rows a winner changed are re-scored (`rescore='incremental'`, exact);
+`rescore='full'` runs a whole contraction per step.
 
 Rows of X are sharded across ranks when torch.distributed is initialised (one process per
 GPU); the candidate basis, V and the greedy decisions are replicated.  Integer partial
-gains are summed with ONE all-reduce per greedy step, so every rank sees identical
-totals and takes the identical lowest-index strict argmax.
+gains (and the step's three counters, in the tail of the same buffer) are summed with ONE all-reduce per greedy step,
+so every rank sees identical totals and takes the identical lowest-index strict argmax.
 """
 from __future__ import annotations
 
@@ -233,8 +237,8 @@ class CoverEngine:
     # ---- association + basis (Asso.py:191-235) -------------------------------------------------
     def build_basis(self, tau: float, prescore: bool = False):
         """Association + basis (+ operand planes).  prescore=True also enqueues the first greedy step's scoring pass
-        before the host-side stored-zero scan, so that the scan (0.09 s for 1e8 values) hides behind ~80 ms of GPU
-        work; the caller must then skip its first score_all() (`self.prescored`)."""
+        before the host-side stored-zero scan, so that the scan (35 ms for 1e8 values on 8 threads) hides behind the
+        first full pass (35 ms at c4); the caller must then skip its own first pass (`self.prescored`)."""
         self._build_basis(tau)                                 # enqueued, not waited for
         if prescore:
             self.score_all()
