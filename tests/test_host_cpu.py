@@ -211,6 +211,40 @@ for step in range(3):
     B = np.delete(B, j, axis=0)
 ref = O.asso_fit(X, 3, 0.4, 0.5)
 assert np.array_equal(U, ref["U"]) and np.array_equal(V, ref["V"])
+
+# round 2: (a) the association exchange -- partial counts -> row blocks -> every rank thresholds ITS block -> all-gather
+# (gloo has no reduce-scatter: the block is taken from the all-reduced sum; NCCL does reduce_scatter_tensor)
+n = X.shape[1]
+per = -(-n // world)
+cnt_blk = cnt.numpy()[rank * per:min(n, (rank + 1) * per)]
+s_blk = np.diag(cnt.numpy())[rank * per:min(n, (rank + 1) * per)].astype(np.float64)
+rows_blk = np.zeros((per, n), np.uint8)
+nzr = s_blk > 0
+rows_blk[:len(s_blk)][nzr] = (cnt_blk[nzr].astype(np.float64) / s_blk[nzr][:, None] > 0.4)
+gathered = [torch.zeros((per, n), dtype=torch.uint8) for _ in range(world)]
+dist.all_gather(gathered, torch.from_numpy(rows_blk))
+B_all = torch.cat(gathered).numpy()[:n]
+B_ref = (O.build_assoc(X) > 0.4).astype(np.uint8)
+assert np.array_equal(B_all, B_ref)
+
+# (b) the product's own exchange routine on CPU tensors: gains and the step's three counters travel in ONE buffer
+from pybmf_b200.engine import CoverEngine
+eng = CoverEngine.__new__(CoverEngine)
+cp = 8
+eng.world = world
+eng.gbuf = torch.arange(2 * cp + 8, dtype=torch.int64) * (rank + 1)
+eng.gred = torch.zeros(2 * cp + 8, dtype=torch.int64)
+eng.tail, eng.tail_red = eng.gbuf[cp:cp + 8], eng.gred[cp:cp + 8]
+for red_len in (cp + 8, 2 * cp + 8):                       # integer mode / general mode
+    eng.red_len = red_len
+    eng.gred.zero_()
+    eng._reduce_gains()
+    want = torch.arange(2 * cp + 8, dtype=torch.int64) * sum(r + 1 for r in range(world))
+    assert torch.equal(eng.gred[:red_len], want[:red_len]) and int(eng.gred[red_len:].abs().sum()) == 0
+    assert torch.equal(eng.gbuf, torch.arange(2 * cp + 8, dtype=torch.int64) * (rank + 1))      # local sums untouched
+eng.gred.zero_()
+eng._reduce_gains(tail_only=True)
+assert torch.equal(eng.tail_red, want[cp:cp + 8]) and int(eng.gred[:cp].abs().sum()) == 0
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
