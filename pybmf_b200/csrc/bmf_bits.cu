@@ -1175,7 +1175,8 @@ confusion_panel_kernel(const uint64_t* __restrict__ gt, int64_t m, int64_t words
         second = !second;
       }
       __syncwarp();                                         // every lane has consumed the slot
-      if (lane == 0 && to_issue > 0) issue();               // refill it with the row RING_DEPTH ahead
+      if (lane == 0 && to_issue > 0) issue();               // refill it with the row RING_DEPTH ahead (a converged-warp
+                                                            // elect_one issue was measured: no change, 2.352 vs 2.334 ms)
       if (++slot == RING_DEPTH) { slot = 0; phase ^= 1u; }
     }
   }

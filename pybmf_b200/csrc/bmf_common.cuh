@@ -87,6 +87,20 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// One elected lane of a CONVERGED warp (elect.sync).  Warps that issue TMA / tcgen05 / bulk-copy instructions run their
+// loops with the whole warp so that every operand is warp-uniform and lives in uniform registers; issuing from inside an
+// `if (lane == 0)` region instead makes the compiler wrap every such instruction in an ELECT + R2UR.BROADCAST loop (7
+// moves per MMA, 4 per bulk copy), which made the ISSUER the bottleneck of the FP4 GEMM (150 instead of 128 cycles per
+// kind::mxf4 instruction).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ uint64_t warp_uniform64(uint64_t v) {
+  return ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(v >> 32), 0) << 32) | __shfl_sync(0xffffffffu, (uint32_t)v, 0);
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // The reference's row test (PyBMF/models/Asso.py:181 on top of PyBMF/utils/metrics.py:201):

@@ -85,17 +85,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
-// One elected lane of a CONVERGED warp (elect.sync).  The MMA issuer runs its loop with the whole warp so that every
-// operand of tcgen05.mma / tcgen05.commit is warp-uniform and lives in uniform registers; issuing from inside an
-// `if (lane == 0)` region instead makes the compiler wrap every instruction in an ELECT + R2UR.BROADCAST loop (7
-// moves per MMA), which made the ISSUER the bottleneck: 150 instead of 128 cycles per kind::mxf4 instruction.
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
-
+// elect_one() / warp_uniform(): see bmf_common.cuh (issue discipline of the producer and MMA warps)
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
