@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY -- config-level fixtures for BASELINE configs c2 / c3 / c4 at FULL size.
 
-    python oracle/make_digests.py c2 c3          # seconds
+    python oracle/make_digests.py c2 c3 c2w02    # seconds (c2w02 = c2 with w_fp = 0.2: the general-weights path)
     python oracle/make_digests.py c4 [threads]   # ~1 h on 8 host cores (20 full greedy steps, 8.5e9 pairs each)
 
 Runs the bit-packed C restatement (oracle/asso_c.c through oracle/asso_oracle_c.py, pinned against the numpy
@@ -67,6 +67,10 @@ def main():
                   "made_by": "oracle/make_digests.py (AssoIter on the c2 digest's factors)"}
             json.dump(d3, open(os.path.join(OUT, "c3_digest.json"), "w"), indent=1)
             print("c3: %d column passes, %d accepted, %.1fs" % (len(it["trace"]), len(it["scores"]), time.time() - t0))
+    if "c2w02" in which:                                   # general (non-dyadic) weights at the full c2 size
+        X = synth.config_c2()
+        d, _r = fit_digest("c2w02", X, 20, 0.5, 0.2, threads)
+        json.dump(d, open(os.path.join(OUT, "c2w02_digest.json"), "w"), indent=1)
     if "c4" in which:
         X = synth.config_c4()
         d, _r = fit_digest("c4", X, 20, 0.5, 0.5, threads)

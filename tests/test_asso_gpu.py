@@ -287,6 +287,22 @@ def test_c2_k20_matches_oracle_digest(M, scorer, rescore):
     assert result_digest(mdl)["u_sha256"] == want["u_sha256"]
 
 
+@pytest.mark.parametrize("scorer,rescore", [("tcgen05", "auto"), ("tcgen05_f4", "full"), ("tcgen05_i8", "incremental"),
+                                            ("tcgen05_i8", "full"), ("popc", "full")])
+def test_c2_k20_general_weights_match_oracle_digest(M, scorer, rescore):
+    """The same full-size config with NON-DYADIC weights (w_fp = 0.2, the reference notebooks' choice): the general-weights
+    path (P/Q planes, fp64 row test in the epilogue, incremental sum_use P / sum_use N) against the C restatement's fixture.
+    The winner ORDER differs from the w = 0.5 fit (57, 20, 9, ... instead of 57, 9, 20, ...), so this is not a re-run of it."""
+    from pybmf_b200 import synth
+    from pybmf_b200.digest import DIGEST_KEYS, result_digest
+    want = _load_digest("c2w02")
+    mdl = M.Asso(tau=0.5, k=20, w_fp=0.2, scorer=scorer, rescore=rescore)
+    mdl.fit(synth.config_c2(), **FIT_KW)
+    got = result_digest(mdl)
+    for key in DIGEST_KEYS:
+        assert got[key] == want[key], key
+
+
 def test_c2_k20_log_rows_match_numpy_oracle(M):
     """Every logged column of the 20 steps (incl. the float rates) against the numpy restatement."""
     from pybmf_b200 import synth

@@ -146,6 +146,26 @@ def test_c2_fixture_is_reproduced_and_agrees_with_numpy_restatement():
     assert np.array_equal(U[:, :2], w["U"]) and [l["score"] for l in w["logs"]] == [s["score"] for s in r["steps"][:2]]
 
 
+def test_c2_general_weights_fixture_is_reproduced():
+    """tests/golden/c2w02_digest.json (w_fp = 0.2): what the C restatement computes today; the first factors equal the numpy
+    restatement's (whose per-row float sums may differ from the integer-total score in the last ulps, never in U / V here)."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from oracle import asso_oracle_c as OC
+    from pybmf_b200 import synth
+    X = synth.config_c2()
+    want = json.load(open(os.path.join(GOLDEN, "c2w02_digest.json")))
+    r = OC.asso_fit(X, 20, 0.5, 0.2)
+    for key in ("winners", "score_bits", "used", "tp", "fp", "u_sha256", "v_sha256"):
+        assert r["digest"][key] == want[key], key
+    assert want["winners"][:3] == [57, 20, 9]
+    w = O.asso_fit(X, 2, 0.5, 0.2)
+    U = np.stack(r["U_cols"], 1)
+    assert np.array_equal(U[:, :2], w["U"])
+    np.testing.assert_allclose([l["score"] for l in w["logs"]], [s["score"] for s in r["steps"][:2]], rtol=1e-12, atol=0)
+
+
 def test_c4_fixture_is_self_consistent():
     """tests/golden/c4_digest.json (480189 x 17770, k = 20; 40 min of host time to regenerate): structural checks."""
     import json
