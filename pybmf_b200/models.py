@@ -608,21 +608,27 @@ class Asso(BaseModel):
         key = (name, self.task)
         if key not in cache:
             Xl = device.csr_rows_view(X, dev.r0, dev.r1)
-            ones = Xl.copy()
-            ones.eliminate_zeros()
+            # the common case stores no explicit zeros: then the stored pattern IS the set of ones (no 1e8-entry copies)
+            dirty = device.has_stored_zeros(Xl)
+            ones = Xl
+            if dirty:
+                ones = Xl.copy()
+                ones.eliminate_zeros()
             entry = {"ones": U_._bits_on_device(ones) if dev.m_loc > 0 else None, "n_ones": int(ones.nnz)}
             if self.task == "prediction":
-                zeros = Xl.copy()
-                zeros.data = (zeros.data == 0).astype(np.int8)
-                zeros.eliminate_zeros()
-                entry["zeros"] = U_._bits_on_device(zeros) if dev.m_loc > 0 else None
+                entry["zeros"] = None
+                if dirty:
+                    zeros = Xl.copy()
+                    zeros.data = (zeros.data == 0).astype(np.int8)
+                    zeros.eliminate_zeros()
+                    entry["zeros"] = U_._bits_on_device(zeros) if dev.m_loc > 0 else None
                 entry["n_stored"] = int(Xl.nnz)
             cache[key] = entry
         e = cache[key]
         counts = device.zeros((6,), torch.int64)
         if dev.m_loc > 0:
             _native.call("bmf_confusion_bits", e["ones"], dev.c_bits, dev.m_loc, dev.words, e["n_ones"], counts[:3], None, None)
-            if self.task == "prediction":
+            if self.task == "prediction" and e["zeros"] is not None:
                 _native.call("bmf_confusion_bits", e["zeros"], dev.c_bits, dev.m_loc, dev.words, -1, counts[3:], None, None)
         stored = torch.tensor([e.get("n_stored", 0)], dtype=torch.int64, device=counts.device)
         both = torch.cat([counts, stored])
