@@ -79,6 +79,17 @@ for rescore in ("auto", "full"):
     got = result_digest(mdl)
     for key in DIGEST_KEYS:
         assert got[key] == want[key], (key, rescore, rank)
+# an input generated ON the devices (every rank only its own rows) against the same matrix fitted from a host csr
+from pybmf_b200 import generate
+Xd = generate.planted_bits(5000, 1500, 12, 0.08, 0.08, 0.1, 0.01, seed=77)                       # this rank's rows
+Xfull = generate.planted_bits(5000, 1500, 12, 0.08, 0.08, 0.1, 0.01, seed=77, rank=0, world=1).to_csr()
+a = models.Asso(tau=0.45, k=6, w_fp=0.5)
+a.fit(Xd, **KW)
+b = models.Asso(tau=0.45, k=6, w_fp=0.5)
+b.fit(Xfull, **KW)
+da, db = result_digest(a), result_digest(b)
+for key in DIGEST_KEYS:
+    assert da[key] == db[key], (key, rank)
 dist.barrier()
 dist.destroy_process_group()
 print("rank %d of %d ok" % (rank, world))
