@@ -184,7 +184,7 @@ def stager(world: int = 1):
             cores = len(os.sched_getaffinity(0))
         except AttributeError:
             pass
-        _STAGER = _Stager(max(1, min(8, cores // (2 * max(world, 1)))))
+        _STAGER = _Stager(max(1, min(8, cores // max(world, 1))))      # the ranks of one box share its cores
     return _STAGER
 
 

@@ -751,9 +751,9 @@ class CoverEngine:
         wmax = device.words_for(self.plan.rows(0)[1] - self.plan.rows(0)[0])
         padded = device.zeros((len(ids), wmax), torch.int64)
         padded[:, : local.shape[1]] = local
-        parts = [torch.empty_like(padded) for _ in range(self.world)]
-        dist.all_gather(parts, padded)
-        both = torch.stack(parts).cpu().numpy()                                  # one D2H
+        gathered = device.empty((self.world, len(ids), wmax), torch.int64)
+        dist.all_gather_into_tensor(gathered, padded)
+        both = gathered.cpu().numpy()                                            # one D2H
         return [(both[r], self.plan.rows(r)[1] - self.plan.rows(r)[0]) for r in range(self.world)]
 
     @staticmethod
