@@ -533,7 +533,10 @@ class Asso(BaseModel):
         n_basis = self._dev_nb
         stepwise = (self.X_val is not None or self.X_test is not None
                     or os.environ.get("BMF_FIT_TRACE_STEPS", "0") == "1")
-        chunk = 1 if stepwise else (self.k if self.k is not None else 16)
+        # steps are enqueued speculatively in stretches; what the reference would not have run (after D2 / D1) is wasted
+        # work, so a stretch is short when a step is expensive (a full scoring pass) and long when it is cheap
+        stretch = 32 if dev.rescore == "incremental" else 8
+        chunk = 1 if stepwise else min(self.k if self.k is not None else stretch, stretch)
         k = 0                                                 # next greedy step to book (the reference's `k`)
         enq = 0                                               # steps enqueued so far
         table = None
