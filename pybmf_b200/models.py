@@ -703,10 +703,17 @@ class AssoIter(Asso):
         with_splits = self.X_val is not None or self.X_test is not None
 
         def write_back():                                       # usage words -> the lil U the caller holds (in place: D7)
-            cols = uw.cpu().numpy()
-            for c in range(kU):
-                col = ((cols[:, c // 64] >> (c % 64)) & 1).astype(np.uint8)
-                self.U[:, c] = _column(col, m)
+            # The reference assigns U[:, k] column by column on the SAME lil object the source model holds (AssoIter.py:28,
+            # 60); here all columns are rebuilt from the usage words at once and the object's row lists are replaced in
+            # place (a lil column assignment walks every row: 0.3 ms per column at 6040 rows).
+            dense = device.words_to_dense(uw.cpu().numpy(), kU)                   # [m, kU] uint8
+            new = _csr_to_lil_fast(csr_matrix(dense, dtype=self.U.dtype))
+            if sp.isspmatrix_lil(self.U) and self.U.shape == new.shape:
+                self.U.rows[:] = new.rows
+                self.U.data[:] = new.data
+            else:
+                for c in range(kU):
+                    self.U[:, c] = _column(dense[:, c], m)
             self.__dict__.pop("X_pd", None)
 
         def sweep(upto):
