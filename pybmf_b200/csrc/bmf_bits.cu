@@ -1044,6 +1044,107 @@ __device__ __forceinline__ void panel_or_fast(const ulonglong2* Vs, int panel_pa
   }
 }
 
+// ---- selection lists ---------------------------------------------------------------------------------
+// Scanning a usage word bit by bit (ffs, clear lowest bit, address) costs ~15 integer instructions per selected V^T row
+// on the ALU pipe, which is what bounds the panel kernels (ncu: ALU 74 %, DRAM 62 %).  The scan is therefore done ONCE
+// per row by the lane that loaded the word -- 32 rows in parallel -- into a packed list: the indices of the set bits in
+// bytes 0..6, their number in byte 7 (0xff = more than seven: the row takes the bit-scan path).  The row loop then
+// broadcasts the list and runs straight-line code: all selected rows are loaded before the first OR (independent
+// shared-memory loads instead of a load -> OR -> load chain) and three rows are combined per LOP3.
+__device__ __forceinline__ uint64_t pack_selection(uint64_t u) {
+  const int c = __popcll(u);
+  if (c > 7) return ~0ull;
+  uint64_t p = (uint64_t)c << 56;
+  for (int s = 0; u != 0; s += 8) {
+    p |= (uint64_t)(__ffsll((long long)u) - 1) << s;
+    u &= u - 1;
+  }
+  return p;
+}
+__device__ __forceinline__ ulonglong2 or2(const ulonglong2 a, const ulonglong2 b) {
+  return make_ulonglong2(a.x | b.x, a.y | b.y);
+}
+__device__ __forceinline__ ulonglong2 or3(const ulonglong2 a, const ulonglong2 b, const ulonglong2 c) {
+  return make_ulonglong2(a.x | b.x | c.x, a.y | b.y | c.y);
+}
+// d = OR of the cnt (1..7) V^T rows named by the list bytes (lo = bytes 0..3, hi = bytes 4..6), at the lane's four pair slots
+__device__ __forceinline__ void panel_or_list(const ulonglong2* Vs, int panel_pairs, uint32_t lo, uint32_t hi, int cnt,
+                                              int slot0, ulonglong2 (&d)[4]) {
+  const ulonglong2* base = Vs + slot0;
+  const ulonglong2* r0 = base + __byte_perm(lo, 0u, 0x4440u) * panel_pairs;
+  if (cnt == 1) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) d[u] = r0[32 * u];
+    return;
+  }
+  const ulonglong2* r1 = base + __byte_perm(lo, 0u, 0x4441u) * panel_pairs;
+  if (cnt == 2) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) d[u] = or2(r0[32 * u], r1[32 * u]);
+    return;
+  }
+  const ulonglong2* r2 = base + __byte_perm(lo, 0u, 0x4442u) * panel_pairs;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) d[u] = or3(r0[32 * u], r1[32 * u], r2[32 * u]);
+  if (cnt == 3) return;
+  const ulonglong2* r3 = base + (lo >> 24) * panel_pairs;
+  if (cnt == 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) d[u] = or2(d[u], r3[32 * u]);
+    return;
+  }
+  const ulonglong2* r4 = base + __byte_perm(hi, 0u, 0x4440u) * panel_pairs;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) d[u] = or3(d[u], r3[32 * u], r4[32 * u]);
+  if (cnt == 5) return;
+  const ulonglong2* r5 = base + __byte_perm(hi, 0u, 0x4441u) * panel_pairs;
+  if (cnt == 6) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) d[u] = or2(d[u], r5[32 * u]);
+    return;
+  }
+  const ulonglong2* r6 = base + __byte_perm(hi, 0u, 0x4442u) * panel_pairs;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) d[u] = or3(d[u], r5[32 * u], r6[32 * u]);
+}
+// |V^T row l| inside this CTA's column panel, l < k: the prediction of a data row that uses ONE factor has exactly that
+// many ones, so such rows (27 % at two factors per row on average) need no popcount of the prediction at all
+__device__ __forceinline__ void panel_row_counts(const ulonglong2* Vs, int panel_pairs, int k, int* pop_v) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int l = warp; l < k; l += nw) {
+    int c = 0;
+    for (int p = lane; p < panel_pairs; p += 32) c += __popcll(Vs[l * panel_pairs + p].x) + __popcll(Vs[l * panel_pairs + p].y);
+    c = warp_sum(c);
+    if (lane == 0) pop_v[l] = c;
+  }
+  __syncthreads();
+}
+
+// four words -> one "fours" carry; two of them make an "eights" word (the half-width tree of count mode 3)
+struct HarleySeal4 {
+  uint64_t ones = 0, twos = 0, fours = 0, pend = 0;
+  int eights = 0;
+  __device__ __forceinline__ uint64_t fold4(uint64_t a, uint64_t b, uint64_t c, uint64_t d) {
+    uint64_t t2a, t2b, t4;
+    csa64(t2a, ones, ones, a, b);
+    csa64(t2b, ones, ones, c, d);
+    csa64(t4, twos, twos, t2a, t2b);
+    return t4;
+  }
+  __device__ __forceinline__ void add4(bool second, uint64_t a, uint64_t b, uint64_t c, uint64_t d) {
+    const uint64_t t4 = fold4(a, b, c, d);
+    if (!second) { pend = t4; return; }
+    uint64_t t8;
+    csa64(t8, fours, fours, pend, t4);
+    pend = 0;
+    eights += __popcll(t8);
+  }
+  __device__ __forceinline__ long long total() const {
+    return 8 * (long long)eights + 4 * (long long)(__popcll(fours) + __popcll(pend)) + 2 * (long long)__popcll(twos) +
+           (long long)__popcll(ones);
+  }
+};
+
 // CTA -> (column panel, row split) for the panel kernels.  A row is ceil(pairs / panel_pairs) panels wide; cutting it into
 // panels of the FULL width leaves a narrow last one (n = 100 000 bits: six 2 KB panels and one of 224 bytes) whose CTAs
 // spend the same per-row instruction overhead on a ninth of the bytes -- 21 of 147 SMs moved 1.8 % of the data.  The row
@@ -1246,6 +1347,209 @@ bool_product_panel_kernel(const uint64_t* __restrict__ u_words, int64_t m, const
   }
 }
 
+// The selection-list forms of the two panel kernels (see pack_selection above): same grid, same ring, same results.
+template <bool COUNT_GT, int MODE>
+__global__ void __launch_bounds__(PANEL_THREADS, 1)
+confusion_panel_list_kernel(const uint64_t* __restrict__ gt, int64_t m, int64_t words,
+                            const uint64_t* __restrict__ u_words, const uint64_t* __restrict__ vt, int64_t k,
+                            int panel_chunks, int RING_DEPTH, const PanelGrid pg, unsigned long long* __restrict__ counts) {
+  extern __shared__ __align__(128) uint8_t panel_smem[];
+  const int panel_pairs = panel_chunks * CH_PAIRS;
+  const int row_bytes = panel_pairs * 16;
+  int pg_panel, pg_split, pg_nsplit;
+  panel_coords(pg, pg_panel, pg_split, pg_nsplit);
+  ulonglong2* Vs = reinterpret_cast<ulonglong2*>(panel_smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* ring = panel_smem + (size_t)k * row_bytes + (size_t)warp * RING_DEPTH * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(panel_smem + (size_t)(k + PANEL_WARPS * RING_DEPTH) * row_bytes);
+  int* pop_v = reinterpret_cast<int*>(bars + PANEL_WARPS * RING_DEPTH_MAX);
+  const uint32_t bar0 = smem_u32(bars + warp * RING_DEPTH);
+  const uint32_t ring0 = smem_u32(ring);
+
+  const int64_t pairs = words >> 1;
+  const int64_t pair0 = (int64_t)pg_panel * pg.width_pairs;
+  const int valid_pairs = (int)((pairs - pair0) < pg.width_pairs ? (pairs - pair0) : pg.width_pairs);
+  const uint32_t seg_bytes = (uint32_t)valid_pairs * 16u;
+  const int nch = (valid_pairs + CH_PAIRS - 1) / CH_PAIRS;
+  if (lane == 0) {
+    for (int s = 0; s < RING_DEPTH; ++s) mbar_init(bar0 + 8u * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int e = lane; e < RING_DEPTH * panel_pairs; e += 32)       // slot tails stay zero: no column predicates below
+    reinterpret_cast<ulonglong2*>(ring)[e] = make_ulonglong2(0ull, 0ull);
+  fence_proxy_async();
+  load_vt_panel(Vs, vt, k, words, pair0, panel_pairs, valid_pairs);
+  panel_row_counts(Vs, panel_pairs, (int)k, pop_v);
+
+  const int64_t gw = (int64_t)pg_split * PANEL_WARPS + warp;
+  const int64_t nwarps = (int64_t)pg_nsplit * PANEL_WARPS;
+  const int64_t blocks_total = (m + 31) >> 5;
+  int my_blocks = 0, last_rows = 0;
+  if (gw < blocks_total) {
+    my_blocks = (int)((blocks_total - 1 - gw) / nwarps) + 1;
+    const int64_t last_block = gw + (int64_t)(my_blocks - 1) * nwarps;
+    last_rows = (int)((m - last_block * 32) < 32 ? (m - last_block * 32) : 32);
+  }
+  int to_issue = my_blocks > 0 ? (my_blocks - 1) * 32 + last_rows : 0;
+  const uint64_t* iss_ptr = gt + 2 * pair0 + gw * 32 * words;
+  const int64_t step_block = (nwarps * 32 - 31) * words;
+  int iss_r = 0, iss_slot = 0;
+  auto issue = [&]() {
+    mbar_expect_tx(bar0 + 8u * iss_slot, seg_bytes);
+    bulk_load(ring0 + (uint32_t)(iss_slot * row_bytes), iss_ptr, seg_bytes, bar0 + 8u * iss_slot);
+    iss_slot = iss_slot == RING_DEPTH - 1 ? 0 : iss_slot + 1;
+    if (++iss_r == 32) { iss_r = 0; iss_ptr += step_block; } else { iss_ptr += words; }
+    --to_issue;
+  };
+  if (lane == 0)
+    for (int d = 0; d < RING_DEPTH && to_issue > 0; ++d) issue();
+
+  HarleySeal8 hs_tp, hs_pd, hs_gt;
+  HarleySeal4 h4_tp;
+  bool sec_tp = false, sec_pd = false, sec_gt = false;
+  long long n_pd = 0, n_tp = 0;
+  int slot = 0;
+  uint32_t phase = 0;
+  const uint64_t kmask = k >= 64 ? ~0ull : ((1ull << k) - 1ull);
+  const uint64_t* u_ptr = u_words + gw * 32 + lane;
+  uint64_t u_next = (my_blocks > 0 && gw * 32 + lane < m) ? __ldg(u_ptr) : 0ull;
+  for (int blk = 0; blk < my_blocks; ++blk) {
+    const uint64_t u_cur = u_next & kmask;
+    u_ptr += nwarps * 32;
+    u_next = (blk + 1 < my_blocks && (gw + (int64_t)(blk + 1) * nwarps) * 32 + lane < m) ? __ldg(u_ptr) : 0ull;
+    const uint64_t list = pack_selection(u_cur);                 // this lane's row, scanned once
+    const uint32_t list_lo = (uint32_t)list, list_hi = (uint32_t)(list >> 32);
+    int blk_pd = (list_hi >> 24) == 1u ? pop_v[list_lo & 0xffu] : 0, blk_tp = 0;
+    const int nrows = blk + 1 < my_blocks ? 32 : last_rows;
+    for (int r = 0; r < nrows; ++r) {
+      const uint32_t lo = __shfl_sync(0xffffffffu, list_lo, r);
+      const uint32_t hi = __shfl_sync(0xffffffffu, list_hi, r);
+      const int cnt = (int)(hi >> 24);
+      const ulonglong2* seg = reinterpret_cast<const ulonglong2*>(ring + (size_t)slot * row_bytes);
+      mbar_wait(bar0 + 8u * slot, phase);
+      if (COUNT_GT || cnt != 0) {                                // a row that uses no factor predicts nothing
+        for (int c = 0; c < nch; ++c) {
+          const int slot0 = c * CH_PAIRS + lane;
+          ulonglong2 g[4], d[4];
+          uint64_t w[8];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) g[u] = seg[slot0 + 32 * u];
+          if (COUNT_GT) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { w[2 * u] = g[u].x; w[2 * u + 1] = g[u].y; }
+            if (!sec_gt) hs_gt.add8_first(w); else hs_gt.add8_second(w);
+            sec_gt = !sec_gt;
+          }
+          if (cnt != 0) {
+            if (cnt <= 7) {
+              panel_or_list(Vs, panel_pairs, lo, hi, cnt, slot0, d);
+            } else {
+              const uint64_t sel = ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(u_cur >> 32), r) << 32) |
+                                   __shfl_sync(0xffffffffu, (uint32_t)u_cur, r);
+              panel_or_fast(Vs, panel_pairs, sel, slot0, d);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { w[2 * u] = g[u].x & d[u].x; w[2 * u + 1] = g[u].y & d[u].y; }
+            if (MODE == 2) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) blk_tp += __popcll(w[u]);
+            } else if (MODE == 3) {
+              h4_tp.add4(sec_tp, w[0], w[2], w[4], w[6]);
+              blk_tp += __popcll(w[1]) + __popcll(w[3]) + __popcll(w[5]) + __popcll(w[7]);
+              sec_tp = !sec_tp;
+            } else {
+              if (!sec_tp) hs_tp.add8_first(w); else hs_tp.add8_second(w);
+              sec_tp = !sec_tp;
+            }
+            if (cnt != 1) {                                      // one factor: |prediction| came from pop_v
+              if (MODE == 0) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { w[2 * u] = d[u].x; w[2 * u + 1] = d[u].y; }
+                if (!sec_pd) hs_pd.add8_first(w); else hs_pd.add8_second(w);
+                sec_pd = !sec_pd;
+              } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) blk_pd += __popcll(d[u].x) + __popcll(d[u].y);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0 && to_issue > 0) issue();
+      if (++slot == RING_DEPTH) { slot = 0; phase ^= 1u; }
+    }
+    n_pd += blk_pd;
+    n_tp += blk_tp;
+  }
+  const long long t_tp = warp_sum_ll(n_tp + hs_tp.total() + h4_tp.total());
+  const long long t_pd = warp_sum_ll(n_pd + hs_pd.total());
+  const long long t_gt = COUNT_GT ? warp_sum_ll(hs_gt.total()) : 0;
+  if (lane == 0 && (t_pd | t_gt)) {
+    atomicAdd(counts + 0, (unsigned long long)t_tp);
+    atomicAdd(counts + 1, (unsigned long long)t_pd);
+    if (COUNT_GT) atomicAdd(counts + 2, (unsigned long long)t_gt);
+  }
+}
+
+__global__ void __launch_bounds__(PRODUCT_THREADS, 1)
+bool_product_panel_list_kernel(const uint64_t* __restrict__ u_words, int64_t m, const uint64_t* __restrict__ vt,
+                               int64_t k, int64_t words, int panel_chunks, int store_mode, const PanelGrid pg,
+                               uint64_t* __restrict__ pd) {
+  extern __shared__ __align__(128) uint8_t panel_smem[];
+  ulonglong2* Vs = reinterpret_cast<ulonglong2*>(panel_smem);
+  const int panel_pairs = panel_chunks * CH_PAIRS;
+  const int64_t pairs = words >> 1;
+  int pg_panel, pg_split, pg_nsplit;
+  panel_coords(pg, pg_panel, pg_split, pg_nsplit);
+  const int64_t pair0 = (int64_t)pg_panel * pg.width_pairs;
+  const int valid_pairs = (int)((pairs - pair0) < pg.width_pairs ? (pairs - pair0) : pg.width_pairs);
+  load_vt_panel(Vs, vt, k, words, pair0, panel_pairs, valid_pairs);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const uint64_t kmask = k >= 64 ? ~0ull : ((1ull << k) - 1ull);
+  const int64_t blk0 = (int64_t)pg_split * nw + warp, blk_step = (int64_t)pg_nsplit * nw;
+  uint64_t mine = (blk0 * 32 + lane < m) ? __ldg(u_words + blk0 * 32 + lane) : 0ull;
+  for (int64_t blk = blk0; blk * 32 < m; blk += blk_step) {
+    const uint64_t u_cur = mine & kmask;
+    const int64_t nxt = blk + blk_step;
+    mine = (nxt * 32 + lane < m) ? __ldg(u_words + nxt * 32 + lane) : 0ull;
+    const uint64_t list = pack_selection(u_cur);
+    const uint32_t list_lo = (uint32_t)list, list_hi = (uint32_t)(list >> 32);
+    const int nrows = (m - blk * 32) < 32 ? (int)(m - blk * 32) : 32;
+    ulonglong2* out = reinterpret_cast<ulonglong2*>(pd + blk * 32 * words) + pair0;
+    for (int r = 0; r < nrows; ++r, out += pairs) {
+      const uint32_t lo = __shfl_sync(0xffffffffu, list_lo, r);
+      const uint32_t hi = __shfl_sync(0xffffffffu, list_hi, r);
+      const int cnt = (int)(hi >> 24);
+      for (int c = 0; c < panel_chunks; ++c) {
+        const int slot0 = c * CH_PAIRS + lane;
+        if (c * CH_PAIRS >= valid_pairs) break;
+        ulonglong2 d[4];
+        if (cnt == 0) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) d[u] = make_ulonglong2(0ull, 0ull);
+        } else if (cnt <= 7) {
+          panel_or_list(Vs, panel_pairs, lo, hi, cnt, slot0, d);
+        } else {
+          const uint64_t sel = ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(u_cur >> 32), r) << 32) |
+                               __shfl_sync(0xffffffffu, (uint32_t)u_cur, r);
+          panel_or_fast(Vs, panel_pairs, sel, slot0, d);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (slot0 + 32 * u < valid_pairs) {
+            ulonglong2* dst = out + slot0 + 32 * u;
+            if (store_mode == 0) __stcs(dst, d[u]);
+            else if (store_mode == 1) *dst = d[u];
+            else __stwt(dst, d[u]);
+          }
+        }
+      }
+    }
+  }
+}
+
 // panel geometry for k <= 64 rows of V^T: chunks (of 256 words) per panel; 0 = use the row-stream kernels
 constexpr int PANEL_SMEM_BUDGET = 224 * 1024;
 static inline int panel_chunks_for(int64_t k, int64_t kw, int64_t words) {
@@ -1262,7 +1566,7 @@ static inline int confusion_ring_depth(int64_t k, int chunks) {
   return (int)depth;
 }
 static inline size_t confusion_panel_smem(int64_t k, int chunks, int depth) {
-  return (size_t)(k + PANEL_WARPS * depth) * chunks * CH_PAIRS * 16 + PANEL_WARPS * RING_DEPTH_MAX * 8;
+  return (size_t)(k + PANEL_WARPS * depth) * chunks * CH_PAIRS * 16 + PANEL_WARPS * RING_DEPTH_MAX * 8 + 64 * sizeof(int);
 }
 // equal-width panels, one wave of CTAs (<= #SM); BMF_PANEL_BALANCE=0 restores full-width panels + a narrow last one
 static inline PanelGrid make_panel_grid(int64_t pairs, int panel_pairs, int64_t max_splits, int* total_ctas) {
@@ -1285,13 +1589,17 @@ static inline int panel_rowmap() {              // BMF_PANEL_ROWMAP=1 selects th
 }
 static inline int confusion_count_mode() {      // BMF_CONFUSION_COUNT = 0 (tree / tree), 1 (tree / POPC), 2 (POPC / POPC)
   const char* e = getenv("BMF_CONFUSION_COUNT");
-  if (e != nullptr && e[0] >= '0' && e[0] <= '2') return e[0] - '0';
+  if (e != nullptr && e[0] >= '0' && e[0] <= '3') return e[0] - '0';   // 3 (list kernel only): half tree, half POPC for |gt & pd|
   return 1;                                     // measured best (profiles/r02_c5_knob_sweep.log)
 }
 static inline int product_store_mode() {        // BMF_PRODUCT_STORE = 0 (st.cs, evict first), 1 (plain st), 2 (st.wt)
   const char* e = getenv("BMF_PRODUCT_STORE");
   if (e != nullptr && e[0] >= '0' && e[0] <= '2') return e[0] - '0';
   return 0;
+}
+static inline bool panel_lists() {              // BMF_PANEL_LIST=0: the bit-scan forms of the panel kernels (A/B experiments)
+  const char* e = getenv("BMF_PANEL_LIST");
+  return !(e != nullptr && e[0] == '0');
 }
 static inline bool panel_disabled() {
   const char* e = getenv("BMF_NO_PANEL");
@@ -1920,9 +2228,17 @@ extern "C" int bmf_bool_product(const uint64_t* u_words, int64_t m, int64_t kw, 
     int rc = check_cuda(cudaFuncSetAttribute(bool_product_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem), "bmf_bool_product");
     if (rc) return rc;
-    bool_product_panel_kernel<<<ctas, PRODUCT_THREADS, smem, as_stream(stream)>>>(u_words, m, vt_bits, k, words, chunks,
-                                                                                panel_rowmap(), product_store_mode(), pg,
-                                                                                pd_bits);
+    if (panel_lists() && panel_rowmap() == 0) {
+      rc = check_cuda(cudaFuncSetAttribute(bool_product_panel_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem), "bmf_bool_product");
+      if (rc) return rc;
+      bool_product_panel_list_kernel<<<ctas, PRODUCT_THREADS, smem, as_stream(stream)>>>(u_words, m, vt_bits, k, words, chunks,
+                                                                                       product_store_mode(), pg, pd_bits);
+    } else {
+      bool_product_panel_kernel<<<ctas, PRODUCT_THREADS, smem, as_stream(stream)>>>(u_words, m, vt_bits, k, words, chunks,
+                                                                                  panel_rowmap(), product_store_mode(), pg,
+                                                                                  pd_bits);
+    }
     BMF_LAUNCH_CHECK("bmf_bool_product");
     return 0;
   }
@@ -1958,12 +2274,29 @@ static int launch_confusion(const uint64_t* gt_bits, const uint64_t* pd_bits, in
     confusion_panel_kernel<CG, MD><<<ctas, PANEL_THREADS, smem, st>>>(gt_bits, m, words, u_words, vt_bits, k, chunks,  \
                                                                       depth, pg, c);                                 \
   } while (0)
-      if (gt_ones >= 0) {
+#define BMF_CONF_LIST_LAUNCH(CG, MD)                                                                                      \
+  do {                                                                                                                    \
+    rc = check_cuda(cudaFuncSetAttribute(confusion_panel_list_kernel<CG, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem), who);                                                                \
+    if (rc) return rc;                                                                                                    \
+    confusion_panel_list_kernel<CG, MD><<<ctas, PANEL_THREADS, smem, st>>>(gt_bits, m, words, u_words, vt_bits, k, chunks,  \
+                                                                           depth, pg, c);                                 \
+  } while (0)
+      if (panel_lists()) {
+        if (gt_ones >= 0) {
+          if (mode == 0) BMF_CONF_LIST_LAUNCH(false, 0); else if (mode == 1) BMF_CONF_LIST_LAUNCH(false, 1);
+          else if (mode == 2) BMF_CONF_LIST_LAUNCH(false, 2); else BMF_CONF_LIST_LAUNCH(false, 3);
+        } else {
+          if (mode == 0) BMF_CONF_LIST_LAUNCH(true, 0); else if (mode == 1) BMF_CONF_LIST_LAUNCH(true, 1);
+          else if (mode == 2) BMF_CONF_LIST_LAUNCH(true, 2); else BMF_CONF_LIST_LAUNCH(true, 3);
+        }
+      } else if (gt_ones >= 0) {
         if (mode == 0) BMF_CONF_LAUNCH(false, 0); else if (mode == 1) BMF_CONF_LAUNCH(false, 1); else BMF_CONF_LAUNCH(false, 2);
       } else {
         if (mode == 0) BMF_CONF_LAUNCH(true, 0); else if (mode == 1) BMF_CONF_LAUNCH(true, 1); else BMF_CONF_LAUNCH(true, 2);
       }
 #undef BMF_CONF_LAUNCH
+#undef BMF_CONF_LIST_LAUNCH
       rc = check_cuda(cudaGetLastError(), who);
       if (rc) return rc;
       confusion_finalize_kernel<<<1, 1, 0, st>>>(reinterpret_cast<long long*>(counts), (long long)gt_ones);

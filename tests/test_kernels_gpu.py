@@ -563,6 +563,41 @@ def test_panel_kernels_match_row_stream_kernels(nat, m, n, k, monkeypatch):
     assert list(out["panel"][1]) == [int(tp), int(fp), int(fn)]
 
 
+@pytest.mark.parametrize("density", [0.02, 0.07, 0.11, 0.3])
+@pytest.mark.parametrize("k", [64, 37, 20])
+def test_panel_selection_lists_and_count_modes(nat, density, k, monkeypatch):
+    """selection-list panel kernels (<= 7 factors per row: straight-line ORs; more: the bit-scan path; one factor:
+    |prediction| from the per-panel row counts; none: the row is skipped) in every count mode, and the bit-scan
+    forms (BMF_PANEL_LIST=0), against numpy.  k = 20 takes the two-chunk panel."""
+    _native, device = nat
+    m, n = 1501, 20010
+    rng = np.random.RandomState(int(density * 1000) + k)
+    U = _rand01(rng, m, k, density)
+    U[5] = 0
+    U[6] = 0; U[6, k - 1] = 1
+    U[7] = 1
+    V = _rand01(rng, n, k, 0.05)
+    G = _rand01(rng, m, n, 0.1)
+    uw_h = np.ascontiguousarray(device.dense_to_words(U, words=1))
+    want = O.bool_product(U, V)
+    tp, fp, fn = (int(v) for v in O.confusion(G, want))
+    vt = _dev(device.dense_to_words(V.T))
+    gt = _dev(device.dense_to_words(G))
+    words = device.words_for(n)
+    uw = _dev(uw_h)
+    for lists in ("1", "0"):
+        monkeypatch.setenv("BMF_PANEL_LIST", lists)
+        pd = device.zeros((m, words), torch.int64) - 1
+        _native.call("bmf_bool_product", uw, m, 1, vt, k, words, pd)
+        assert np.array_equal(device.bits_to_host(pd, n), want)
+        for mode in ("0", "1", "2", "3"):
+            monkeypatch.setenv("BMF_CONFUSION_COUNT", mode)
+            for known in (-1, tp + fn):
+                c = device.zeros((3,), torch.int64) + 7
+                _native.call("bmf_confusion_factors", gt, m, words, uw, 1, vt, k, known, c, None, None)
+                assert [int(v) for v in c.cpu().numpy()] == [tp, fp, fn], (lists, mode, known)
+
+
 def test_c5_scale_panel_kernels_properties(nat, monkeypatch):
     """BASELINE configs[4] scale (200k x 100k bits, k = 64; the 1M-row point runs in bench.py --workload c5 with the same
     checks): the column-panel kernels equal the row-stream kernels bit for bit, the two confusion forms agree, and
