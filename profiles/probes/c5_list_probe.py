@@ -57,13 +57,14 @@ def timed(fn):
 
 print("usage density 2^-%d per bit, reference counts %s" % (ands, ref), flush=True)
 pd2 = device.zeros((m, words), torch.int64)
-for lst in ("0", "1"):
+for lst, dyn in (("0", "1"), ("1", "0"), ("1", "1")):
     os.environ["BMF_PANEL_LIST"] = lst
+    os.environ["BMF_PANEL_DYNAMIC"] = dyn
     pd2.fill_(-1)
     ms = timed(lambda: _native.call("bmf_bool_product", uw, m, 1, vt, k, words, pd2))
-    print("product   list=%s          %.3f ms  %.2f TB/s  equal=%s" % (lst, ms, bytes_one / ms / 1e9, bool(torch.equal(pd, pd2))), flush=True)
+    print("product   list=%s dynamic=%s %.3f ms  %.2f TB/s  equal=%s" % (lst, dyn, ms, bytes_one / ms / 1e9, bool(torch.equal(pd, pd2))), flush=True)
     for mode in ("0", "1", "2", "3"):
-        if lst == "0" and mode == "3":
+        if (lst == "0" and mode == "3") or (lst, dyn) == ("1", "0"):
             continue
         os.environ["BMF_CONFUSION_COUNT"] = mode
         for known in (ones, -1):

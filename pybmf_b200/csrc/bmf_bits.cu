@@ -4,6 +4,10 @@
 // pipe (POPC); rows are 16-byte aligned so every row stream uses 128-bit loads.
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "bmf_common.cuh"
 
 namespace bmf {
@@ -1492,10 +1496,16 @@ confusion_panel_list_kernel(const uint64_t* __restrict__ gt, int64_t m, int64_t 
   }
 }
 
+// DYNAMIC: the warps of all CTAs of a column panel draw their 32-row blocks from one counter (sched[panel], zero at launch)
+// instead of owning every (#warps)-th block.  ncu on the static form: the CTAs do equal work but live 3.6 M cycles on
+// average out of 4.3 M elapsed -- SMs drain their stores at different rates, and the early finishers idle for a sixth of
+// the kernel.  The counter is read two blocks ahead (atomic for block i+2 and the usage words of block i+1 are in flight
+// while block i is written), so its latency is never waited for.
+template <bool DYNAMIC>
 __global__ void __launch_bounds__(PRODUCT_THREADS, 1)
 bool_product_panel_list_kernel(const uint64_t* __restrict__ u_words, int64_t m, const uint64_t* __restrict__ vt,
                                int64_t k, int64_t words, int panel_chunks, int store_mode, const PanelGrid pg,
-                               uint64_t* __restrict__ pd) {
+                               unsigned int* __restrict__ sched, uint64_t* __restrict__ pd) {
   extern __shared__ __align__(128) uint8_t panel_smem[];
   ulonglong2* Vs = reinterpret_cast<ulonglong2*>(panel_smem);
   const int panel_pairs = panel_chunks * CH_PAIRS;
@@ -1508,11 +1518,22 @@ bool_product_panel_list_kernel(const uint64_t* __restrict__ u_words, int64_t m, 
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const uint64_t kmask = k >= 64 ? ~0ull : ((1ull << k) - 1ull);
-  const int64_t blk0 = (int64_t)pg_split * nw + warp, blk_step = (int64_t)pg_nsplit * nw;
-  uint64_t mine = (blk0 * 32 + lane < m) ? __ldg(u_words + blk0 * 32 + lane) : 0ull;
-  for (int64_t blk = blk0; blk * 32 < m; blk += blk_step) {
+  const int64_t blk_step = (int64_t)pg_nsplit * nw;
+  int64_t blk = (int64_t)pg_split * nw + warp;
+  unsigned int ahead = 0;                                          // lane 0: the block after next
+  if (DYNAMIC) {
+    unsigned int first = 0;
+    if (lane == 0) { first = atomicAdd(sched + pg_panel, 1u); ahead = atomicAdd(sched + pg_panel, 1u); }
+    blk = (int64_t)__shfl_sync(0xffffffffu, first, 0);
+  }
+  uint64_t mine = (blk * 32 + lane < m) ? __ldg(u_words + blk * 32 + lane) : 0ull;
+  while (blk * 32 < m) {
     const uint64_t u_cur = mine & kmask;
-    const int64_t nxt = blk + blk_step;
+    int64_t nxt = blk + blk_step;
+    if (DYNAMIC) {
+      nxt = (int64_t)__shfl_sync(0xffffffffu, ahead, 0);
+      if (lane == 0) ahead = atomicAdd(sched + pg_panel, 1u);
+    }
     mine = (nxt * 32 + lane < m) ? __ldg(u_words + nxt * 32 + lane) : 0ull;
     const uint64_t list = pack_selection(u_cur);
     const uint32_t list_lo = (uint32_t)list, list_hi = (uint32_t)(list >> 32);
@@ -1547,7 +1568,24 @@ bool_product_panel_list_kernel(const uint64_t* __restrict__ u_words, int64_t m, 
         }
       }
     }
+    blk = nxt;
   }
+}
+
+// One zeroed counter block per (device, stream) for the dynamically scheduled kernels: launches on a stream are ordered,
+// so the memset that precedes each launch cannot race with the previous launch's atomics.
+static unsigned int* stream_counters(cudaStream_t st) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, unsigned int*> table;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = table.find({dev, st});
+  if (it != table.end()) return it->second;
+  unsigned int* p = nullptr;
+  if (cudaMalloc(&p, 64 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+  table[{dev, st}] = p;
+  return p;
 }
 
 // panel geometry for k <= 64 rows of V^T: chunks (of 256 words) per panel; 0 = use the row-stream kernels
@@ -1587,18 +1625,22 @@ static inline int panel_rowmap() {              // BMF_PANEL_ROWMAP=1 selects th
   const char* e = getenv("BMF_PANEL_ROWMAP");
   return (e != nullptr && e[0] == '1') ? 1 : 0;
 }
+static inline bool panel_lists() {              // BMF_PANEL_LIST=0: the bit-scan forms of the panel kernels (A/B experiments)
+  const char* e = getenv("BMF_PANEL_LIST");
+  return !(e != nullptr && e[0] == '0');
+}
 static inline int confusion_count_mode() {      // BMF_CONFUSION_COUNT = 0 (tree / tree), 1 (tree / POPC), 2 (POPC / POPC)
   const char* e = getenv("BMF_CONFUSION_COUNT");
   if (e != nullptr && e[0] >= '0' && e[0] <= '3') return e[0] - '0';   // 3 (list kernel only): half tree, half POPC for |gt & pd|
-  return 1;                                     // measured best (profiles/r02_c5_knob_sweep.log)
+  return panel_lists() ? 3 : 1;                 // measured best (profiles/r02z_c5_list_probe.log; bit-scan form: r02_c5_knob_sweep.log)
 }
 static inline int product_store_mode() {        // BMF_PRODUCT_STORE = 0 (st.cs, evict first), 1 (plain st), 2 (st.wt)
   const char* e = getenv("BMF_PRODUCT_STORE");
   if (e != nullptr && e[0] >= '0' && e[0] <= '2') return e[0] - '0';
   return 0;
 }
-static inline bool panel_lists() {              // BMF_PANEL_LIST=0: the bit-scan forms of the panel kernels (A/B experiments)
-  const char* e = getenv("BMF_PANEL_LIST");
+static inline bool panel_dynamic() {            // BMF_PANEL_DYNAMIC=0: static row split of the product kernel (A/B experiments)
+  const char* e = getenv("BMF_PANEL_DYNAMIC");
   return !(e != nullptr && e[0] == '0');
 }
 static inline bool panel_disabled() {
@@ -2229,11 +2271,22 @@ extern "C" int bmf_bool_product(const uint64_t* u_words, int64_t m, int64_t kw, 
                                              (int)smem), "bmf_bool_product");
     if (rc) return rc;
     if (panel_lists() && panel_rowmap() == 0) {
-      rc = check_cuda(cudaFuncSetAttribute(bool_product_panel_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem), "bmf_bool_product");
-      if (rc) return rc;
-      bool_product_panel_list_kernel<<<ctas, PRODUCT_THREADS, smem, as_stream(stream)>>>(u_words, m, vt_bits, k, words, chunks,
-                                                                                       product_store_mode(), pg, pd_bits);
+      unsigned int* sched = (panel_dynamic() && pg.panels <= 64 && m < (1ll << 36)) ? stream_counters(as_stream(stream)) : nullptr;
+      if (sched != nullptr) {
+        rc = check_cuda(cudaMemsetAsync(sched, 0, 64 * sizeof(unsigned int), as_stream(stream)), "bmf_bool_product");
+        if (rc) return rc;
+        rc = check_cuda(cudaFuncSetAttribute(bool_product_panel_list_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem), "bmf_bool_product");
+        if (rc) return rc;
+        bool_product_panel_list_kernel<true><<<ctas, PRODUCT_THREADS, smem, as_stream(stream)>>>(
+            u_words, m, vt_bits, k, words, chunks, product_store_mode(), pg, sched, pd_bits);
+      } else {
+        rc = check_cuda(cudaFuncSetAttribute(bool_product_panel_list_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem), "bmf_bool_product");
+        if (rc) return rc;
+        bool_product_panel_list_kernel<false><<<ctas, PRODUCT_THREADS, smem, as_stream(stream)>>>(
+            u_words, m, vt_bits, k, words, chunks, product_store_mode(), pg, nullptr, pd_bits);
+      }
     } else {
       bool_product_panel_kernel<<<ctas, PRODUCT_THREADS, smem, as_stream(stream)>>>(u_words, m, vt_bits, k, words, chunks,
                                                                                   panel_rowmap(), product_store_mode(), pg,

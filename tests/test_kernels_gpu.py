@@ -585,8 +585,9 @@ def test_panel_selection_lists_and_count_modes(nat, density, k, monkeypatch):
     gt = _dev(device.dense_to_words(G))
     words = device.words_for(n)
     uw = _dev(uw_h)
-    for lists in ("1", "0"):
+    for lists, dynamic in (("1", "1"), ("1", "0"), ("0", "1")):
         monkeypatch.setenv("BMF_PANEL_LIST", lists)
+        monkeypatch.setenv("BMF_PANEL_DYNAMIC", dynamic)                # row blocks drawn from a counter / static split
         pd = device.zeros((m, words), torch.int64) - 1
         _native.call("bmf_bool_product", uw, m, 1, vt, k, words, pd)
         assert np.array_equal(device.bits_to_host(pd, n), want)
