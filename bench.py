@@ -262,6 +262,18 @@ def product_sweep(points, steps, warmup, rank, world):
     return results
 
 
+def c5_traffic(last, world):
+    """DRAM bytes of one product + one confusion launch from the committed ncu capture (largest point on one GPU only)."""
+    if world != 1 or (last["m"], last["n"]) != (1_000_000, 100_000):
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            t = json.load(fh)
+        return t["c5:product:1"]["bytes"] + t["c5:confusion:1"]["bytes"]
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 C5_POINTS = [(10_000, 1_000), (100_000, 10_000), (1_000_000, 10_000), (100_000, 100_000), (1_000_000, 100_000)]
 
 
@@ -307,7 +319,12 @@ def run_product_sweep(args, rank, world, local_rank, real_stdout):
                 "config": {"workload": "Boolean product + TP/FP/FN sweep, k=64 (BASELINE configs[4]); headline = largest point",
                            "m": last["m"], "n": last["n"], "l2": "bit matrices of the large points exceed L2"},
                 "roofline": {"bound": "hbm", "achieved": value / world, "peak": hbm / world, "unit": "GB/s",
-                             "frac": value / hbm, "traffic": None, "kernel": "bool_product_panel_kernel + confusion_panel_kernel<false> (V^T panel in shared memory; TMA ring + Harley-Seal counting)",
+                             "frac": value / hbm, "traffic": c5_traffic(last, world),
+                             "traffic_unit": "bytes per step = one product + one confusion launch (profiles/ncu_traffic.json; largest point, 1 GPU)",
+                             "algorithmic_bytes_per_step": bytes_step,
+                             "kernel": "bool_product_panel_list_kernel + confusion_panel_list_kernel<false, 3> (V^T panel in shared memory; "
+                                       "packed selection lists; TMA ring; carry-save tree + POPC counting; dynamic row blocks)",
+                             "frac_product": last["product_gbs"] / hbm, "frac_confusion": last["confusion_gbs"] / hbm,
                              "peak_source": peak_src},
                 "sweep": results, "library_stream_ceilings": ceilings, "gpu_launches": 2 * args.steps * len(results),
                 "clocks": clocks,

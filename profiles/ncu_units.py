@@ -34,7 +34,9 @@ def parse(path):
 
 
 TRAFFIC_SOURCES = {
-    "c4:f4:1": ("r01d_prof_gain_f4s_raw.csv", "gemm_f4s_2sm_kernel<EPI_GAIN>, 480189 x 17770"),
+    "c4:f4:1": ("r02_prof_gain_f4s_raw.csv", "gemm_f4s_2sm_kernel<EPI_GAIN>, 480189 x 17770, full pass = first launch of the capture"),
+    "c5:product:1": ("r02za_prof_c5_raw.csv", "bool_product_panel_list_kernel<dynamic>, 1M x 100k, k = 64", "bool_product"),
+    "c5:confusion:1": ("r02za_prof_c5_raw.csv", "confusion_panel_list_kernel<|gt| known, count mode 3>, 1M x 100k, k = 64", "confusion"),
     "c4:i8:1": ("r01b_prof_gain_raw.csv", "gemm_i8_2sm_kernel<EPI_GAIN>"),
     "c4:pq-i8:1": ("r01b_prof_gain2_raw.csv", "gemm_i8_2sm_kernel<EPI_GAIN2>, w_fp = 0.2"),
     "c4:pq-f4:1": ("r01e_prof_gain2_f4_raw.csv", "gemm_f4_2sm_kernel<EPI_GAIN2>, w_fp = 0.2"),
@@ -47,11 +49,13 @@ def rebuild_traffic(extra=None):
                          "roofline.traffic (workload:kernel-variant:gpus)"}
     src = dict(TRAFFIC_SOURCES)
     src.update(extra or {})
-    for key, (fn, what) in src.items():
+    for key, spec in src.items():
+        fn, what = spec[0], spec[1]
+        name = spec[2] if len(spec) > 2 else ""                 # substring of the kernel name when a capture holds several
         path = os.path.join(HERE, fn)
         if not os.path.exists(path):
             continue
-        rec = [r for r in parse(path) if r.get("dram_read_bytes") is not None][0]
+        rec = [r for r in parse(path) if r.get("dram_read_bytes") is not None and name in r["kernel"]][0]
         table[key] = {"bytes": rec["dram_read_bytes"] + rec["dram_write_bytes"],
                       "read_bytes": rec["dram_read_bytes"], "write_bytes": rec["dram_write_bytes"],
                       "kernel_seconds_under_ncu": rec.get("seconds"),
