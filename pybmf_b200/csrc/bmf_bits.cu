@@ -610,6 +610,150 @@ struct ApplyExtra {
   int32_t* comp_fp_new;
 };
 
+// The update of ONE data row that uses the winner (warp-collective; P / N = the row's new true / false positives, tpo / fpo
+// its counters before): usage bit, cover OR, counters, the operand-plane patch and the compacted before / after rows.
+__device__ __forceinline__ void apply_used_row(const uint64_t* __restrict__ xb, uint64_t* __restrict__ cb, int64_t n, int64_t words,
+                                               const uint64_t* __restrict__ b, int32_t* __restrict__ tp_old,
+                                               int32_t* __restrict__ fp_old, int8_t* __restrict__ rows_plane, int64_t ld,
+                                               int covered_value, int pq_layout, unsigned long long* __restrict__ u_bits,
+                                               const ApplyExtra& ex, int64_t i, int lane, int P, int N, int tpo, int fpo,
+                                               long long& t_used, long long& t_p, long long& t_n) {
+  const int64_t pairs = words >> 1;
+  int64_t slot = -1;
+  if (ex.comp_kind) {
+    int s0 = 0;
+    if (lane == 0) s0 = atomicAdd(ex.nused, 1);
+    s0 = __shfl_sync(0xffffffffu, s0, 0);
+    slot = s0 < ex.comp_cap ? s0 : -1;                                // capacity = all rows: never exceeded
+  }
+  for (int64_t p = lane; p < pairs; p += 32) {
+    ulonglong2* cp = reinterpret_cast<ulonglong2*>(cb + i * words + 2 * p);
+    ulonglong2 c = *cp;
+    const ulonglong2 v = ld_words2(b + 2 * p);
+    if (slot >= 0) {                                                  // this row before / after the update
+      const ulonglong2 x = ld_words2(xb + i * words + 2 * p);
+      const uint64_t xw[2] = {x.x, x.y}, cw[2] = {c.x, c.y}, nw[2] = {c.x | v.x, c.y | v.y};
+      const int kind = ex.comp_kind;
+      // plane row of this slot (P row for the P/Q layouts; the Q row sits q_off rows further)
+      const int64_t prow = kind == 3 ? (slot / 120) * 240 + slot % 120 : (kind == 4 ? (slot >> 7) * 256 + (slot & 127) : slot);
+      const int64_t q_off = (kind == 3 ? 120 : 128) * ex.comp_ld;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int64_t col0 = (2 * p + h) * 64;
+        const int64_t left = n - col0;
+        const uint64_t valid = left >= 64 ? ~0ull : (left <= 0 ? 0ull : ((1ull << left) - 1ull));
+        if (kind == 1 || kind == 3) {                                 // 64 bits -> 32 bytes of packed E2M1
+          uint4* o = reinterpret_cast<uint4*>(ex.comp_old + prow * ex.comp_ld + (2 * p + h) * 32);
+          uint4* q = reinterpret_cast<uint4*>(ex.comp_new + prow * ex.comp_ld + (2 * p + h) * 32);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const uint32_t x32 = (uint32_t)(xw[h] >> (32 * g)), vd = (uint32_t)(valid >> (32 * g));
+            const uint32_t c32 = (uint32_t)(cw[h] >> (32 * g)), n32 = (uint32_t)(nw[h] >> (32 * g));
+            if (kind == 1) {
+              o[g] = f4_codes32(x32, c32, vd, ex.v_one, ex.v_zero, ex.v_cov);
+              q[g] = f4_codes32(x32, n32, vd, ex.v_one, ex.v_zero, ex.v_cov);
+            } else {                                                  // P = x & ~c and Q = c as E2M1 1.0 (code 2)
+              o[g] = f4_codes32(x32 & ~c32, 0u, vd, 2u, 0u, 0u);
+              q[g] = f4_codes32(x32 & ~n32, 0u, vd, 2u, 0u, 0u);
+              reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(o) + q_off)[g] = f4_codes32(c32, 0u, vd, 2u, 0u, 0u);
+              reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(q) + q_off)[g] = f4_codes32(n32, 0u, vd, 2u, 0u, 0u);
+            }
+          }
+        } else {                                                      // 64 bits -> 64 int8
+          uint4* o = reinterpret_cast<uint4*>(ex.comp_old + prow * ex.comp_ld + (2 * p + h) * 64);
+          uint4* q = reinterpret_cast<uint4*>(ex.comp_new + prow * ex.comp_ld + (2 * p + h) * 64);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t x16 = (uint32_t)(xw[h] >> (16 * g)) & 0xffffu, vd = (uint32_t)(valid >> (16 * g)) & 0xffffu;
+            const uint32_t c16 = (uint32_t)(cw[h] >> (16 * g)) & 0xffffu, n16 = (uint32_t)(nw[h] >> (16 * g)) & 0xffffu;
+            if (kind == 2) {
+              o[g] = i8_bytes16(x16, c16, vd, ex.v_one, ex.v_zero, ex.v_cov);
+              q[g] = i8_bytes16(x16, n16, vd, ex.v_one, ex.v_zero, ex.v_cov);
+            } else {
+              o[g] = i8_bytes16(x16 & ~c16, 0u, vd, 1, 0, 0);
+              q[g] = i8_bytes16(x16 & ~n16, 0u, vd, 1, 0, 0);
+              reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(o) + q_off)[g] = i8_bytes16(c16, 0u, vd, 1, 0, 0);
+              reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(q) + q_off)[g] = i8_bytes16(n16, 0u, vd, 1, 0, 0);
+            }
+          }
+        }
+      }
+    }
+    if (rows_plane != nullptr) {
+      uint64_t s0 = v.x & ~c.x, s1 = v.y & ~c.y;                      // newly covered columns
+      if (!pq_layout) {
+        int8_t* rowp = rows_plane + i * ld + p * 128;
+        while (s0) { const int k = __ffsll((long long)s0) - 1; s0 &= s0 - 1; rowp[k] = (int8_t)covered_value; }
+        while (s1) { const int k = __ffsll((long long)s1) - 1; s1 &= s1 - 1; rowp[64 + k] = (int8_t)covered_value; }
+      } else if (pq_layout == 2) {                                     // packed E2M1 plane: rewrite the nibble
+        uint8_t* rowp = reinterpret_cast<uint8_t*>(rows_plane) + i * ld + p * 64;
+        const uint32_t code = (uint32_t)covered_value & 0xFu;
+        while (s0) {
+          const int k = __ffsll((long long)s0) - 1; s0 &= s0 - 1;
+          uint8_t* bp = rowp + (k >> 1);
+          *bp = (k & 1) ? (uint8_t)((*bp & 0x0Fu) | (code << 4)) : (uint8_t)((*bp & 0xF0u) | code);
+        }
+        while (s1) {
+          const int k = __ffsll((long long)s1) - 1; s1 &= s1 - 1;
+          uint8_t* bp = rowp + 32 + (k >> 1);
+          *bp = (k & 1) ? (uint8_t)((*bp & 0x0Fu) | (code << 4)) : (uint8_t)((*bp & 0xF0u) | code);
+        }
+      } else if (pq_layout == 3) {                                     // packed E2M1 P/Q planes, blocks of 120 rows
+        uint8_t* rowp = reinterpret_cast<uint8_t*>(rows_plane) + ((i / 120) * 240 + (i % 120)) * ld + p * 64;
+        uint8_t* rowq = rowp + 120 * ld;
+        while (s0) {
+          const int k = __ffsll((long long)s0) - 1; s0 &= s0 - 1;
+          const int b = k >> 1;
+          if (k & 1) { rowp[b] &= 0x0Fu; rowq[b] = (uint8_t)((rowq[b] & 0x0Fu) | 0x20u); }
+          else       { rowp[b] &= 0xF0u; rowq[b] = (uint8_t)((rowq[b] & 0xF0u) | 0x02u); }
+        }
+        while (s1) {
+          const int k = __ffsll((long long)s1) - 1; s1 &= s1 - 1;
+          const int b = 32 + (k >> 1);
+          if (k & 1) { rowp[b] &= 0x0Fu; rowq[b] = (uint8_t)((rowq[b] & 0x0Fu) | 0x20u); }
+          else       { rowp[b] &= 0xF0u; rowq[b] = (uint8_t)((rowq[b] & 0xF0u) | 0x02u); }
+        }
+      } else {                                                         // P plane: no longer uncovered; Q plane: covered
+        int8_t* rowp = rows_plane + ((i >> 7) * 256 + (i & 127)) * ld + p * 128;
+        int8_t* rowq = rowp + 128 * ld;
+        while (s0) { const int k = __ffsll((long long)s0) - 1; s0 &= s0 - 1; rowp[k] = 0; rowq[k] = 1; }
+        while (s1) { const int k = __ffsll((long long)s1) - 1; s1 &= s1 - 1; rowp[64 + k] = 0; rowq[64 + k] = 1; }
+      }
+    }
+    c.x |= v.x;
+    c.y |= v.y;
+    *cp = c;
+  }
+  if (slot >= 0) {                                                    // K padding of the compact rows (never written above)
+    const int kind = ex.comp_kind;
+    const int64_t used_bytes = words * ((kind == 1 || kind == 3) ? 32 : 64);
+    const int64_t prow = kind == 3 ? (slot / 120) * 240 + slot % 120 : (kind == 4 ? (slot >> 7) * 256 + (slot & 127) : slot);
+    const int64_t q_off = (kind == 3 ? 120 : 128) * ex.comp_ld;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int64_t q = lane; q < ((ex.comp_ld - used_bytes) >> 4); q += 32) {
+      uint4* o = reinterpret_cast<uint4*>(ex.comp_old + prow * ex.comp_ld + used_bytes) + q;
+      uint4* w = reinterpret_cast<uint4*>(ex.comp_new + prow * ex.comp_ld + used_bytes) + q;
+      *o = z;
+      *w = z;
+      if (kind >= 3) {
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(o) + q_off) = z;
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(w) + q_off) = z;
+      }
+    }
+    if (lane == 0 && kind >= 3) {
+      ex.comp_tp_old[slot] = tpo; ex.comp_fp_old[slot] = fpo;
+      ex.comp_tp_new[slot] = tpo + P; ex.comp_fp_new[slot] = fpo + N;
+    }
+  }
+  if (lane == 0) {
+    tp_old[i] = tpo + P;
+    fp_old[i] = fpo + N;
+    atomicOr(u_bits + (i >> 6), 1ull << (i & 63));
+    if (ex.u_words != nullptr) ex.u_words[i * ex.kw + (ex.factor_bit >> 6)] |= 1ull << (ex.factor_bit & 63);
+    t_used += 1; t_p += P; t_n += N;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 cover_apply_kernel(const uint64_t* __restrict__ xb, uint64_t* __restrict__ cb, int64_t m, int64_t n,
                    int64_t words, const uint64_t* __restrict__ basis, uint8_t* __restrict__ alive,
@@ -641,139 +785,8 @@ cover_apply_kernel(const uint64_t* __restrict__ xb, uint64_t* __restrict__ cb, i
     N = warp_sum(N) - P;
     const int tpo = tp_old[i], fpo = fp_old[i];
     if (!row_uses(wa, wb, neg_w_fp, w_fn, tpo, fpo, P, N)) continue;    // warp-uniform
-    int64_t slot = -1;
-    if (ex.comp_kind) {
-      int s0 = 0;
-      if (lane == 0) s0 = atomicAdd(ex.nused, 1);
-      s0 = __shfl_sync(0xffffffffu, s0, 0);
-      slot = s0 < ex.comp_cap ? s0 : -1;                                // capacity = all rows: never exceeded
-    }
-    for (int64_t p = lane; p < pairs; p += 32) {
-      ulonglong2* cp = reinterpret_cast<ulonglong2*>(cb + i * words + 2 * p);
-      ulonglong2 c = *cp;
-      const ulonglong2 v = ld_words2(b + 2 * p);
-      if (slot >= 0) {                                                  // this row before / after the update
-        const ulonglong2 x = ld_words2(xb + i * words + 2 * p);
-        const uint64_t xw[2] = {x.x, x.y}, cw[2] = {c.x, c.y}, nw[2] = {c.x | v.x, c.y | v.y};
-        const int kind = ex.comp_kind;
-        // plane row of this slot (P row for the P/Q layouts; the Q row sits q_off rows further)
-        const int64_t prow = kind == 3 ? (slot / 120) * 240 + slot % 120 : (kind == 4 ? (slot >> 7) * 256 + (slot & 127) : slot);
-        const int64_t q_off = (kind == 3 ? 120 : 128) * ex.comp_ld;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int64_t col0 = (2 * p + h) * 64;
-          const int64_t left = n - col0;
-          const uint64_t valid = left >= 64 ? ~0ull : (left <= 0 ? 0ull : ((1ull << left) - 1ull));
-          if (kind == 1 || kind == 3) {                                 // 64 bits -> 32 bytes of packed E2M1
-            uint4* o = reinterpret_cast<uint4*>(ex.comp_old + prow * ex.comp_ld + (2 * p + h) * 32);
-            uint4* q = reinterpret_cast<uint4*>(ex.comp_new + prow * ex.comp_ld + (2 * p + h) * 32);
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              const uint32_t x32 = (uint32_t)(xw[h] >> (32 * g)), vd = (uint32_t)(valid >> (32 * g));
-              const uint32_t c32 = (uint32_t)(cw[h] >> (32 * g)), n32 = (uint32_t)(nw[h] >> (32 * g));
-              if (kind == 1) {
-                o[g] = f4_codes32(x32, c32, vd, ex.v_one, ex.v_zero, ex.v_cov);
-                q[g] = f4_codes32(x32, n32, vd, ex.v_one, ex.v_zero, ex.v_cov);
-              } else {                                                  // P = x & ~c and Q = c as E2M1 1.0 (code 2)
-                o[g] = f4_codes32(x32 & ~c32, 0u, vd, 2u, 0u, 0u);
-                q[g] = f4_codes32(x32 & ~n32, 0u, vd, 2u, 0u, 0u);
-                reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(o) + q_off)[g] = f4_codes32(c32, 0u, vd, 2u, 0u, 0u);
-                reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(q) + q_off)[g] = f4_codes32(n32, 0u, vd, 2u, 0u, 0u);
-              }
-            }
-          } else {                                                      // 64 bits -> 64 int8
-            uint4* o = reinterpret_cast<uint4*>(ex.comp_old + prow * ex.comp_ld + (2 * p + h) * 64);
-            uint4* q = reinterpret_cast<uint4*>(ex.comp_new + prow * ex.comp_ld + (2 * p + h) * 64);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint32_t x16 = (uint32_t)(xw[h] >> (16 * g)) & 0xffffu, vd = (uint32_t)(valid >> (16 * g)) & 0xffffu;
-              const uint32_t c16 = (uint32_t)(cw[h] >> (16 * g)) & 0xffffu, n16 = (uint32_t)(nw[h] >> (16 * g)) & 0xffffu;
-              if (kind == 2) {
-                o[g] = i8_bytes16(x16, c16, vd, ex.v_one, ex.v_zero, ex.v_cov);
-                q[g] = i8_bytes16(x16, n16, vd, ex.v_one, ex.v_zero, ex.v_cov);
-              } else {
-                o[g] = i8_bytes16(x16 & ~c16, 0u, vd, 1, 0, 0);
-                q[g] = i8_bytes16(x16 & ~n16, 0u, vd, 1, 0, 0);
-                reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(o) + q_off)[g] = i8_bytes16(c16, 0u, vd, 1, 0, 0);
-                reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(q) + q_off)[g] = i8_bytes16(n16, 0u, vd, 1, 0, 0);
-              }
-            }
-          }
-        }
-      }
-      if (rows_plane != nullptr) {
-        uint64_t s0 = v.x & ~c.x, s1 = v.y & ~c.y;                      // newly covered columns
-        if (!pq_layout) {
-          int8_t* rowp = rows_plane + i * ld + p * 128;
-          while (s0) { const int k = __ffsll((long long)s0) - 1; s0 &= s0 - 1; rowp[k] = (int8_t)covered_value; }
-          while (s1) { const int k = __ffsll((long long)s1) - 1; s1 &= s1 - 1; rowp[64 + k] = (int8_t)covered_value; }
-        } else if (pq_layout == 2) {                                     // packed E2M1 plane: rewrite the nibble
-          uint8_t* rowp = reinterpret_cast<uint8_t*>(rows_plane) + i * ld + p * 64;
-          const uint32_t code = (uint32_t)covered_value & 0xFu;
-          while (s0) {
-            const int k = __ffsll((long long)s0) - 1; s0 &= s0 - 1;
-            uint8_t* bp = rowp + (k >> 1);
-            *bp = (k & 1) ? (uint8_t)((*bp & 0x0Fu) | (code << 4)) : (uint8_t)((*bp & 0xF0u) | code);
-          }
-          while (s1) {
-            const int k = __ffsll((long long)s1) - 1; s1 &= s1 - 1;
-            uint8_t* bp = rowp + 32 + (k >> 1);
-            *bp = (k & 1) ? (uint8_t)((*bp & 0x0Fu) | (code << 4)) : (uint8_t)((*bp & 0xF0u) | code);
-          }
-        } else if (pq_layout == 3) {                                     // packed E2M1 P/Q planes, blocks of 120 rows
-          uint8_t* rowp = reinterpret_cast<uint8_t*>(rows_plane) + ((i / 120) * 240 + (i % 120)) * ld + p * 64;
-          uint8_t* rowq = rowp + 120 * ld;
-          while (s0) {
-            const int k = __ffsll((long long)s0) - 1; s0 &= s0 - 1;
-            const int b = k >> 1;
-            if (k & 1) { rowp[b] &= 0x0Fu; rowq[b] = (uint8_t)((rowq[b] & 0x0Fu) | 0x20u); }
-            else       { rowp[b] &= 0xF0u; rowq[b] = (uint8_t)((rowq[b] & 0xF0u) | 0x02u); }
-          }
-          while (s1) {
-            const int k = __ffsll((long long)s1) - 1; s1 &= s1 - 1;
-            const int b = 32 + (k >> 1);
-            if (k & 1) { rowp[b] &= 0x0Fu; rowq[b] = (uint8_t)((rowq[b] & 0x0Fu) | 0x20u); }
-            else       { rowp[b] &= 0xF0u; rowq[b] = (uint8_t)((rowq[b] & 0xF0u) | 0x02u); }
-          }
-        } else {                                                         // P plane: no longer uncovered; Q plane: covered
-          int8_t* rowp = rows_plane + ((i >> 7) * 256 + (i & 127)) * ld + p * 128;
-          int8_t* rowq = rowp + 128 * ld;
-          while (s0) { const int k = __ffsll((long long)s0) - 1; s0 &= s0 - 1; rowp[k] = 0; rowq[k] = 1; }
-          while (s1) { const int k = __ffsll((long long)s1) - 1; s1 &= s1 - 1; rowp[64 + k] = 0; rowq[64 + k] = 1; }
-        }
-      }
-      c.x |= v.x;
-      c.y |= v.y;
-      *cp = c;
-    }
-    if (slot >= 0) {                                                    // K padding of the compact rows (never written above)
-      const int kind = ex.comp_kind;
-      const int64_t used_bytes = words * ((kind == 1 || kind == 3) ? 32 : 64);
-      const int64_t prow = kind == 3 ? (slot / 120) * 240 + slot % 120 : (kind == 4 ? (slot >> 7) * 256 + (slot & 127) : slot);
-      const int64_t q_off = (kind == 3 ? 120 : 128) * ex.comp_ld;
-      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-      for (int64_t q = lane; q < ((ex.comp_ld - used_bytes) >> 4); q += 32) {
-        uint4* o = reinterpret_cast<uint4*>(ex.comp_old + prow * ex.comp_ld + used_bytes) + q;
-        uint4* w = reinterpret_cast<uint4*>(ex.comp_new + prow * ex.comp_ld + used_bytes) + q;
-        *o = z;
-        *w = z;
-        if (kind >= 3) {
-          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(o) + q_off) = z;
-          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(w) + q_off) = z;
-        }
-      }
-      if (lane == 0 && kind >= 3) {
-        ex.comp_tp_old[slot] = tpo; ex.comp_fp_old[slot] = fpo;
-        ex.comp_tp_new[slot] = tpo + P; ex.comp_fp_new[slot] = fpo + N;
-      }
-    }
-    if (lane == 0) {
-      tp_old[i] = tpo + P;
-      fp_old[i] = fpo + N;
-      atomicOr(u_bits + (i >> 6), 1ull << (i & 63));
-      if (ex.u_words != nullptr) ex.u_words[i * ex.kw + (ex.factor_bit >> 6)] |= 1ull << (ex.factor_bit & 63);
-      t_used += 1; t_p += P; t_n += N;
-    }
+    apply_used_row(xb, cb, n, words, b, tp_old, fp_old, rows_plane, ld, covered_value, pq_layout, u_bits, ex, i, lane, P, N,
+                   tpo, fpo, t_used, t_p, t_n);
   }
   if (lane == 0 && t_used) {
     atomicAdd(totals + 0, (unsigned long long)t_used);
@@ -781,6 +794,106 @@ cover_apply_kernel(const uint64_t* __restrict__ xb, uint64_t* __restrict__ cb, i
     atomicAdd(totals + 2, (unsigned long long)t_n);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) alive[j] = 0;               // Asso.py:106-107
+}
+
+// Ring-fed form of cover_apply_kernel.  ncu on the register-fed kernel above at 480189 x 17770: 59 % of DRAM peak,
+// 12 of 24 resident warps per scheduler waiting on global loads (80 registers cap the occupancy, a warp has two or three
+// 128-bit loads in flight per row).  Here every warp streams ITS rows -- the x row and the cover row, 2 x words x 8 bytes --
+// through a private ring of shared-memory slots filled by 1-D bulk copies (TMA engine, mbarrier complete_tx), the same
+// protocol as confusion_panel_list_kernel: depth x 16 row pairs in flight per SM at no register cost.  The winner's basis row
+// sits in shared memory.  Rows that use the winner (1-2 %) take apply_used_row, which works on global memory as before;
+// the slot is re-armed first, so the copy engine never waits for an update.
+constexpr int APPLY_RING_THREADS = 512;
+constexpr int APPLY_RING_WARPS = APPLY_RING_THREADS / 32;
+constexpr int APPLY_RING_DEPTH_MAX = 4;
+__global__ void __launch_bounds__(APPLY_RING_THREADS, 1)
+cover_apply_ring_kernel(const uint64_t* __restrict__ xb, uint64_t* __restrict__ cb, int64_t m, int64_t n,
+                        int64_t words, const uint64_t* __restrict__ basis, uint8_t* __restrict__ alive,
+                        const int64_t* __restrict__ winner, int32_t* __restrict__ tp_old,
+                        int32_t* __restrict__ fp_old, int wa, int wb, double neg_w_fp, double w_fn,
+                        int8_t* __restrict__ rows_plane, int64_t ld, int covered_value, int pq_layout,
+                        unsigned long long* __restrict__ u_bits, unsigned long long* __restrict__ totals,
+                        const ApplyExtra ex, int depth) {
+  extern __shared__ __align__(128) uint8_t apply_smem[];
+  const int64_t j = *winner;
+  if (j < 0) return;
+  const uint64_t* __restrict__ b = basis + j * words;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t pairs = words >> 1;
+  const uint32_t row_bytes = (uint32_t)(words * 8);
+  ulonglong2* bs = reinterpret_cast<ulonglong2*>(apply_smem);
+  uint8_t* ring = apply_smem + row_bytes + (size_t)warp * depth * 2 * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(apply_smem + row_bytes + (size_t)APPLY_RING_WARPS * depth * 2 * row_bytes);
+  const uint32_t bar0 = smem_u32(bars + warp * depth);
+  const uint32_t ring0 = smem_u32(ring);
+  if (lane == 0) {
+    for (int s = 0; s < depth; ++s) mbar_init(bar0 + 8u * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int64_t q = threadIdx.x; q < pairs; q += blockDim.x) bs[q] = ld_words2(b + 2 * q);
+  if (ex.vt_row != nullptr && blockIdx.x == 0)
+    for (int64_t q = threadIdx.x; q < words; q += blockDim.x) ex.vt_row[q] = b[q];
+  __syncthreads();
+
+  const int64_t gw = (int64_t)blockIdx.x * APPLY_RING_WARPS + warp;
+  const int64_t nwarps = (int64_t)gridDim.x * APPLY_RING_WARPS;
+  const int64_t my_rows = gw < m ? (m - 1 - gw) / nwarps + 1 : 0;
+  int64_t issued = 0;
+  int iss_slot = 0;
+  auto issue = [&]() {                                                 // lane 0: x row and cover row of this warp's next row
+    const int64_t i = gw + issued * nwarps;
+    const uint32_t bar = bar0 + 8u * iss_slot, dst = ring0 + (uint32_t)iss_slot * 2u * row_bytes;
+    mbar_expect_tx(bar, 2u * row_bytes);
+    bulk_load(dst, xb + i * words, row_bytes, bar);
+    bulk_load(dst + row_bytes, cb + i * words, row_bytes, bar);
+    iss_slot = iss_slot == depth - 1 ? 0 : iss_slot + 1;
+    ++issued;
+  };
+  if (lane == 0)
+    for (int d = 0; d < depth && issued < my_rows; ++d) issue();
+
+  const bool general = (wa | wb) == 0;
+  long long t_used = 0, t_p = 0, t_n = 0;
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int64_t t = 0; t < my_rows; ++t) {
+    const int64_t i = gw + t * nwarps;
+    int tpo = 0, fpo = 0;
+    if (general) { tpo = tp_old[i]; fpo = fp_old[i]; }                  // the fp64 row test needs them; in flight during the wait
+    const ulonglong2* xs = reinterpret_cast<const ulonglong2*>(ring + (size_t)slot * 2 * row_bytes);
+    const ulonglong2* cs = reinterpret_cast<const ulonglong2*>(ring + (size_t)slot * 2 * row_bytes + row_bytes);
+    mbar_wait(bar0 + 8u * slot, phase);
+    int P = 0, N = 0;
+    for (int64_t p = lane; p < pairs; p += 32) {
+      const ulonglong2 x = xs[p], c = cs[p], v = bs[p];
+      P += __popcll(x.x & ~c.x & v.x) + __popcll(x.y & ~c.y & v.y);
+      N += __popcll(~c.x & v.x) + __popcll(~c.y & v.y);                 // |v & ~c| (v has zero pad bits), minus P below
+    }
+    __syncwarp();                                                       // every lane has read the slot
+    if (lane == 0 && issued < my_rows) issue();
+    if (++slot == depth) { slot = 0; phase ^= 1u; }
+    P = warp_sum(P);
+    N = warp_sum(N) - P;
+    if (!row_uses(wa, wb, neg_w_fp, w_fn, tpo, fpo, P, N)) continue;    // warp-uniform
+    if (!general) { tpo = tp_old[i]; fpo = fp_old[i]; }
+    apply_used_row(xb, cb, n, words, b, tp_old, fp_old, rows_plane, ld, covered_value, pq_layout, u_bits, ex, i, lane, P, N,
+                   tpo, fpo, t_used, t_p, t_n);
+  }
+  if (lane == 0 && t_used) {
+    atomicAdd(totals + 0, (unsigned long long)t_used);
+    atomicAdd(totals + 1, (unsigned long long)t_p);
+    atomicAdd(totals + 2, (unsigned long long)t_n);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) alive[j] = 0;               // Asso.py:106-107
+}
+// ring slots per warp that fit next to the basis row; < 2 = use the register-fed kernel (very wide matrices)
+static inline int apply_ring_depth(int64_t words) {
+  const char* e = getenv("BMF_APPLY_RING");
+  if (e != nullptr && e[0] == '0') return 0;
+  const int64_t row_bytes = words * 8;
+  int64_t depth = (224 * 1024 - row_bytes - APPLY_RING_WARPS * APPLY_RING_DEPTH_MAX * 8) / (APPLY_RING_WARPS * 2 * row_bytes);
+  if (depth > APPLY_RING_DEPTH_MAX) depth = APPLY_RING_DEPTH_MAX;
+  return (int)depth;
 }
 
 // =========================================================================================
@@ -2085,6 +2198,21 @@ static int launch_cover_apply(const uint64_t* x_bits, uint64_t* c_bits, int64_t 
   BMF_REQUIRE(m > 0 && n > 0 && words % 2 == 0 && words * 64 >= n, "bmf_cover_apply: bad shape");
   BMF_REQUIRE(rows_plane == nullptr || (ld % 128 == 0 && ld * (pq_layout >= 2 ? 2 : 1) >= words * 64),
               "bmf_cover_apply: ld must cover words*64");
+  const int depth = apply_ring_depth(words);
+  if (depth >= 2) {
+    const size_t smem = (size_t)words * 8 + (size_t)APPLY_RING_WARPS * depth * 2 * words * 8 + APPLY_RING_WARPS * APPLY_RING_DEPTH_MAX * 8;
+    int64_t ctas = ceil_div(m, APPLY_RING_WARPS);
+    if (ctas > num_sms()) ctas = num_sms();
+    int rc = check_cuda(cudaFuncSetAttribute(cover_apply_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                        "bmf_cover_apply");
+    if (rc) return rc;
+    cover_apply_ring_kernel<<<(unsigned)ctas, APPLY_RING_THREADS, smem, as_stream(stream)>>>(
+        x_bits, c_bits, m, n, words, basis_bits, alive, winner, tp_old, fp_old, wa, wb, -w_fp, w_fn, rows_plane,
+        ld, covered_value, pq_layout, reinterpret_cast<unsigned long long*>(u_bits),
+        reinterpret_cast<unsigned long long*>(totals), ex, depth);
+    BMF_LAUNCH_CHECK("bmf_cover_apply");
+    return 0;
+  }
   int64_t blocks = ceil_div(m, 8);
   if (blocks > row_stream_grid()) blocks = row_stream_grid();
   cover_apply_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
