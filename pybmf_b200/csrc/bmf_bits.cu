@@ -68,15 +68,40 @@ __device__ __forceinline__ uint32_t spread8(uint32_t x) {
   return x;
 }
 
-// 32 data bits + 32 mask bits -> 32 E2M1 codes (16 bytes): `masked` where the mask bit is set, else `one` / `zero`
+// 16 bits -> 16 nibbles holding `code` where the bit is set (element k in byte k / 2, low nibble for even k).  The bits
+// are first spread into 2-bit groups, one per nibble; each nibble then SELECTS, through PRMT, the byte that encodes its
+// two elements: {0, code, code << 4, code | code << 4}.  Nine instructions per 16 elements; the shift-and-mask spread to
+// single nibbles followed by a multiply took 3.5x as many, which made the plane expansions instruction bound
+// (4.3 GB written at 2.3 TB/s).
+__device__ __forceinline__ uint32_t f4_pair_lut(uint32_t code) { return (code | (code << 4)) << 24 | (code << 4) << 16 | code << 8; }
+__device__ __forceinline__ void f4_spread16(uint32_t x16, uint32_t lut, uint32_t& lo, uint32_t& hi) {
+  uint32_t t = x16;
+  t = (t | (t << 8)) & 0x00FF00FFu;
+  t = (t | (t << 4)) & 0x0F0F0F0Fu;
+  t = (t | (t << 2)) & 0x33333333u;                        // bits 2j, 2j+1 -> nibble j
+  lo |= __byte_perm(lut, 0u, t);
+  hi |= __byte_perm(lut, 0u, t >> 16);
+}
+// 32 data bits + 32 mask bits -> 32 E2M1 codes (16 bytes): `masked` where the mask bit is set, else `one` / `zero`;
+// a set whose code is 0 costs nothing (the codes are launch constants, so the branches are uniform)
 __device__ __forceinline__ uint4 f4_codes32(uint32_t b32, uint32_t k32, uint32_t valid, uint32_t one, uint32_t zero,
                                             uint32_t masked) {
-  const uint32_t s_one = b32 & ~k32 & valid, s_zero = ~b32 & ~k32 & valid, s_mask = k32 & valid;
-  uint32_t out[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    out[q] = spread8((s_one >> (8 * q)) & 0xFFu) * one + spread8((s_zero >> (8 * q)) & 0xFFu) * zero +
-             spread8((s_mask >> (8 * q)) & 0xFFu) * masked;
+  uint32_t out[4] = {0u, 0u, 0u, 0u};
+  if (one) {
+    const uint32_t s = b32 & ~k32 & valid, lut = f4_pair_lut(one);
+    f4_spread16(s & 0xFFFFu, lut, out[0], out[1]);
+    f4_spread16(s >> 16, lut, out[2], out[3]);
+  }
+  if (zero) {
+    const uint32_t s = ~b32 & ~k32 & valid, lut = f4_pair_lut(zero);
+    f4_spread16(s & 0xFFFFu, lut, out[0], out[1]);
+    f4_spread16(s >> 16, lut, out[2], out[3]);
+  }
+  if (masked) {
+    const uint32_t s = k32 & valid, lut = f4_pair_lut(masked);
+    f4_spread16(s & 0xFFFFu, lut, out[0], out[1]);
+    f4_spread16(s >> 16, lut, out[2], out[3]);
+  }
   return make_uint4(out[0], out[1], out[2], out[3]);
 }
 // 16 data bits + 16 mask bits -> 16 int8 values
@@ -91,31 +116,33 @@ __device__ __forceinline__ uint4 i8_bytes16(uint32_t b16, uint32_t k16, uint32_t
   return make_uint4(out[0], out[1], out[2], out[3]);
 }
 
-// 32 bits -> 32 E2M1 codes (16 bytes) per thread, one 128-bit store; element k of a row lives in byte k/2,
-// low nibble for even k
-__global__ void expand_bits_f4_kernel(const uint64_t* __restrict__ bits, const uint64_t* __restrict__ mask,
-                                      int64_t rows, int64_t ncols, int64_t words, uint32_t one, uint32_t zero,
-                                      uint32_t masked, uint8_t* __restrict__ plane, int64_t rows_pad, int64_t ld_bytes) {
-  const int64_t chunks = ld_bytes >> 4;
-  const int64_t total = rows_pad * chunks;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = t / chunks, ch = t - r * chunks;
-    const int64_t c0 = ch << 5;
-    uint32_t out[4] = {0, 0, 0, 0};
-    if (r < rows && c0 < ncols) {
-      const int64_t w = c0 >> 6;
-      const uint32_t b32 = (w < words) ? (uint32_t)(bits[r * words + w] >> (c0 & 63)) : 0u;
-      const uint32_t k32 = (mask != nullptr && w < words) ? (uint32_t)(mask[r * words + w] >> (c0 & 63)) : 0u;
-      const int64_t left = ncols - c0;                              // valid columns in this chunk
-      const uint32_t valid = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
-      const uint32_t s_one = b32 & ~k32 & valid, s_zero = ~b32 & ~k32 & valid, s_mask = k32 & valid;
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        out[q] = spread8((s_one >> (8 * q)) & 0xFFu) * one + spread8((s_zero >> (8 * q)) & 0xFFu) * zero +
-                 spread8((s_mask >> (8 * q)) & 0xFFu) * masked;
+// One warp per plane row, one 64-bit word (32 bytes of E2M1 codes, two 128-bit stores) per lane and pass: coalesced
+// 8-byte loads, 1 KB contiguous per warp store pass, no index arithmetic beyond a pointer bump.  Element k of a row lives
+// in byte k/2, low nibble for even k; rows >= `rows` and columns >= ncols are zero.
+__global__ void __launch_bounds__(256)
+expand_bits_f4_kernel(const uint64_t* __restrict__ bits, const uint64_t* __restrict__ mask,
+                      int64_t rows, int64_t ncols, int64_t words, uint32_t one, uint32_t zero,
+                      uint32_t masked, uint8_t* __restrict__ plane, int64_t rows_pad, int64_t ld_bytes) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t slots = ld_bytes >> 5;                             // 64-element groups per plane row
+  const int64_t full = ncols >> 6;                                 // words with 64 valid columns
+  for (int64_t r = warp0; r < rows_pad; r += nwarps) {
+    uint4* dst = reinterpret_cast<uint4*>(plane + r * ld_bytes);
+    const bool live = r < rows;
+    for (int64_t w = lane; w < slots; w += 32) {
+      uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
+      if (live && w < words && w * 64 < ncols) {
+        const uint64_t b = bits[r * words + w];
+        const uint64_t k = mask != nullptr ? mask[r * words + w] : 0ull;
+        const uint64_t valid = w < full ? ~0ull : ((1ull << (ncols - w * 64)) - 1ull);
+        lo = f4_codes32((uint32_t)b, (uint32_t)k, (uint32_t)valid, one, zero, masked);
+        hi = f4_codes32((uint32_t)(b >> 32), (uint32_t)(k >> 32), (uint32_t)(valid >> 32), one, zero, masked);
+      }
+      dst[2 * w] = lo;
+      dst[2 * w + 1] = hi;
     }
-    *reinterpret_cast<uint4*>(plane + r * ld_bytes + (ch << 4)) = make_uint4(out[0], out[1], out[2], out[3]);
   }
 }
 
@@ -237,6 +264,23 @@ __global__ void __launch_bounds__(256) assoc_counts_popc_kernel(const uint64_t* 
 // Rows [row0, row0 + nrows) of the n x n matrix; cnt / basis_bits / cand_plane / alive / row_pop point at row row0
 // (multi-GPU: every rank thresholds the row block it received from the reduce-scatter).  symmetric != 0 (row0 = 0
 // only): the counts below the diagonal were never computed, cnt[i][j] is read as cnt[min][max].
+// The reference's test is `(double)c / (double)s > tau` (IEEE division, strict; Asso.py:207-212 + binarize).  Correctly
+// rounded division is monotone in c, so for a row with support s the test holds exactly for c >= c_min(s, tau): c_min is
+// found once per row with the LITERAL division around floor(tau * s), and the n^2 elements are compared as integers
+// (B200's fp64 divide is a long instruction sequence: 316 M of them were most of this kernel).  No c in [0, s] passes
+// (tau >= 1, NaN) -> s + 1; counts never exceed s.
+__device__ __forceinline__ int32_t assoc_min_count(int32_t si, double tau) {
+  if (si <= 0) return 1;
+  const double s = (double)si;
+  auto passes = [&](int32_t c) { return ((double)c / s) > tau; };
+  const double guess = tau * s;
+  int32_t c = guess >= s ? si : (guess > 0.0 ? (int32_t)guess : 0);       // NaN -> 0, walks up to s + 1 only if nothing passes
+  if (!(tau == tau)) return si + 1;
+  while (c > 0 && passes(c - 1)) --c;
+  while (c <= si && !passes(c)) ++c;
+  return c;
+}
+
 __global__ void basis_threshold_kernel(const int32_t* __restrict__ cnt, int64_t ldc, int64_t n, int64_t row0,
                                        int64_t nrows, int symmetric, double tau,
                                        uint64_t* __restrict__ basis_bits, int64_t words,
@@ -248,7 +292,7 @@ __global__ void basis_threshold_kernel(const int32_t* __restrict__ cnt, int64_t 
   for (int64_t i = warp0; i < nrows; i += nwarps) {
     const int64_t gi = row0 + i;                 // global row = diagonal column
     const int32_t si = cnt[i * ldc + gi];
-    const double s = (double)si;
+    const int32_t cmin = assoc_min_count(si, tau);
     int any = 0, pop = 0;
     for (int64_t w = 0; w < words; ++w) {       // each pass: 2 x 32 columns -> one word
       uint64_t word = 0;
@@ -258,7 +302,7 @@ __global__ void basis_threshold_kernel(const int32_t* __restrict__ cnt, int64_t 
         bool bit = false;
         if (j < n && si > 0) {
           const int32_t cij = (symmetric && j < gi) ? cnt[j * ldc + gi] : cnt[i * ldc + j];
-          bit = ((double)cij / s) > tau;                                     // IEEE division, strict >
+          bit = cij >= cmin;                                                 // <=> (double)cij / (double)si > tau
         }
         if (cand_plane != nullptr && j < ld) cand_plane[i * ld + j] = bit ? 1 : 0;
         const uint32_t bal = __ballot_sync(0xffffffffu, bit);
@@ -2360,9 +2404,8 @@ extern "C" int bmf_expand_bits_f4(const uint64_t* bits, const uint64_t* mask_bit
   BMF_REQUIRE(ld_bytes % 128 == 0 && ld_bytes * 2 >= ncols && rows_pad >= rows && rows >= 0, "bmf_expand_bits_f4: bad ld / rows_pad");
   BMF_REQUIRE(((one | zero | masked) & ~7) == 0, "bmf_expand_bits_f4: codes must be non-negative E2M1 bit patterns (0..7)");
   if (rows_pad == 0) return 0;
-  const int64_t total = rows_pad * (ld_bytes >> 4);
-  int64_t blocks = ceil_div(total, 256);
-  if (blocks > (int64_t)num_sms() * 64) blocks = (int64_t)num_sms() * 64;
+  int64_t blocks = ceil_div(rows_pad, 8);
+  if (blocks > (int64_t)num_sms() * 8) blocks = (int64_t)num_sms() * 8;
   expand_bits_f4_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(bits, mask_bits, rows, ncols, words, (uint32_t)one,
                                                                        (uint32_t)zero, (uint32_t)masked, plane, rows_pad,
                                                                        ld_bytes);
