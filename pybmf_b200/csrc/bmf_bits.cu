@@ -116,9 +116,10 @@ __device__ __forceinline__ uint4 i8_bytes16(uint32_t b16, uint32_t k16, uint32_t
   return make_uint4(out[0], out[1], out[2], out[3]);
 }
 
-// One warp per plane row, one 64-bit word (32 bytes of E2M1 codes, two 128-bit stores) per lane and pass: coalesced
-// 8-byte loads, 1 KB contiguous per warp store pass, no index arithmetic beyond a pointer bump.  Element k of a row lives
-// in byte k/2, low nibble for even k; rows >= `rows` and columns >= ncols are zero.
+// One warp per plane row, 32 elements (16 bytes of E2M1 codes, one 128-bit store) per lane and pass: a pass reads 16 bit
+// words (two lanes share one, a broadcast) and writes 512 contiguous bytes -- fully coalesced sectors; there is no index
+// arithmetic beyond a pointer bump.  Element k of a row lives in byte k/2, low nibble for even k; rows >= `rows` and
+// columns >= ncols are zero.
 __global__ void __launch_bounds__(256)
 expand_bits_f4_kernel(const uint64_t* __restrict__ bits, const uint64_t* __restrict__ mask,
                       int64_t rows, int64_t ncols, int64_t words, uint32_t one, uint32_t zero,
@@ -126,22 +127,21 @@ expand_bits_f4_kernel(const uint64_t* __restrict__ bits, const uint64_t* __restr
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  const int64_t slots = ld_bytes >> 5;                             // 64-element groups per plane row
-  const int64_t full = ncols >> 6;                                 // words with 64 valid columns
+  const int64_t pieces = ld_bytes >> 4;                            // 32-element groups per plane row
   for (int64_t r = warp0; r < rows_pad; r += nwarps) {
     uint4* dst = reinterpret_cast<uint4*>(plane + r * ld_bytes);
     const bool live = r < rows;
-    for (int64_t w = lane; w < slots; w += 32) {
-      uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
-      if (live && w < words && w * 64 < ncols) {
-        const uint64_t b = bits[r * words + w];
-        const uint64_t k = mask != nullptr ? mask[r * words + w] : 0ull;
-        const uint64_t valid = w < full ? ~0ull : ((1ull << (ncols - w * 64)) - 1ull);
-        lo = f4_codes32((uint32_t)b, (uint32_t)k, (uint32_t)valid, one, zero, masked);
-        hi = f4_codes32((uint32_t)(b >> 32), (uint32_t)(k >> 32), (uint32_t)(valid >> 32), one, zero, masked);
+    for (int64_t q = lane; q < pieces; q += 32) {
+      const int64_t w = q >> 1, c0 = q << 5;
+      uint4 out = make_uint4(0u, 0u, 0u, 0u);
+      if (live && w < words && c0 < ncols) {
+        const int sh = (int)(q & 1) * 32;
+        const uint32_t b = (uint32_t)(bits[r * words + w] >> sh);
+        const uint32_t k = mask != nullptr ? (uint32_t)(mask[r * words + w] >> sh) : 0u;
+        const int64_t left = ncols - c0;
+        out = f4_codes32(b, k, left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u), one, zero, masked);
       }
-      dst[2 * w] = lo;
-      dst[2 * w + 1] = hi;
+      dst[q] = out;
     }
   }
 }
@@ -318,6 +318,80 @@ __global__ void basis_threshold_kernel(const int32_t* __restrict__ cnt, int64_t 
       alive[i] = any ? 1 : 0;
       if (row_pop != nullptr) row_pop[i] = pop;
     }
+  }
+}
+
+// Tile form of the threshold for the UPPER-stored symmetric count matrix of one GPU (the row-per-warp kernel above reads
+// cnt[j][i] for j < i down a column: one 32-byte sector per 4 useful bytes, 1.15 ms at n = 17770).  A block takes a 64 x 64
+// tile (bi <= bj) of the stored triangle with coalesced row reads and emits BOTH words it decides: basis[i][bj] for the
+// tile's rows against their own minimal counts, and -- reading the tile transposed out of shared memory -- basis[j][bi] for
+// the tile's columns against theirs.  basis_rows_finish_kernel then counts each row (alive, |b_i|) and clears the pad words.
+constexpr int BT = 64;
+__global__ void __launch_bounds__(256)
+basis_threshold_tile_kernel(const int32_t* __restrict__ cnt, int64_t ldc, int64_t n, double tau,
+                            uint64_t* __restrict__ basis_bits, int64_t words) {
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bi > bj) return;
+  __shared__ int32_t tile[BT][BT + 1];
+  __shared__ int32_t cmin_i[BT], cmin_j[BT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i0 = (int64_t)bi * BT, j0 = (int64_t)bj * BT;
+  if (threadIdx.x < 2 * BT) {                                   // minimal counts of the tile's rows and of its columns
+    const int t = threadIdx.x & (BT - 1);
+    const int64_t g = (threadIdx.x < BT ? i0 : j0) + t;
+    const int32_t c = g < n ? assoc_min_count(cnt[g * ldc + g], tau) : 0x7fffffff;
+    if (threadIdx.x < BT) cmin_i[t] = c; else cmin_j[t] = c;
+  }
+  for (int a = warp; a < BT; a += 8) {                          // 64 rows x 256 bytes, coalesced
+    const int64_t gi = i0 + a;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t gj = j0 + h * 32 + lane;
+      tile[a][h * 32 + lane] = (gi < n && gj < n) ? cnt[gi * ldc + gj] : 0;
+    }
+  }
+  __syncthreads();
+  const bool diag = bi == bj;                                   // only a <= b is stored there: read tile[min][max]
+  for (int a = warp * 8; a < warp * 8 + 8; ++a) {
+    const int32_t need = cmin_i[a];
+    uint64_t word = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int b = h * 32 + lane;
+      const int32_t c = (diag && b < a) ? tile[b][a] : tile[a][b];
+      const bool bit = (j0 + b < n) && c >= need;
+      word |= (uint64_t)__ballot_sync(0xffffffffu, bit) << (h * 32);
+    }
+    if (lane == 0 && i0 + a < n) basis_bits[(i0 + a) * words + bj] = word;
+  }
+  if (diag) return;
+  for (int b = warp * 8; b < warp * 8 + 8; ++b) {               // the mirrored word: rows j of block bj, columns of block bi
+    const int32_t need = cmin_j[b];
+    uint64_t word = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int a = h * 32 + lane;
+      const bool bit = (i0 + a < n) && tile[a][b] >= need;
+      word |= (uint64_t)__ballot_sync(0xffffffffu, bit) << (h * 32);
+    }
+    if (lane == 0 && j0 + b < n) basis_bits[(j0 + b) * words + bi] = word;
+  }
+}
+__global__ void __launch_bounds__(256)
+basis_rows_finish_kernel(uint64_t* __restrict__ basis_bits, int64_t n, int64_t words, int64_t used_words,
+                         uint8_t* __restrict__ alive, int32_t* __restrict__ row_pop) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  int pop = 0;
+  for (int64_t w = lane; w < words; w += 32) {
+    if (w < used_words) pop += __popcll(basis_bits[i * words + w]);
+    else basis_bits[i * words + w] = 0ull;
+  }
+  pop = warp_sum(pop);
+  if (lane == 0) {
+    alive[i] = pop ? 1 : 0;
+    if (row_pop != nullptr) row_pop[i] = pop;
   }
 }
 
@@ -2183,6 +2257,17 @@ extern "C" int bmf_basis_threshold_rows(const int32_t* cnt_rows, int64_t ldc, in
   BMF_REQUIRE(words % 2 == 0 && words * 64 >= n, "bmf_basis_threshold_rows: words must be even and cover n");
   BMF_REQUIRE(!symmetric || row0 == 0, "bmf_basis_threshold_rows: the symmetric read needs the whole matrix (row0 = 0)");
   if (nrows == 0) return 0;
+  const char* e = getenv("BMF_BASIS_TILES");                    // 0: the row-per-warp kernel on the symmetric matrix (A/B)
+  const int64_t nb = ceil_div(n, BT);
+  if (symmetric && nrows == n && nb <= 65535 && !(e != nullptr && e[0] == '0')) {
+    basis_threshold_tile_kernel<<<dim3((unsigned)nb, (unsigned)nb), 256, 0, as_stream(stream)>>>(cnt_rows, ldc, n, tau,
+                                                                                               basis_rows, words);
+    BMF_LAUNCH_CHECK("bmf_basis_threshold_rows");
+    basis_rows_finish_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, as_stream(stream)>>>(basis_rows, n, words, nb, alive_rows,
+                                                                                     pop_rows);
+    BMF_LAUNCH_CHECK("bmf_basis_threshold_rows");
+    return 0;
+  }
   int64_t blocks = ceil_div(nrows, 8);
   basis_threshold_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(cnt_rows, ldc, n, row0, nrows, symmetric ? 1 : 0,
                                                                         tau, basis_rows, words, nullptr, 0, alive_rows,

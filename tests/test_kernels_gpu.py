@@ -138,6 +138,37 @@ def test_basis_threshold(nat, tau):
     assert np.array_equal(alive.cpu().numpy(), (want.sum(axis=1) != 0).astype(np.uint8))
 
 
+@pytest.mark.parametrize("tau", [-0.5, 0.0, 0.1, 1.0 / 3.0, 0.5, 0.75, 1.0, float("inf")])
+@pytest.mark.parametrize("n", [37, 150, 333])
+def test_basis_threshold_symmetric_tiles(nat, tau, n, monkeypatch):
+    """UPPER-stored X^T X (junk below the diagonal, as the symmetric association GEMM leaves it): the 64 x 64 tile kernel and
+    the row-per-warp kernel (BMF_BASIS_TILES=0), both deciding `(double)c / (double)s > tau` through the per-row minimal
+    count, against the literal numpy division -- incl. ratios that are exactly tau (columns duplicated on purpose)."""
+    _native, device = nat
+    rng = np.random.RandomState(n)
+    A = _rand01(rng, 90, n, 0.3)
+    A[:, 5] = 0                                                    # dead candidate
+    A[:, 7] = A[:, 3]                                              # ratio exactly 1.0
+    A[:45, 9] = 1; A[45:, 9] = 0; A[:, 11] = 0; A[:15, 11] = 1     # 15 / 45 = 1 / 3
+    cnt_h = O.assoc_counts(A).astype(np.int32)
+    junk = np.tril(rng.randint(-5, 1000, size=cnt_h.shape), -1).astype(np.int32)
+    n_pad = device.round_up(n, 64)
+    up = np.zeros((n_pad, n_pad), np.int32)
+    up[:n, :n] = np.triu(cnt_h) + junk
+    want = (O.build_assoc(A) > tau).astype(np.uint8)
+    words = device.words_for(n)
+    for tiles in ("1", "0"):
+        monkeypatch.setenv("BMF_BASIS_TILES", tiles)
+        bits = device.zeros((n, words), torch.int64) - 1            # every word (pad word too) must be written
+        alive = device.zeros((n,), torch.uint8) + 9
+        pop = device.zeros((n,), torch.int32) - 1
+        _native.call("bmf_basis_threshold_rows", _dev(up), n_pad, n, 0, n, 1, float(tau), bits, words, alive, pop)
+        assert np.array_equal(device.bits_to_host(bits, n), want), tiles
+        assert np.array_equal(bits.cpu().numpy(), device.dense_to_words(want)), tiles
+        assert np.array_equal(pop.cpu().numpy(), want.sum(axis=1)), tiles
+        assert np.array_equal(alive.cpu().numpy(), (want.sum(axis=1) != 0).astype(np.uint8)), tiles
+
+
 def _cover_inputs(seed, m, n, nb_density=0.25):
     rng = np.random.RandomState(seed)
     X = _rand01(rng, m, n, 0.3)
