@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) assoc_counts_popc_kernel(const uint64_t* 
 // (B200's fp64 divide is a long instruction sequence: 316 M of them were most of this kernel).  No c in [0, s] passes
 // (tau >= 1, NaN) -> s + 1; counts never exceed s.
 __device__ __forceinline__ int32_t assoc_min_count(int32_t si, double tau) {
-  if (si <= 0) return 1;
+  if (si <= 0) return 0.0 > tau ? 0 : 1;                  // empty column: the reference sets its association row to 0 (Asso.py:211)
   const double s = (double)si;
   auto passes = [&](int32_t c) { return ((double)c / s) > tau; };
   const double guess = tau * s;
@@ -300,7 +300,7 @@ __global__ void basis_threshold_kernel(const int32_t* __restrict__ cnt, int64_t 
       for (int h = 0; h < 2; ++h) {
         const int64_t j = w * 64 + h * 32 + lane;
         bool bit = false;
-        if (j < n && si > 0) {
+        if (j < n) {
           const int32_t cij = (symmetric && j < gi) ? cnt[j * ldc + gi] : cnt[i * ldc + j];
           bit = cij >= cmin;                                                 // <=> (double)cij / (double)si > tau
         }

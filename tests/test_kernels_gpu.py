@@ -114,7 +114,7 @@ def test_assoc_counts_i8_matches_popc_and_oracle(nat, m, n, gemm_variant):
     assert np.array_equal(cnt.cpu().numpy()[:n, :n].astype(np.int64), O.assoc_counts(A))
 
 
-@pytest.mark.parametrize("tau", [0.0, 0.25, 0.5, 0.99, 1.0])
+@pytest.mark.parametrize("tau", [-0.25, 0.0, 0.25, 0.5, 0.99, 1.0])
 def test_basis_threshold(nat, tau):
     _native, device = nat
     rng = np.random.RandomState(17)
