@@ -131,17 +131,24 @@ expand_bits_f4_kernel(const uint64_t* __restrict__ bits, const uint64_t* __restr
   for (int64_t r = warp0; r < rows_pad; r += nwarps) {
     uint4* dst = reinterpret_cast<uint4*>(plane + r * ld_bytes);
     const bool live = r < rows;
-    for (int64_t q = lane; q < pieces; q += 32) {
-      const int64_t w = q >> 1, c0 = q << 5;
-      uint4 out = make_uint4(0u, 0u, 0u, 0u);
-      if (live && w < words && c0 < ncols) {
-        const int sh = (int)(q & 1) * 32;
-        const uint32_t b = (uint32_t)(bits[r * words + w] >> sh);
-        const uint32_t k = mask != nullptr ? (uint32_t)(mask[r * words + w] >> sh) : 0u;
-        const int64_t left = ncols - c0;
-        out = f4_codes32(b, k, left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u), one, zero, masked);
+    for (int64_t q0 = lane; q0 < pieces; q0 += 128) {              // four pieces per lane: eight loads in flight, then the math
+      uint64_t bw[4], kw[4];
+      uint32_t valid[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t q = q0 + 32 * u, w = q >> 1, left = ncols - (q << 5);
+        const bool ok = live && q < pieces && w < words && left > 0;
+        bw[u] = ok ? bits[r * words + w] : 0ull;
+        kw[u] = (ok && mask != nullptr) ? mask[r * words + w] : 0ull;
+        valid[u] = ok ? (left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u)) : 0u;
       }
-      dst[q] = out;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t q = q0 + 32 * u;
+        if (q >= pieces) break;
+        const int sh = (int)(q & 1) * 32;
+        dst[q] = f4_codes32((uint32_t)(bw[u] >> sh), (uint32_t)(kw[u] >> sh), valid[u], one, zero, masked);
+      }
     }
   }
 }
@@ -329,7 +336,7 @@ __global__ void basis_threshold_kernel(const int32_t* __restrict__ cnt, int64_t 
 constexpr int BT = 64;
 __global__ void __launch_bounds__(256)
 basis_threshold_tile_kernel(const int32_t* __restrict__ cnt, int64_t ldc, int64_t n, double tau,
-                            uint64_t* __restrict__ basis_bits, int64_t words) {
+                            const int32_t* __restrict__ min_count, uint64_t* __restrict__ basis_bits, int64_t words) {
   const int bi = blockIdx.y, bj = blockIdx.x;
   if (bi > bj) return;
   __shared__ int32_t tile[BT][BT + 1];
@@ -339,7 +346,7 @@ basis_threshold_tile_kernel(const int32_t* __restrict__ cnt, int64_t ldc, int64_
   if (threadIdx.x < 2 * BT) {                                   // minimal counts of the tile's rows and of its columns
     const int t = threadIdx.x & (BT - 1);
     const int64_t g = (threadIdx.x < BT ? i0 : j0) + t;
-    const int32_t c = g < n ? assoc_min_count(cnt[g * ldc + g], tau) : 0x7fffffff;
+    const int32_t c = g >= n ? 0x7fffffff : (min_count != nullptr ? min_count[g] : assoc_min_count(cnt[g * ldc + g], tau));
     if (threadIdx.x < BT) cmin_i[t] = c; else cmin_j[t] = c;
   }
   for (int a = warp; a < BT; a += 8) {                          // 64 rows x 256 bytes, coalesced
@@ -376,6 +383,12 @@ basis_threshold_tile_kernel(const int32_t* __restrict__ cnt, int64_t ldc, int64_
     }
     if (lane == 0 && j0 + b < n) basis_bits[(j0 + b) * words + bi] = word;
   }
+}
+// c_min of every column, once (the fp64 divisions it takes are long sequences: 2 x 64 of them per tile were half the tile kernel)
+__global__ void assoc_min_counts_kernel(const int32_t* __restrict__ cnt, int64_t ldc, int64_t n, double tau,
+                                        int32_t* __restrict__ min_count) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) min_count[g] = assoc_min_count(cnt[g * ldc + g], tau);
 }
 __global__ void __launch_bounds__(256)
 basis_rows_finish_kernel(uint64_t* __restrict__ basis_bits, int64_t n, int64_t words, int64_t used_words,
@@ -2260,7 +2273,11 @@ extern "C" int bmf_basis_threshold_rows(const int32_t* cnt_rows, int64_t ldc, in
   const char* e = getenv("BMF_BASIS_TILES");                    // 0: the row-per-warp kernel on the symmetric matrix (A/B)
   const int64_t nb = ceil_div(n, BT);
   if (symmetric && nrows == n && nb <= 65535 && !(e != nullptr && e[0] == '0')) {
-    basis_threshold_tile_kernel<<<dim3((unsigned)nb, (unsigned)nb), 256, 0, as_stream(stream)>>>(cnt_rows, ldc, n, tau,
+    if (pop_rows != nullptr) {                                  // the |b_i| output doubles as scratch for the minimal counts
+      assoc_min_counts_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(cnt_rows, ldc, n, tau, pop_rows);
+      BMF_LAUNCH_CHECK("bmf_basis_threshold_rows");
+    }
+    basis_threshold_tile_kernel<<<dim3((unsigned)nb, (unsigned)nb), 256, 0, as_stream(stream)>>>(cnt_rows, ldc, n, tau, pop_rows,
                                                                                                basis_rows, words);
     BMF_LAUNCH_CHECK("bmf_basis_threshold_rows");
     basis_rows_finish_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, as_stream(stream)>>>(basis_rows, n, words, nb, alive_rows,

@@ -124,7 +124,10 @@ class _Stager:
     SLOTS = 4
 
     def __init__(self, threads):
+        import os
         from concurrent.futures import ThreadPoolExecutor
+        self.SLOT = int(os.environ.get("BMF_STAGE_SLOT_MB", self.SLOT >> 20)) << 20      # experiments: slot size / thread count
+        threads = int(os.environ.get("BMF_STAGE_THREADS", threads))
         self.buf = torch.empty(self.SLOT * self.SLOTS, dtype=torch.uint8, pin_memory=True)
         self.view = self.buf.numpy()
         self.events = [None] * self.SLOTS
