@@ -79,8 +79,11 @@ int bmf_gemm_i8_nt(const int8_t* a_plane, int64_t a_rows_pad, const int8_t* b_pl
 int bmf_assoc_counts_i8(const int8_t* xt_plane, int64_t n, int64_t n_pad, int64_t ld, int32_t* cnt,
                         int64_t ldc, bmf_stream_t stream);
 /* build_basis, Asso.py:216-235 + binarize, PyBMF/utils/common.py:75: bit (i,j) =
- * ((double)cnt[i][j] / (double)cnt[i][i] > tau) when cnt[i][i] > 0, else 0 (IEEE
- * division, strict >).  alive[i] = row i has any bit set (the reference drops all-zero
+ * ((double)cnt[i][j] / (double)cnt[i][i] > tau) (IEEE division, strict >); the association
+ * row of an empty column (cnt[i][i] = 0) is 0 (Asso.py:211), so its bits are (0 > tau).
+ * Evaluated as cnt[i][j] >= c_min(cnt[i][i], tau): correctly rounded division is monotone in
+ * the count, and c_min is found per column with the literal division -- the same predicate,
+ * without n^2 fp64 divisions.  alive[i] = row i has any bit set (the reference drops all-zero
  * rows but keeps order, so candidate rank = rank among alive rows).  cand_plane
  * (nullable) receives the same rows as int8 0/1, [n_pad(128)][ld]. */
 int bmf_basis_threshold(const int32_t* cnt, int64_t ldc, int64_t n, double tau, uint64_t* basis_bits,
@@ -254,7 +257,8 @@ int bmf_cover_rescore_i8_general(const int8_t* cand_plane, int64_t cand_pad, con
 /* bmf_basis_threshold on a row window [row0, row0 + nrows) (all pointers at row row0): with the rows of X sharded, every
  * rank thresholds the block of X^T X it received from the reduce-scatter and the bit rows are all-gathered.
  * symmetric != 0 (row0 = 0): entries below the diagonal were skipped by bmf_gemm_f4_nt(accumulate bit 1) and are read
- * as cnt[min(i,j)][max(i,j)]. */
+ * as cnt[min(i,j)][max(i,j)]; with nrows = n the stored triangle is walked in 64 x 64 tiles, each emitting both of the
+ * mirrored bit words (pop_rows, when given, is also used as scratch for the per-column minimal counts). */
 int bmf_basis_threshold_rows(const int32_t* cnt_rows, int64_t ldc, int64_t n, int64_t row0, int64_t nrows,
                              int32_t symmetric, double tau, uint64_t* basis_rows, int64_t words, uint8_t* alive_rows,
                              int32_t* pop_rows, bmf_stream_t stream);
