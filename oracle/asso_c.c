@@ -96,7 +96,8 @@ void bmfo_assoc_counts(const u64* xt, i64 n, i64 wm, int32_t* cnt) {
 }
 
 /* ---- build_assoc row normalisation Asso.py:208-212 + build_basis Asso.py:231-234 (binarize, common.py:75) ----
- * bit (i, j) = (double)cnt[i][j] / (double)cnt[i][i] > tau  when cnt[i][i] > 0, else 0  (IEEE division, strict >).
+ * bit (i, j) = (double)cnt[i][j] / (double)cnt[i][i] > tau (IEEE division, strict >); the association row of an empty
+ * column is 0 (`... if s[i] > 0 else 0`, Asso.py:211), so its bits are 0 > tau (set only for a negative tau).
  * alive[i] = row has any bit (all-zero rows are dropped by the reference, order kept); pop[i] = |b_i|. */
 void bmfo_basis(const int32_t* cnt, i64 n, double tau, u64* basis, i64 words, uint8_t* alive, int32_t* pop) {
 #pragma omp parallel for schedule(static)
@@ -105,10 +106,10 @@ void bmfo_basis(const int32_t* cnt, i64 n, double tau, u64* basis, i64 words, ui
     memset(row, 0, sizeof(u64) * (size_t)words);
     const int32_t si = cnt[i * n + i];
     int p = 0;
-    if (si > 0) {
-      const double s = (double)si;
-      for (i64 j = 0; j < n; ++j)
-        if ((double)cnt[i * n + j] / s > tau) { row[j >> 6] |= 1ull << (j & 63); ++p; }
+    const double s = (double)si;
+    for (i64 j = 0; j < n; ++j) {
+      const double a = si > 0 ? (double)cnt[i * n + j] / s : 0.0;
+      if (a > tau) { row[j >> 6] |= 1ull << (j & 63); ++p; }
     }
     alive[i] = p > 0;
     pop[i] = p;

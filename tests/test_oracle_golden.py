@@ -127,6 +127,24 @@ def test_c_restatement_matches_reference_outputs(name):
         assert np.array_equal(np.array([(a, int(b)) for a, b in it["trace"]]).reshape(-1, 2), g["iter_trace"])
 
 
+@pytest.mark.parametrize("tau", [-0.25, 0.0, 1.0 / 3.0, 0.5, 1.0])
+def test_c_restatement_basis_equals_numpy_restatement(tau):
+    """Candidate basis of the two restatements, incl. an empty column (its association row is 0, Asso.py:211: every bit is
+    set for a negative tau, none otherwise) and ratios exactly equal to tau."""
+    import scipy.sparse as sp
+    from oracle import asso_oracle_c as OC
+    rng = np.random.RandomState(3)
+    A = (rng.rand(90, 70) < 0.3).astype(np.uint8)
+    A[:, 5] = 0
+    A[:, 7] = A[:, 3]
+    A[:45, 9] = 1; A[45:, 9] = 0; A[:, 11] = 0; A[:15, 11] = 1     # 15 / 45 = 1 / 3
+    st = OC.BitState(sp.csr_matrix(A), tau)
+    want = (O.build_assoc(A) > tau).astype(np.uint8)
+    got = np.unpackbits(st.basis.view(np.uint8), axis=1, bitorder="little")[:, :70]
+    assert np.array_equal(got, want)
+    assert np.array_equal(st.pop, want.sum(axis=1)) and np.array_equal(st.alive, (want.sum(axis=1) != 0).astype(np.uint8))
+
+
 def test_c2_fixture_is_reproduced_and_agrees_with_numpy_restatement():
     """tests/golden/c2_digest.json (BASELINE configs[1], full size, k = 20) is what the C restatement computes today, and
     its first greedy steps equal the dense numpy restatement's (the two share no code; k = 20 was compared once when the
